@@ -1,0 +1,185 @@
+/*
+ * scalaopt_cuda.h — C ABI of libscalaopt_cuda.so
+ *
+ * B200 (sm_100a) evaluation of scalaopt's data-set objective: loss, gradient J^T r,
+ * Gauss-Newton Gram J^T J, Hessian-vector products and multi-alpha line-search scores over
+ * fp64 observations resident in HBM.  This is the drop-in boundary behind the reference's
+ * `DataSet` / `MSEFunction` / `DifferentiableObjectiveFunction` traits; the reference has no
+ * FFI of its own (it is pure Scala), so every entry point below cites the reference
+ * interface it replaces.  Paths are relative to the reference root, with
+ *   core/... = core/src/main/scala/com/github/bruneli/scalaopt/core/...
+ *
+ * Conventions
+ *   - blocking calls, `int` return: 0 = ok, <0 = one of SO_E*; message via so_last_error()
+ *   - plain pointers and sizes only; caller owns every host buffer, the library owns device
+ *     memory behind opaque handles
+ *   - a context may be used by one host thread at a time (internal mutex)
+ *   - observations: row-major X[m x f] and y[m] (scalar output), fp64, row-sharded in
+ *     contiguous blocks across the context's GPUs
+ *   - there is NO CPU fallback: every so_eval_* runs the sm_100a kernels or fails
+ */
+#ifndef SCALAOPT_CUDA_H
+#define SCALAOPT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO_ABI_VERSION 1
+
+/* error codes */
+#define SO_OK            0
+#define SO_EINVAL       -1   /* bad argument (IllegalArgumentException on the Scala side) */
+#define SO_ECUDA        -2   /* CUDA runtime / driver error */
+#define SO_ENOMEM       -3   /* device or pinned-host allocation failed */
+#define SO_ENCCL        -4   /* NCCL error */
+#define SO_EUNSUPPORTED -5   /* family / shape outside the catalogue */
+#define SO_ESTATE       -6   /* e.g. evaluating a data set that has not been filled */
+
+/*
+ * Model-family catalogue.  Arbitrary Scala closures (core/.../function/RegressionFunction.scala:24-37)
+ * cannot run on the device, so the regression function is one of these.
+ *   p = parameter vector (n doubles), x = one observation's inputs (f doubles), y scalar.
+ */
+typedef enum so_family {
+  /* y ~ p0 + sum_j p[j+1] x[j]; n = f+1.  core/src/test/.../leastsquares/LevenbergMarquardtSpec.scala:38-40 */
+  SO_FAMILY_LINEAR = 0,
+  /* y ~ sum_j p[j] x[j]; n = f (BASELINE config 4) */
+  SO_FAMILY_LINEAR_NOINT = 1,
+  /* o = 1/(1+exp(-(p0 + sum_j p[j+1] x[j]))), cross-entropy loss, y in [0,1]; n = f+1.
+   * std-apps/.../learning/nnet/{Neuron.scala:40-49, activation/LogisticFunction.scala:24-26,
+   * FFNeuralNetwork.scala:80-88,174-179, FFNeuralNetworkTrainer.scala:59-69} */
+  SO_FAMILY_LOGISTIC = 2,
+  /* y ~ p0 * exp(p1 * t); f = 1, n = 2.  LevenbergMarquardtSpec.scala:62-63 */
+  SO_FAMILY_EXPDECAY = 3,
+  /* y ~ A exp(-(t-mu)^2 / (2 sigma^2)); p = (A, mu, sigma); f = 1, n = 3 */
+  SO_FAMILY_GAUSS = 4,
+  /* y ~ A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t); p = (A, mu, sigma, B, lambda); f = 1, n = 5.
+   * functional form of std-apps/.../stats/example/ExSignalPlusBackgroundFit.scala:78-114 */
+  SO_FAMILY_GAUSS_EXPBKG = 5,
+  /* y ~ sum_k p[k] t^k; f = 1, 1 <= n <= SO_MAX_POLY_N */
+  SO_FAMILY_POLY = 6,
+  SO_FAMILY_COUNT = 7
+} so_family;
+
+#define SO_MAX_POLY_N   8      /* polynomial family: at most 8 coefficients */
+#define SO_MAX_FEATURES 512    /* linear-predictor families: f <= 512 */
+#define SO_MAX_ALPHAS   32     /* so_eval_line: k <= 32 step sizes per pass */
+
+typedef struct so_ctx so_ctx;
+typedef struct so_dataset so_dataset;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------------- */
+
+/* Single-process mode: this process drives `ngpus` devices (device_ids may be NULL = 0..ngpus-1).
+ * Replaces the SparkContext behind spark-apps/.../SparkDataSetConverter.scala:32.  With ngpus > 1 an
+ * NCCL communicator is created with ncclCommInitAll. */
+int so_init(int ngpus, const int* device_ids, so_ctx** out);
+
+/* One-process-per-GPU mode (torchrun): rank `rank` of `world` drives device `device_id`.
+ * `nccl_uid` is the SO_NCCL_UID_BYTES-byte id made by so_nccl_unique_id() on rank 0 and broadcast by the
+ * caller (any channel).  world == 1 needs no id. */
+#define SO_NCCL_UID_BYTES 128
+int so_nccl_unique_id(void* out_uid, size_t bytes);
+int so_init_rank(int device_id, int rank, int world, const void* nccl_uid, size_t uid_bytes, so_ctx** out);
+
+void so_shutdown(so_ctx* ctx);
+
+/* Message of the last failing call on `ctx` (ctx may be NULL: last so_init* failure of this thread). */
+const char* so_last_error(so_ctx* ctx);
+
+int so_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data set  —  core/.../DataSet.scala:27-145 (`trait DataSet[A]`, A = DataPoint, core/.../variable/Point.scala:29)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Reserve HBM for `m` observations of `f` inputs + 1 output.  In single-process mode m is the whole data
+ * set (sharded evenly, contiguous row blocks); in rank mode m is THIS rank's shard and the data-set size
+ * used for the 1/m normalisation is the sum over ranks. */
+int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out);
+
+/* Append `rows` observations from host memory (H2D, chunked through pinned staging when the source is
+ * pageable).  `DataSet.++` (DataSet.scala:36) / Seq -> data-set conversion (SeqDataSetConverter.scala:28). */
+int so_dataset_append(so_dataset* ds, const double* X_rowmajor, const double* y, int64_t rows);
+
+/* Fill the whole data set on the device with the synthetic observations of SURVEY.md §8d:
+ * counter-based RNG u = splitmix64(seed ^ (global_row*(f+1)+col)), inputs per `family`,
+ * y = f(p_true, x) + noise_sigma * N(0,1) (Bernoulli(o) labels for the logistic family).
+ * `row_offset` is the global index of this data set's first row (rank mode: shards of one global set). */
+int so_dataset_generate(so_dataset* ds, int family, const double* p_true, int n,
+                        uint64_t seed, double noise_sigma, int64_t row_offset);
+
+/* Copy observations [row_begin, row_begin+rows) back to the host (`DataSet.collect`, DataSet.scala:51;
+ * bounded: the caller chooses the window). Row indices are local to this process. */
+int so_dataset_read(so_dataset* ds, int64_t row_begin, int64_t rows, double* X_rowmajor, double* y);
+
+/* `DataSet.size` (DataSet.scala:126): number of observations filled so far, summed over ranks. */
+int so_dataset_size(so_dataset* ds, int64_t* m);
+
+/* `DataSet.head` (DataSet.scala:82): first observation. */
+int so_dataset_head(so_dataset* ds, double* x, double* y);
+
+/* Non-owning view of local rows [begin, end) — the data-set analogue of `filter` on the row index
+ * (DataSet.scala:60, as used by QR.scala:147).  The parent must outlive the view. */
+int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_dataset** view);
+
+void so_dataset_free(so_dataset* ds);
+
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation  —  one pass over the resident observations per call, one all-reduce of the small
+ * partial buffer when the context spans several GPUs (replaces `DataSet.aggregate`, DataSet.scala:49)
+ * ------------------------------------------------------------------------------------------- */
+
+/* K1. loss and gradient in one fused pass.
+ *   MSE families:  loss = (1/m) sum_i r_i^2/2,  r_i = |y_i - f(p, x_i)|      (MSEFunction.scala:33-36,45-48,106-108)
+ *                  grad = (1/m) sum_i r_i dr_i/dp  (analytic; replaces the n+1-pass finite difference
+ *                         of MSEFunction.scala:138-140 / linalg/DenseVector.scala:269-275)
+ *   logistic:      loss = (1/m) sum_i CE(o_i, y_i)                           (FFNeuralNetwork.scala:80-88, Trainer:59-62)
+ *                  grad = (1/m) sum_i (o_i - y_i) [1, x_i]                   (Neuron.scala:65, Trainer:64-69)
+ * grad may be NULL (loss-only pass, e.g. LevenbergMarquardt.scala:164). */
+int so_eval_loss_grad(so_dataset* ds, int family, const double* p, int n, double* loss, double* grad);
+
+/* K2. normal equations of the Jacobian/residual system that MSEFunction.jacobianAndResidualsMatrix
+ * (MSEFunction.scala:74,132-136) would materialise and QR.apply (linalg/QR.scala:131-152) would factor:
+ *   JtJ[a*n+b] = sum_i J_ia J_ib,  Jtr[a] = sum_i J_ia r_i,  rtr = sum_i r_i^2   (NOT divided by m)
+ * with J_i = dr_i/dp = -sign(y_i - f) df/dp  (the analytic limit of MSEFunction.scala:117-124).
+ * Logistic family: the reference trainer's LM convention J_i = [1, x_i], r_i = o_i - y_i
+ * (Neuron.scala:67-73, FFNeuralNetwork.scala:174-179).  loss at p = rtr/(2m) for the MSE families. */
+int so_eval_normal_eq(so_dataset* ds, int family, const double* p, int n,
+                      double* JtJ /* n*n row-major, full symmetric */, double* Jtr /* n */, double* rtr);
+
+/* K3. k step sizes scored in one pass:  phi[j] = loss(p + alpha[j] d),  dphi[j] = grad(p + alpha[j] d) . d
+ * (LineSearchPoint.fx / dfx, variable/Point.scala:54-57, as requested by linesearch/StrongWolfe.scala:96-118,214-217). */
+int so_eval_line(so_dataset* ds, int family, const double* p, const double* d, int n,
+                 const double* alpha, int k, double* phi, double* dphi);
+
+/* K4. Hessian-vector product Hd = (d/d eps) grad(p + eps d) at eps = 0, exact (analytic second
+ * derivatives), replacing the two-gradient finite difference of
+ * function/ObjectiveFunctionWithGradient.scala:41-47 consumed at gradient/NewtonCG.scala:91-96,
+ * gradient/SteihaugCG.scala:101-111 and variable/Point.scala:75. */
+int so_eval_hess_vec(so_dataset* ds, int family, const double* p, const double* d, int n, double* Hd);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-call counters (the reference has no metrics; new)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct so_call_stats {
+  int64_t rows;            /* observations streamed by the last so_eval_* (this process) */
+  int64_t bytes;           /* algorithmic HBM bytes of that pass: rows * 8 * (f+1) */
+  double  kernel_ms;       /* CUDA-event time of the evaluation kernel (max over this process's GPUs) */
+  double  device_ms;       /* kernel + all-reduce + result copy, CUDA events on the evaluation stream */
+  int64_t launches;        /* kernels launched by the last call (all GPUs of this process) */
+  int64_t total_launches;  /* kernels launched since so_init */
+  int64_t total_evals;     /* so_eval_* calls since so_init */
+} so_call_stats;
+int so_stats(so_ctx* ctx, so_call_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCALAOPT_CUDA_H */
