@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the data-set evaluation hot path (BASELINE.json).
+
+Metric: fp64 observations/s for the fused loss + J^T r + J^T J evaluation (K2, `so_eval_normal_eq`) on
+BASELINE config 3: Levenberg-Marquardt Gaussian-peak + exponential-background fit, n = 5 parameters,
+10^9 observations PER GPU (16 GB of fp64 (t, y) pairs resident in HBM; weak scaling over 1/2/4/8 B200).
+
+  python bench.py --gpus 1 --steps K --warmup W              own arm (this repo's CUDA path through the C ABI)
+  python bench.py --impl reference ...                       the reference's algorithm on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...          one rank per GPU, NCCL all-reduce per evaluation
+
+One "step" = one evaluation of (loss, J^T r, J^T J) over the whole resident data set at a fresh parameter
+vector.  `value` is timed with the observations already in HBM; `e2e` re-ingests the observations from
+pinned host memory (H2D) inside every timed step and reads the result back, through the same C ABI.
+Inputs are larger than L2 (16 GB vs 126 MB), so no L2 flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRUTH = np.array([2.0, 0.5, 0.05, 1.0, 3.0])     # (A, mu, sigma, B, lambda), SURVEY.md §8d cfg3
+NOISE = 0.05
+SEED = 12345
+METRIC = "fp64 observations/s, loss + J^T r + J^T J evaluation (LM normal equations, n=5)"
+UNIT = "observations/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="observations per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="timed steps of the e2e leg (default: min(steps, 5))")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-lm", action="store_true")
+    return ap.parse_args()
+
+
+def params_for_step(i: int) -> np.ndarray:
+    # a different, nearby parameter vector every step (what successive LM iterates look like)
+    return TRUTH * (1.1 - 0.002 * (i % 50))
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     c[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker / the reported baseline, never the product path)
+# ------------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model_name() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_single_pass(threads: int, budget_s: float = 12.0):
+    """oracle port, single-pass analytic normal equations, par[threads] — an optimistic stand-in for the
+    reference (no JVM boxing, no finite differences, no 2n+1-pass QR)."""
+    import oracle
+    fam = oracle.GAUSS_EXPBKG
+    m0 = 2_000_000
+    X, y = oracle.generate(fam, m0, 1, TRUTH, SEED, NOISE)
+    t0 = time.perf_counter()
+    oracle.normal_eq(fam, X, y, params_for_step(0), parts=threads, threads=threads)
+    rate0 = m0 / (time.perf_counter() - t0)
+    m = int(min(max(rate0 * budget_s, m0), 200_000_000))
+    if m > m0:
+        X, y = oracle.generate(fam, m, 1, TRUTH, SEED, NOISE)
+    t0 = time.perf_counter()
+    oracle.normal_eq(fam, X, y, params_for_step(1), parts=threads, threads=threads)
+    dt = time.perf_counter() - t0
+    return m / dt, m
+
+
+def reference_sample_rows(threads: int, target_s: float = 3.0) -> int:
+    import oracle
+    fam = oracle.GAUSS_EXPBKG
+    m0 = 1_000_000
+    X, y = oracle.generate(fam, m0, 1, TRUTH, SEED, NOISE)
+    t0 = time.perf_counter()
+    oracle.lm_reference_passes(fam, X, y, params_for_step(0), threads=threads)
+    rate = m0 / (time.perf_counter() - t0)
+    return int(min(max(rate * target_s, m0), 50_000_000))
+
+
+def run_reference(args):
+    """--impl reference: the reference's OWN algorithm for this evaluation — finite-difference Jacobian rows
+    (MSEFunction.scala:117-136), the 2n+1-pass Householder QR over the data set (QR.scala:131-250) and the loss
+    pass (LevenbergMarquardt.scala:164) — restated in C (oracle/oracle.c; the Scala original cannot run: no JVM
+    here or on the GPU box), partitions folded on all host threads like Spark local[N]."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = host_threads()
+    fam = oracle.GAUSS_EXPBKG
+    m = reference_sample_rows(threads)
+    X, y = oracle.generate(fam, m, 1, TRUTH, SEED, NOISE)
+    for i in range(args.warmup):
+        oracle.lm_reference_passes(fam, X, y, params_for_step(i), threads=threads)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        oracle.lm_reference_passes(fam, X, y, params_for_step(i), threads=threads)
+    dt = time.perf_counter() - t0
+    value = m * args.steps / dt
+    sample = (f"{m} observations per step (bounded sample of the 1e9-per-GPU workload), reference algorithm: "
+              f"FD Jacobian + 11-pass QR + loss pass, C restatement, {threads} threads, {cpu_model_name()}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": "BASELINE configs[2]: Levenberg-Marquardt Gaussian-peak + exponential-background fit, "
+                    "n=5 params, fp64 (t,y) observations, normal-equation evaluation (loss + J^T r + J^T J)",
+        "family": "gauss_expbkg", "n_params": 5, "rows_per_gpu": args.rows, "rows_total": args.rows * world,
+        "bytes_per_row": 16, "parallelism": f"dp{world} (row shards, one NCCL all-reduce of 21 doubles per evaluation)",
+        "l2_policy": "inputs larger than L2 (16 GB per GPU vs 126 MB), no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------
+def run_own(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from scalaopt_b200 import native
+    native.load()
+    if world > 1:
+        box = [native.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fam = native.GAUSS_EXPBKG
+    ctx = native.Context(rank=rank, world=world, device_id=local_rank, nccl_uid=uid)
+    m = args.rows
+    ds = native.Dataset(ctx, m, 1).generate(fam, TRUTH, seed=SEED, noise_sigma=NOISE, row_offset=rank * m)
+    total_rows = ds.size()
+    assert total_rows == m * world
+
+    # ---- value: observations resident in HBM ----
+    for i in range(args.warmup):
+        ds.normal_eq(fam, params_for_step(i))
+    launches0 = ctx.stats().total_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kernel_ms = device_ms = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        JtJ, Jtr, rtr = ds.normal_eq(fam, params_for_step(i))
+        st = ctx.stats()
+        kernel_ms += st.kernel_ms
+        device_ms += st.device_ms
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = ctx.stats().total_launches - launches0
+    wall_s = max_over_ranks(wall_s)
+    device_ms = max_over_ranks(device_ms)
+    kernel_ms_max = max_over_ranks(kernel_ms)
+    value = total_rows * args.steps / wall_s
+
+    # ---- LM iterations/s through the host-side mirror of LevenbergMarquardt.minimize ----
+    lm = None
+    if not args.no_lm:
+        try:
+            from scalaopt_b200 import host as sohost
+            lm = sohost.bench_lm(ctx, ds, fam, TRUTH * 1.1, barrier, max_over_ranks)
+        except Exception as e:  # the evaluation numbers stand on their own
+            lm = {"unavailable": f"{type(e).__name__}: {e}"}
+
+    # ---- e2e: host buffers, H2D of the observations + evaluation + result read-back, every step ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, native, ctx, ds, fam, m, world, barrier, max_over_ranks)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+        oracle.build()
+        threads = host_threads()
+        v, ms = cpu_single_pass(threads)
+        mref = reference_sample_rows(threads, target_s=2.0)
+        Xr, yr = oracle.generate(oracle.GAUSS_EXPBKG, mref, 1, TRUTH, SEED, NOISE)
+        t0 = time.perf_counter()
+        oracle.lm_reference_passes(oracle.GAUSS_EXPBKG, Xr, yr, params_for_step(0), threads=threads)
+        vref = mref / (time.perf_counter() - t0)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{ms} observations, single-pass analytic loss+J^T r+J^T J, oracle par[{threads}] "
+                         f"({cpu_model_name()}); the JVM/Spark reference cannot run here (no JVM)",
+               "reference_algorithm": {"value": vref, "unit": UNIT, "cores": threads,
+                                       "sample": f"{mref} observations, FD Jacobian + 11-pass QR + loss pass "
+                                                 f"(what LevenbergMarquardt.iterate does per outer iteration)"}}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6650 GB/s)"
+        alg_bytes = 16.0 * m                                   # per launch: one GPU's shard, 16 B per observation
+        ach = alg_bytes / (kernel_ms_max / args.steps * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "device_ms_per_step": device_ms / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_scalar<OpNormalEq<FamGaussExpBkg>>", "algorithmic_bytes_per_launch": alg_bytes},
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if lm is not None:
+            line["lm"] = lm
+        print(json.dumps(line), flush=True)
+    ds.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, native, ctx, ds, fam, m, world, barrier, max_over_ranks):
+    """Every timed step: so_dataset_clear + so_dataset_append from PINNED HOST buffers (H2D of all of this rank's
+    observations) + so_eval_normal_eq with the result landing in host memory."""
+    steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 5)
+    # bound the pinned allocation by what the host can spare
+    avail = 0
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail = int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    rows = m
+    if avail:
+        rows = int(min(m, max(1_000_000, (avail // (4 * world)) // 16)))
+    rows -= rows & 1
+    hx, hy = native.PinnedBuffer(rows), native.PinnedBuffer(rows)
+    # fill the host buffers with this rank's own observations (device -> host, outside the timed region)
+    CH = 1 << 26
+    for b in range(0, rows, CH):
+        e = min(rows, b + CH)
+        X, y = ds.read(b, e - b)
+        hx.array[b:e] = X[:, 0]
+        hy.array[b:e] = y
+    ds2 = ds if rows == m else native.Dataset(ctx, rows, 1)
+    xa, ya = hx.array.ctypes.data, hy.array.ctypes.data
+
+    def step(i):
+        ds2.clear()
+        ds2.append_raw(xa, ya, rows)
+        return ds2.normal_eq(fam, params_for_step(i))
+
+    step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    out = {"value": rows * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * rows * world,
+           "d2h_bytes_per_step": 21 * 8, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+           "rows_per_gpu": rows,
+           "what": "so_dataset_clear + so_dataset_append(pinned host -> HBM) + so_eval_normal_eq per step"}
+    if ds2 is not ds:
+        ds2.free()
+    hx.free(); hy.free()
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

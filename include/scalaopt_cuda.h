@@ -95,6 +95,11 @@ const char* so_last_error(so_ctx* ctx);
 
 int so_abi_version(void);
 
+/* Pinned (page-locked) host memory so that so_dataset_append runs at full PCIe speed, e.g. as the backing
+ * store of a JNI direct ByteBuffer.  Plain malloc'ed memory works too, only slower. */
+int  so_host_alloc(size_t bytes, void** out);
+void so_host_free(void* p);
+
 /* ---------------------------------------------------------------------------------------------
  * Data set  —  core/.../DataSet.scala:27-145 (`trait DataSet[A]`, A = DataPoint, core/.../variable/Point.scala:29)
  * ------------------------------------------------------------------------------------------- */
@@ -108,10 +113,14 @@ int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out);
  * pageable).  `DataSet.++` (DataSet.scala:36) / Seq -> data-set conversion (SeqDataSetConverter.scala:28). */
 int so_dataset_append(so_dataset* ds, const double* X_rowmajor, const double* y, int64_t rows);
 
+/* Forget the observations but keep the HBM reservation (re-ingest into the same data set). */
+int so_dataset_clear(so_dataset* ds);
+
 /* Fill the whole data set on the device with the synthetic observations of SURVEY.md §8d:
  * counter-based RNG u = splitmix64(seed ^ (global_row*(f+1)+col)), inputs per `family`,
  * y = f(p_true, x) + noise_sigma * N(0,1) (Bernoulli(o) labels for the logistic family).
- * `row_offset` is the global index of this data set's first row (rank mode: shards of one global set). */
+ * `row_offset` is the global index of this data set's first row (rank mode: rank r passes r*m so the ranks
+ * hold consecutive shards of one global data set of world*m rows). */
 int so_dataset_generate(so_dataset* ds, int family, const double* p_true, int n,
                         uint64_t seed, double noise_sigma, int64_t row_offset);
 

@@ -1,0 +1,654 @@
+// so_api.cu — the C ABI of libscalaopt_cuda.so (include/scalaopt_cuda.h): contexts, HBM-resident data
+// sets, the four evaluation entry points and the cross-GPU sum.
+//
+// Per evaluation and per GPU: ONE kernel launch (parameters travel in the kernel argument buffer, the
+// per-block partials are folded by the last block of the same launch), then — only when the context
+// spans several GPUs — one ncclAllReduce of the (Q+1)-double partial buffer over NVLink, then one small
+// device->pinned-host copy.  The reference does the same sum as `rdd.aggregate` on the Spark driver
+// (spark-apps/.../SparkDataSetConverter.scala:42-45).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen'ed on first multi-GPU use (see NcclApi)
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "so_internal.h"
+
+using namespace so;
+
+namespace {
+
+thread_local std::string g_init_error;
+
+// NCCL is bound at run time, not link time: a host process that also imports torch must end up with ONE
+// libnccl.so.2 (torch bundles its own), and a single-GPU context needs none at all.  Search order:
+// $SCALAOPT_NCCL_LIB, an already-loaded libnccl.so.2, then the system library.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool load() {
+    if (handle) return true;
+    const char* env = getenv("SCALAOPT_NCCL_LIB");
+    const char* names[] = { env, "libnccl.so.2", "libnccl.so" };
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+      if (handle) break;
+    }
+    if (!handle) { error = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define SO_BIND(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(handle, sym)); \
+    if (!field) { error = std::string("libnccl lacks ") + sym; handle = nullptr; return false; }
+    SO_BIND(GetUniqueId, "ncclGetUniqueId") SO_BIND(CommInitAll, "ncclCommInitAll")
+    SO_BIND(CommInitRank, "ncclCommInitRank") SO_BIND(CommDestroy, "ncclCommDestroy")
+    SO_BIND(AllReduce, "ncclAllReduce") SO_BIND(GroupStart, "ncclGroupStart") SO_BIND(GroupEnd, "ncclGroupEnd")
+    SO_BIND(GetErrorString, "ncclGetErrorString")
+#undef SO_BIND
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+bool nccl_ready(std::string* why) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.load()) return true;
+  if (why) *why = g_nccl.error;
+  return false;
+}
+
+struct Device {
+  int id = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  double* partials = nullptr; size_t partials_cap = 0;
+  double* out = nullptr;      size_t out_cap = 0;
+  double* hout = nullptr;     // pinned, out_cap doubles
+  unsigned int* ticket = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  ncclComm_t comm = nullptr;
+};
+
+}  // namespace
+
+struct so_ctx {
+  std::vector<Device> devs;
+  int rank = 0, world = 1;
+  bool rank_mode = false;
+  bool use_nccl = false;
+  std::mutex mu;
+  std::string err;
+  so_call_stats stats{};
+};
+
+struct ShardMem {
+  double* X = nullptr; double* y = nullptr;
+  int64_t cap = 0;      // rows reserved on this device
+  int64_t filled = 0;   // rows written so far
+};
+
+struct so_dataset {
+  so_ctx* ctx = nullptr;
+  int64_t m = 0;        // rows reserved in this process
+  int f = 0;
+  std::vector<ShardMem> shards;   // one per device of the context
+  bool view = false;
+  int64_t global_m = -1;          // rank mode: sum of filled rows over ranks (cached)
+};
+
+namespace {
+
+int fail(so_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (ctx) ctx->err = buf; else g_init_error = buf;
+  return code;
+}
+
+#define SO_CUDA(ctx, call)                                                                            \
+  do { cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail((ctx), e_ == cudaErrorMemoryAllocation ? SO_ENOMEM : SO_ECUDA, \
+                                       "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+#define SO_NCCL(ctx, call)                                                                            \
+  do { ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess) return fail((ctx), SO_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
+
+int setup_device(so_ctx* ctx, Device& d) {
+  SO_CUDA(ctx, cudaSetDevice(d.id));
+  cudaDeviceProp prop;
+  SO_CUDA(ctx, cudaGetDeviceProperties(&prop, d.id));
+  if (prop.major < 10) return fail(ctx, SO_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", d.id, prop.major, prop.minor);
+  d.sm_count = prop.multiProcessorCount;
+  SO_CUDA(ctx, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+  SO_CUDA(ctx, cudaEventCreate(&d.ev0));
+  SO_CUDA(ctx, cudaEventCreate(&d.ev1));
+  SO_CUDA(ctx, cudaEventCreate(&d.ev2));
+  SO_CUDA(ctx, cudaMalloc(&d.ticket, sizeof(unsigned int)));
+  SO_CUDA(ctx, cudaMemset(d.ticket, 0, sizeof(unsigned int)));
+  return SO_OK;
+}
+
+int ensure_workspace(so_ctx* ctx, Device& d, size_t partials, size_t out) {
+  SO_CUDA(ctx, cudaSetDevice(d.id));
+  if (partials > d.partials_cap) {
+    if (d.partials) cudaFree(d.partials);
+    d.partials = nullptr; d.partials_cap = 0;
+    SO_CUDA(ctx, cudaMalloc(&d.partials, partials * sizeof(double)));
+    d.partials_cap = partials;
+  }
+  if (out > d.out_cap) {
+    if (d.out) cudaFree(d.out);
+    if (d.hout) cudaFreeHost(d.hout);
+    d.out = nullptr; d.hout = nullptr; d.out_cap = 0;
+    SO_CUDA(ctx, cudaMalloc(&d.out, out * sizeof(double)));
+    SO_CUDA(ctx, cudaHostAlloc(&d.hout, out * sizeof(double), cudaHostAllocDefault));
+    d.out_cap = out;
+  }
+  return SO_OK;
+}
+
+void teardown(so_ctx* ctx) {
+  for (Device& d : ctx->devs) {
+    cudaSetDevice(d.id);
+    if (d.comm) g_nccl.CommDestroy(d.comm);
+    if (d.partials) cudaFree(d.partials);
+    if (d.out) cudaFree(d.out);
+    if (d.hout) cudaFreeHost(d.hout);
+    if (d.ticket) cudaFree(d.ticket);
+    if (d.ev0) cudaEventDestroy(d.ev0);
+    if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.ev2) cudaEventDestroy(d.ev2);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+}
+
+int check_family(so_ctx* ctx, int family, int f, int n) {
+  if (family < 0 || family >= SO_FAMILY_COUNT) return fail(ctx, SO_EINVAL, "unknown family %d", family);
+  if (family_is_scalar_t(family) && f != 1) return fail(ctx, SO_EINVAL, "family %d takes one input per observation, data set has f=%d", family, f);
+  if (family == SO_FAMILY_POLY) {
+    if (n < 1 || n > SO_MAX_POLY_N) return fail(ctx, SO_EUNSUPPORTED, "polynomial family supports 1..%d coefficients, got %d", SO_MAX_POLY_N, n);
+    return SO_OK;
+  }
+  if (f > SO_MAX_FEATURES) return fail(ctx, SO_EUNSUPPORTED, "f=%d exceeds SO_MAX_FEATURES=%d", f, SO_MAX_FEATURES);
+  const int want = family_nparams(family, f, n);
+  if (n != want) return fail(ctx, SO_EINVAL, "family %d on f=%d inputs takes n=%d parameters, got %d", family, f, want, n);
+  return SO_OK;
+}
+
+int global_rows(so_dataset* ds, int64_t* m) {
+  so_ctx* ctx = ds->ctx;
+  int64_t filled = 0;
+  for (const ShardMem& sm : ds->shards) filled += sm.filled;
+  if (ctx->rank_mode && ctx->world > 1) {
+    if (ds->global_m < 0) {
+      Device& dv = ctx->devs[0];
+      int rc = ensure_workspace(ctx, dv, 1, 2);
+      if (rc) return rc;
+      SO_CUDA(ctx, cudaSetDevice(dv.id));
+      dv.hout[1] = (double)filled;
+      SO_CUDA(ctx, cudaMemcpyAsync(dv.out, dv.hout + 1, sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+      SO_NCCL(ctx, g_nccl.AllReduce(dv.out, dv.out, 1, ncclDouble, ncclSum, dv.comm, dv.stream));
+      SO_CUDA(ctx, cudaMemcpyAsync(dv.hout, dv.out, sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+      SO_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+      ds->global_m = (int64_t)dv.hout[0];
+    }
+    *m = ds->global_m;
+  } else {
+    *m = filled;
+  }
+  return SO_OK;
+}
+
+// Run one evaluation: launch per device, sum across devices/ranks, copy the (Q+1) doubles to host.
+// On return `res` holds the summed raw sums and res[Q] the global number of rows.
+int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const double* d, int n, const double* alpha,
+             int k, int want_grad, int Q, std::vector<double>& res) {
+  so_ctx* ctx = ds->ctx;
+  const bool scalar = family_is_scalar_t(family);
+  const int G = (int)ctx->devs.size();
+  int64_t rows_local = 0, launches = 0;
+  // data.size (DataSet.scala:126) is known on the host; in rank mode it is summed over ranks once and cached
+  int64_t m_global = 0;
+  {
+    int rc0 = global_rows(ds, &m_global);
+    if (rc0) return rc0;
+    if (m_global < 1) return fail(ctx, SO_ESTATE, "data set is empty");
+  }
+  for (int g = 0; g < G; ++g) {
+    Device& dv = ctx->devs[g];
+    const ShardMem& sm = ds->shards[g];
+    const size_t need_partials = scalar ? scalar_partials_needed(kind, n, k, dv.sm_count)
+                                        : wide_partials_needed(kind, family, n, ds->f, k, dv.sm_count);
+    int rc = ensure_workspace(ctx, dv, need_partials, (size_t)Q + 2);
+    if (rc) return rc;
+    SO_CUDA(ctx, cudaSetDevice(dv.id));
+    SO_CUDA(ctx, cudaEventRecord(dv.ev0, dv.stream));
+    if (sm.filled > 0) {
+      Shard sh;
+      sh.X = sm.X; sh.y = sm.y; sh.rows = sm.filled; sh.f = ds->f;
+      sh.partials = dv.partials; sh.partials_doubles = dv.partials_cap;
+      sh.out = dv.out; sh.out_doubles = dv.out_cap; sh.ticket = dv.ticket;
+      sh.stream = dv.stream; sh.sm_count = dv.sm_count;
+      rc = scalar ? launch_scalar(kind, sh, family, p, d, n, alpha, k, want_grad)
+                  : launch_wide(kind, sh, family, p, d, n, alpha, k, want_grad);
+      if (rc < 0) {
+        if (rc == SO_EUNSUPPORTED) return fail(ctx, rc, "family %d with n=%d, f=%d, k=%d is outside the kernel catalogue", family, n, ds->f, k);
+        cudaError_t e = cudaGetLastError();
+        return fail(ctx, rc, "kernel launch failed (%d): %s", rc, cudaGetErrorString(e));
+      }
+      launches += rc;
+    } else {
+      SO_CUDA(ctx, cudaMemsetAsync(dv.out, 0, sizeof(double) * (size_t)Q, dv.stream));
+    }
+    SO_CUDA(ctx, cudaEventRecord(dv.ev1, dv.stream));
+    rows_local += sm.filled;
+  }
+  if (ctx->use_nccl) {
+    SO_NCCL(ctx, g_nccl.GroupStart());
+    for (int g = 0; g < G; ++g) {
+      Device& dv = ctx->devs[g];
+      SO_NCCL(ctx, g_nccl.AllReduce(dv.out, dv.out, (size_t)Q, ncclDouble, ncclSum, dv.comm, dv.stream));
+    }
+    SO_NCCL(ctx, g_nccl.GroupEnd());
+  }
+  {
+    Device& d0 = ctx->devs[0];
+    SO_CUDA(ctx, cudaSetDevice(d0.id));
+    SO_CUDA(ctx, cudaMemcpyAsync(d0.hout, d0.out, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, d0.stream));
+  }
+  for (int g = 0; g < G; ++g) {
+    Device& dv = ctx->devs[g];
+    SO_CUDA(ctx, cudaSetDevice(dv.id));
+    SO_CUDA(ctx, cudaEventRecord(dv.ev2, dv.stream));
+  }
+  double kernel_ms = 0.0, device_ms = 0.0;
+  for (int g = 0; g < G; ++g) {
+    Device& dv = ctx->devs[g];
+    SO_CUDA(ctx, cudaSetDevice(dv.id));
+    SO_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, dv.ev0, dv.ev1);
+    cudaEventElapsedTime(&b, dv.ev0, dv.ev2);
+    kernel_ms = std::max(kernel_ms, (double)a);
+    device_ms = std::max(device_ms, (double)b);
+  }
+  res.assign(ctx->devs[0].hout, ctx->devs[0].hout + Q);
+  res.push_back((double)m_global);
+  ctx->stats.rows = rows_local;
+  ctx->stats.bytes = rows_local * 8 * (int64_t)(ds->f + 1);
+  ctx->stats.kernel_ms = kernel_ms;
+  ctx->stats.device_ms = device_ms;
+  ctx->stats.launches = launches;
+  ctx->stats.total_launches += launches;
+  ctx->stats.total_evals += 1;
+  return SO_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// Context
+// =================================================================================================
+extern "C" int so_abi_version(void) { return SO_ABI_VERSION; }
+
+extern "C" const char* so_last_error(so_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+extern "C" int so_init(int ngpus, const int* device_ids, so_ctx** out) {
+  if (!out || ngpus < 1) return fail(nullptr, SO_EINVAL, "so_init: ngpus must be >= 1 and out non-null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1)
+    return fail(nullptr, SO_ECUDA, "so_init: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (ngpus > count) return fail(nullptr, SO_EINVAL, "so_init: %d GPUs requested, %d visible", ngpus, count);
+  so_ctx* ctx = new so_ctx();
+  ctx->devs.resize(ngpus);
+  for (int g = 0; g < ngpus; ++g) {
+    ctx->devs[g].id = device_ids ? device_ids[g] : g;
+    int rc = setup_device(ctx, ctx->devs[g]);
+    if (rc) { g_init_error = ctx->err; teardown(ctx); delete ctx; return rc; }
+  }
+  if (ngpus > 1) {
+    std::vector<ncclComm_t> comms(ngpus);
+    std::vector<int> ids(ngpus);
+    for (int g = 0; g < ngpus; ++g) ids[g] = ctx->devs[g].id;
+    std::string why;
+    if (!nccl_ready(&why)) { int rc = fail(nullptr, SO_ENCCL, "%s", why.c_str()); teardown(ctx); delete ctx; return rc; }
+    ncclResult_t r = g_nccl.CommInitAll(comms.data(), ngpus, ids.data());
+    if (r != ncclSuccess) {
+      int rc = fail(nullptr, SO_ENCCL, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+      teardown(ctx); delete ctx; return rc;
+    }
+    for (int g = 0; g < ngpus; ++g) ctx->devs[g].comm = comms[g];
+    ctx->use_nccl = true;
+  }
+  *out = ctx;
+  return SO_OK;
+}
+
+extern "C" int so_nccl_unique_id(void* out_uid, size_t bytes) {
+  if (!out_uid || bytes < sizeof(ncclUniqueId)) return fail(nullptr, SO_EINVAL, "so_nccl_unique_id: need %zu bytes", sizeof(ncclUniqueId));
+  std::string why;
+  if (!nccl_ready(&why)) return fail(nullptr, SO_ENCCL, "%s", why.c_str());
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, SO_ENCCL, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+  memset(out_uid, 0, bytes);
+  memcpy(out_uid, &id, sizeof id);
+  return SO_OK;
+}
+
+extern "C" int so_init_rank(int device_id, int rank, int world, const void* nccl_uid, size_t uid_bytes, so_ctx** out) {
+  static_assert(sizeof(ncclUniqueId) <= SO_NCCL_UID_BYTES, "uid size");
+  if (!out || world < 1 || rank < 0 || rank >= world) return fail(nullptr, SO_EINVAL, "so_init_rank: bad rank/world");
+  if (world > 1 && (!nccl_uid || uid_bytes < sizeof(ncclUniqueId))) return fail(nullptr, SO_EINVAL, "so_init_rank: world > 1 needs the NCCL unique id");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1)
+    return fail(nullptr, SO_ECUDA, "so_init_rank: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  so_ctx* ctx = new so_ctx();
+  ctx->devs.resize(1);
+  ctx->devs[0].id = device_id;
+  ctx->rank = rank; ctx->world = world; ctx->rank_mode = true;
+  int rc = setup_device(ctx, ctx->devs[0]);
+  if (rc) { g_init_error = ctx->err; teardown(ctx); delete ctx; return rc; }
+  if (world > 1) {
+    ncclUniqueId id;
+    memcpy(&id, nccl_uid, sizeof id);
+    std::string why;
+    if (!nccl_ready(&why)) { rc = fail(nullptr, SO_ENCCL, "%s", why.c_str()); teardown(ctx); delete ctx; return rc; }
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->devs[0].comm, world, id, rank);
+    if (r != ncclSuccess) {
+      rc = fail(nullptr, SO_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+      teardown(ctx); delete ctx; return rc;
+    }
+    ctx->use_nccl = true;
+  }
+  *out = ctx;
+  return SO_OK;
+}
+
+extern "C" void so_shutdown(so_ctx* ctx) {
+  if (!ctx) return;
+  teardown(ctx);
+  delete ctx;
+}
+
+extern "C" int so_stats(so_ctx* ctx, so_call_stats* out) {
+  if (!ctx || !out) return SO_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = ctx->stats;
+  return SO_OK;
+}
+
+// pinned host memory for callers that want full-speed H2D (e.g. a JNI direct buffer)
+extern "C" int so_host_alloc(size_t bytes, void** out) {
+  if (!out) return SO_EINVAL;
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(nullptr, SO_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return SO_OK;
+}
+extern "C" void so_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// =================================================================================================
+// Data set
+// =================================================================================================
+extern "C" int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out) {
+  if (!ctx || !out) return SO_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (m < 0 || f < 1) return fail(ctx, SO_EINVAL, "so_dataset_create: m=%lld f=%d", (long long)m, f);
+  so_dataset* ds = new so_dataset();
+  ds->ctx = ctx; ds->m = m; ds->f = f;
+  const int G = (int)ctx->devs.size();
+  ds->shards.resize(G);
+  int64_t mg = (m + G - 1) / G;
+  if (f == 1 && (mg & 1) && G > 1) ++mg;    // keep every shard's first row 16-byte aligned for 128-bit loads
+  for (int g = 0; g < G; ++g) {
+    const int64_t b = std::min<int64_t>((int64_t)g * mg, m), e = std::min<int64_t>((int64_t)(g + 1) * mg, m);
+    ShardMem& sm = ds->shards[g];
+    sm.cap = e - b;
+    if (sm.cap > 0) {
+      cudaError_t ce = cudaSetDevice(ctx->devs[g].id);
+      if (ce == cudaSuccess) ce = cudaMalloc(&sm.X, sizeof(double) * (size_t)sm.cap * f);
+      if (ce == cudaSuccess) ce = cudaMalloc(&sm.y, sizeof(double) * (size_t)sm.cap);
+      if (ce != cudaSuccess) {
+        int rc = fail(ctx, ce == cudaErrorMemoryAllocation ? SO_ENOMEM : SO_ECUDA,
+                      "so_dataset_create: %lld rows x %d on device %d: %s", (long long)sm.cap, f, ctx->devs[g].id, cudaGetErrorString(ce));
+        cudaGetLastError();
+        for (ShardMem& s2 : ds->shards) { if (s2.X) cudaFree(s2.X); if (s2.y) cudaFree(s2.y); }
+        delete ds;
+        return rc;
+      }
+    }
+  }
+  *out = ds;
+  return SO_OK;
+}
+
+extern "C" void so_dataset_free(so_dataset* ds) {
+  if (!ds) return;
+  if (!ds->view) {
+    for (size_t g = 0; g < ds->shards.size(); ++g) {
+      cudaSetDevice(ds->ctx->devs[g].id);
+      if (ds->shards[g].X) cudaFree(ds->shards[g].X);
+      if (ds->shards[g].y) cudaFree(ds->shards[g].y);
+    }
+  }
+  delete ds;
+}
+
+extern "C" int so_dataset_append(so_dataset* ds, const double* X, const double* y, int64_t rows) {
+  if (!ds) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_append: cannot append to a view");
+  if (rows < 0 || (rows > 0 && (!X || !y))) return fail(ctx, SO_EINVAL, "so_dataset_append: bad arguments");
+  int64_t filled = 0;
+  for (const ShardMem& sm : ds->shards) filled += sm.filled;
+  if (filled + rows > ds->m) return fail(ctx, SO_EINVAL, "so_dataset_append: %lld rows do not fit (%lld of %lld used)", (long long)rows, (long long)filled, (long long)ds->m);
+  int64_t done = 0;
+  for (size_t g = 0; g < ds->shards.size() && done < rows; ++g) {
+    ShardMem& sm = ds->shards[g];
+    const int64_t take = std::min<int64_t>(sm.cap - sm.filled, rows - done);
+    if (take <= 0) continue;
+    Device& dv = ctx->devs[g];
+    SO_CUDA(ctx, cudaSetDevice(dv.id));
+    SO_CUDA(ctx, cudaMemcpyAsync(sm.X + (size_t)sm.filled * ds->f, X + (size_t)done * ds->f, sizeof(double) * (size_t)take * ds->f, cudaMemcpyHostToDevice, dv.stream));
+    SO_CUDA(ctx, cudaMemcpyAsync(sm.y + sm.filled, y + done, sizeof(double) * (size_t)take, cudaMemcpyHostToDevice, dv.stream));
+    sm.filled += take;
+    done += take;
+  }
+  for (Device& dv : ctx->devs) { SO_CUDA(ctx, cudaSetDevice(dv.id)); SO_CUDA(ctx, cudaStreamSynchronize(dv.stream)); }
+  ds->global_m = -1;
+  return SO_OK;
+}
+
+// empty the data set without releasing HBM (lets a caller re-ingest into the same reservation)
+extern "C" int so_dataset_clear(so_dataset* ds) {
+  if (!ds) return SO_EINVAL;
+  std::lock_guard<std::mutex> lk(ds->ctx->mu);
+  if (ds->view) return fail(ds->ctx, SO_EINVAL, "so_dataset_clear: cannot clear a view");
+  for (ShardMem& sm : ds->shards) sm.filled = 0;
+  ds->global_m = -1;
+  return SO_OK;
+}
+
+extern "C" int so_dataset_generate(so_dataset* ds, int family, const double* p_true, int n, uint64_t seed,
+                                   double noise_sigma, int64_t row_offset) {
+  if (!ds || !p_true) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_generate: cannot fill a view");
+  int rc = check_family(ctx, family, ds->f, n);
+  if (rc) return rc;
+  // the t grid of the scalar families spans the global data set: in rank mode every rank holds m rows
+  const int64_t total = ctx->rank_mode ? ds->m * ctx->world : ds->m;
+  int64_t off = row_offset;
+  for (size_t g = 0; g < ds->shards.size(); ++g) {
+    ShardMem& sm = ds->shards[g];
+    Device& dv = ctx->devs[g];
+    SO_CUDA(ctx, cudaSetDevice(dv.id));
+    Shard sh; sh.rows = sm.cap; sh.f = ds->f; sh.stream = dv.stream; sh.sm_count = dv.sm_count;
+    rc = launch_generate(sh, sm.X, sm.y, family, p_true, n, seed, noise_sigma, off, total);
+    if (rc < 0) return fail(ctx, rc, "so_dataset_generate: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->stats.total_launches += rc;
+    sm.filled = sm.cap;
+    off += sm.cap;
+  }
+  for (Device& dv : ctx->devs) { SO_CUDA(ctx, cudaSetDevice(dv.id)); SO_CUDA(ctx, cudaStreamSynchronize(dv.stream)); }
+  ds->global_m = -1;
+  return SO_OK;
+}
+
+extern "C" int so_dataset_read(so_dataset* ds, int64_t row_begin, int64_t rows, double* X, double* y) {
+  if (!ds) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int64_t filled = 0;
+  for (const ShardMem& sm : ds->shards) filled += sm.filled;
+  if (row_begin < 0 || rows < 0 || row_begin + rows > filled) return fail(ctx, SO_EINVAL, "so_dataset_read: rows [%lld, %lld) outside [0, %lld)", (long long)row_begin, (long long)(row_begin + rows), (long long)filled);
+  int64_t base = 0, done = 0;
+  for (size_t g = 0; g < ds->shards.size() && done < rows; ++g) {
+    const ShardMem& sm = ds->shards[g];
+    const int64_t lo = std::max<int64_t>(row_begin + done, base), hi = std::min<int64_t>(row_begin + rows, base + sm.filled);
+    if (hi > lo) {
+      SO_CUDA(ctx, cudaSetDevice(ctx->devs[g].id));
+      if (X) SO_CUDA(ctx, cudaMemcpy(X + (size_t)done * ds->f, sm.X + (size_t)(lo - base) * ds->f, sizeof(double) * (size_t)(hi - lo) * ds->f, cudaMemcpyDeviceToHost));
+      if (y) SO_CUDA(ctx, cudaMemcpy(y + done, sm.y + (lo - base), sizeof(double) * (size_t)(hi - lo), cudaMemcpyDeviceToHost));
+      done += hi - lo;
+    }
+    base += sm.filled;
+  }
+  return SO_OK;
+}
+
+extern "C" int so_dataset_size(so_dataset* ds, int64_t* m) {
+  if (!ds || !m) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return global_rows(ds, m);
+}
+
+extern "C" int so_dataset_head(so_dataset* ds, double* x, double* y) {
+  if (!ds) return SO_EINVAL;
+  int64_t filled = 0;
+  for (const ShardMem& sm : ds->shards) filled += sm.filled;
+  if (filled < 1) return fail(ds->ctx, SO_ESTATE, "so_dataset_head: empty data set");   // Seq.head on Nil throws
+  return so_dataset_read(ds, 0, 1, x, y);
+}
+
+extern "C" int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_dataset** view) {
+  if (!ds || !view) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int64_t filled = 0;
+  for (const ShardMem& sm : ds->shards) filled += sm.filled;
+  if (begin < 0 || end < begin || end > filled) return fail(ctx, SO_EINVAL, "so_dataset_slice: [%lld, %lld) outside [0, %lld)", (long long)begin, (long long)end, (long long)filled);
+  so_dataset* v = new so_dataset();
+  v->ctx = ctx; v->f = ds->f; v->view = true; v->m = end - begin;
+  v->shards.resize(ds->shards.size());
+  int64_t base = 0;
+  for (size_t g = 0; g < ds->shards.size(); ++g) {
+    const ShardMem& sm = ds->shards[g];
+    const int64_t lo = std::max<int64_t>(begin, base), hi = std::min<int64_t>(end, base + sm.filled);
+    if (hi > lo) {
+      v->shards[g].X = sm.X + (size_t)(lo - base) * ds->f;
+      v->shards[g].y = sm.y + (lo - base);
+      v->shards[g].cap = v->shards[g].filled = hi - lo;
+    }
+    base += sm.filled;
+  }
+  *view = v;
+  return SO_OK;
+}
+
+// =================================================================================================
+// Evaluation
+// =================================================================================================
+extern "C" int so_eval_loss_grad(so_dataset* ds, int family, const double* p, int n, double* loss, double* grad) {
+  if (!ds || !p || !loss) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = check_family(ctx, family, ds->f, n);
+  if (rc) return rc;
+  const int Q = grad ? 1 + n : 1;
+  std::vector<double> res;
+  rc = run_eval(ds, kLossGrad, family, p, nullptr, n, nullptr, 0, grad ? 1 : 0, Q, res);
+  if (rc) return rc;
+  const double m = res[Q];
+  *loss = res[0] / m;                                   // ... / data.size, MSEFunction.scala:35
+  if (grad) for (int i = 0; i < n; ++i) grad[i] = res[1 + i] / m;
+  return SO_OK;
+}
+
+extern "C" int so_eval_normal_eq(so_dataset* ds, int family, const double* p, int n, double* JtJ, double* Jtr, double* rtr) {
+  if (!ds || !p || !JtJ || !Jtr || !rtr) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = check_family(ctx, family, ds->f, n);
+  if (rc) return rc;
+  const int T = n * (n + 1) / 2, Q = T + n + 1;
+  std::vector<double> res;
+  rc = run_eval(ds, kNormalEq, family, p, nullptr, n, nullptr, 0, 0, Q, res);
+  if (rc) return rc;
+  int q = 0;
+  for (int a = 0; a < n; ++a)
+    for (int b = a; b < n; ++b) { JtJ[a * n + b] = res[q]; JtJ[b * n + a] = res[q]; ++q; }
+  for (int a = 0; a < n; ++a) Jtr[a] = res[T + a];
+  *rtr = res[T + n];
+  return SO_OK;
+}
+
+extern "C" int so_eval_line(so_dataset* ds, int family, const double* p, const double* d, int n,
+                            const double* alpha, int k, double* phi, double* dphi) {
+  if (!ds || !p || !d || !alpha || !phi || !dphi) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = check_family(ctx, family, ds->f, n);
+  if (rc) return rc;
+  if (k < 1 || k > SO_MAX_ALPHAS) return fail(ctx, SO_EINVAL, "so_eval_line: k=%d outside [1, %d]", k, SO_MAX_ALPHAS);
+  const bool scalar = family_is_scalar_t(family);
+  // one pass scores up to `chunk` step sizes; longer schedules take ceil(k/chunk) passes
+  const int chunk = 8;
+  so_call_stats acc{};
+  for (int k0 = 0; k0 < k; k0 += chunk) {
+    const int kk = std::min(chunk, k - k0);
+    const int KB = scalar ? scalar_line_block(kk) : kk;
+    std::vector<double> res;
+    rc = run_eval(ds, kLine, family, p, d, n, alpha + k0, kk, 0, 2 * KB, res);
+    if (rc) return rc;
+    const double m = res[2 * KB];
+    for (int j = 0; j < kk; ++j) { phi[k0 + j] = res[j] / m; dphi[k0 + j] = res[KB + j] / m; }
+    acc.kernel_ms += ctx->stats.kernel_ms; acc.device_ms += ctx->stats.device_ms; acc.launches += ctx->stats.launches;
+    acc.rows += ctx->stats.rows; acc.bytes += ctx->stats.bytes;
+  }
+  ctx->stats.kernel_ms = acc.kernel_ms; ctx->stats.device_ms = acc.device_ms; ctx->stats.launches = acc.launches;
+  ctx->stats.rows = acc.rows; ctx->stats.bytes = acc.bytes;
+  return SO_OK;
+}
+
+extern "C" int so_eval_hess_vec(so_dataset* ds, int family, const double* p, const double* d, int n, double* Hd) {
+  if (!ds || !p || !d || !Hd) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = check_family(ctx, family, ds->f, n);
+  if (rc) return rc;
+  std::vector<double> res;
+  rc = run_eval(ds, kHessVec, family, p, d, n, nullptr, 0, 0, n, res);
+  if (rc) return rc;
+  const double m = res[n];
+  for (int i = 0; i < n; ++i) Hd[i] = res[i] / m;
+  return SO_OK;
+}

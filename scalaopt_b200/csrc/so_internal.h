@@ -1,0 +1,78 @@
+// so_internal.h — launch interface between the C-ABI layer (so_api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/scalaopt_cuda.h"
+
+namespace so {
+
+// One GPU's resident shard (or a slice of it) plus the workspace the kernels reduce through.
+struct Shard {
+  const double* X = nullptr;   // rows x f, row-major
+  const double* y = nullptr;   // rows
+  int64_t rows = 0;
+  int f = 0;
+  // workspace owned by the context (per device)
+  double* partials = nullptr;  // per-block partial sums
+  size_t partials_doubles = 0;
+  double* out = nullptr;       // reduced result of the running evaluation
+  size_t out_doubles = 0;
+  unsigned int* ticket = nullptr;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+};
+
+enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4 };
+
+// number of doubles each evaluation leaves in Shard::out (before the 1/m normalisation, which the
+// API layer applies after the cross-GPU sum):
+//   kLossGrad : [ loss_sum, g_0 .. g_{n-1} ]                          (loss_sum = sum r^2/2 or sum CE)
+//   kNormalEq : [ JtJ upper triangle packed row-major (a<=b), Jtr_0..Jtr_{n-1}, rtr ]
+//   kLine     : [ phi_sum_0..phi_sum_{k-1}, dphi_sum_0..dphi_sum_{k-1} ]
+//   kHessVec  : [ Hd_sum_0 .. Hd_sum_{n-1} ]
+inline int out_doubles(Kind kind, int n, int k) {
+  switch (kind) {
+    case kLossGrad: return 1 + n;
+    case kNormalEq: return n * (n + 1) / 2 + n + 1;
+    case kLine: return 2 * k;
+    case kHessVec: return n;
+  }
+  return 0;
+}
+
+// required size of Shard::partials for an evaluation (doubles)
+size_t scalar_partials_needed(Kind kind, int n, int k, int sm_count);
+size_t wide_partials_needed(Kind kind, int family, int n, int f, int k, int sm_count);
+
+// Each launcher enqueues its kernel(s) on shard.stream and returns the number of kernels launched
+// (>0) or a negative SO_E* code.  `want_grad` = 0 makes kLossGrad a loss-only pass.
+int launch_scalar(Kind kind, const Shard& s, int family, const double* p, const double* d, int n,
+                  const double* alpha, int k, int want_grad);
+int launch_wide(Kind kind, const Shard& s, int family, const double* p, const double* d, int n,
+                const double* alpha, int k, int want_grad);
+
+// padded width KB of the kLine result of launch_scalar: phi at out[0,k), dphi at out[KB, KB+k)
+int scalar_line_block(int k);
+
+// synthetic data
+int launch_generate(const Shard& s, double* X, double* y, int family, const double* p_true, int n, uint64_t seed,
+                    double noise_sigma, int64_t row_offset, int64_t total_rows);
+
+inline bool family_is_scalar_t(int family) {
+  return family == SO_FAMILY_EXPDECAY || family == SO_FAMILY_GAUSS || family == SO_FAMILY_GAUSS_EXPBKG ||
+         family == SO_FAMILY_POLY;
+}
+inline int family_nparams(int family, int f, int n_hint) {
+  switch (family) {
+    case SO_FAMILY_LINEAR: case SO_FAMILY_LOGISTIC: return f + 1;
+    case SO_FAMILY_LINEAR_NOINT: return f;
+    case SO_FAMILY_EXPDECAY: return 2;
+    case SO_FAMILY_GAUSS: return 3;
+    case SO_FAMILY_GAUSS_EXPBKG: return 5;
+    case SO_FAMILY_POLY: return n_hint;
+  }
+  return -1;
+}
+
+}  // namespace so
