@@ -1,0 +1,284 @@
+// so_gram.cu — K2 for the linear-predictor families: J^T J, J^T r and r^T r in one pass.
+//
+// For these families a Jacobian row is +-[1, x_i] (linear least squares: J = -sign(y - f) [1, x], r = |y - f|;
+// logistic under Levenberg-Marquardt: the reference trainer's convention J = [1, x], r = o - y,
+// Neuron.scala:67-73 / FFNeuralNetwork.scala:174-179).  With Z = [x | 1 | res] (the intercept column is moved
+// behind the inputs so that the inputs stay contiguous) all three results are blocks of the Gram matrix Z^T Z:
+// a SYRK over m rows.  This replaces MSEFunction.jacobianAndResidualsMatrix (MSEFunction.scala:132-136) plus the
+// 2n+1 passes of QR.apply (linalg/QR.scala:131-250) that only ever needed these sums.
+//
+//   n <= 8      one thread per observation, packed upper triangle in registers (FP64 FMA pipe, HBM-bound)
+//   n+1 <= 48   DMMA (mma.sync.m8n8k4.f64): a warp owns the whole upper triangle of 8x8 tiles and streams slabs
+//               of 4 rows.  The A and B fragments of tile (ta, tb) are the SAME registers — lane l holds
+//               Z[row0 + l%4][8t + l/4] — so a slab costs T 64-bit loads per lane, straight from global memory.
+//               Measured on this pool's B200: DMMA 37.2 TFLOP/s vs 33.8 for register-resident DFMA
+//               (profiles/r1_fp64_peak.json), and one DMMA replaces 8 DFMA issue slots + their operand traffic.
+//   larger n    not in this file yet (returns SO_EUNSUPPORTED; see DESIGN.md "next")
+#include <algorithm>
+
+#include "so_wide.cuh"
+
+namespace so {
+namespace wide {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// n <= 8: thread per observation
+// ---------------------------------------------------------------------------------------------------
+template <int FAM, int NP, int ICPT>
+__global__ void __launch_bounds__(kThreads, 2)
+k_gram_small(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+             double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+  constexpr int F = NP - ICPT, T = NP * (NP + 1) / 2, Q = T + NP + 1;
+  __shared__ double s_red[kWarps * Q];
+  __shared__ double s_scale[Q];
+  if (FAM == kLogistic) exp_table_init();
+  for (int q = threadIdx.x; q < Q; q += kThreads) s_scale[q] = (q >= T && q < T + NP && FAM == kLinear) ? -1.0 : 1.0;
+  __syncthreads();
+  double acc[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = 0.0;
+  double p[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = P.p[i];
+  for (int64_t row = (int64_t)blockIdx.x * kThreads + threadIdx.x; row < rows; row += (int64_t)gridDim.x * kThreads) {
+    double xt[NP];
+    if (ICPT) xt[0] = 1.0;
+#pragma unroll
+    for (int j = 0; j < F; ++j) xt[ICPT + j] = ld_stream(X + row * F + j);
+    const double yv = ld_stream(y + row);
+    double z = 0.0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) z = fma(p[i], xt[i], z);
+    double res;
+    if (FAM == kLinear) {
+      res = yv - z;                     // rho; J r = -x~ rho
+    } else {
+      const double e = so_exp(-fabs(z));
+      const double inv = 1.0 / (1.0 + e);
+      res = ((z >= 0.0) ? inv : e * inv) - yv;
+    }
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+#pragma unroll
+      for (int j = i; j < NP; ++j) { acc[q] = fma(xt[i], xt[j], acc[q]); ++q; }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[T + i] = fma(xt[i], res, acc[T + i]);
+    acc[T + NP] = fma(res, res, acc[T + NP]);
+  }
+  grid_reduce<Q>(acc, s_red, partials, out, s_scale, ticket);
+}
+
+template <int FAM, int NP, int ICPT>
+int launch_small(const Shard& s, const Params& P) {
+  auto kern = k_gram_small<FAM, NP, ICPT>;
+  constexpr int Q = NP * (NP + 1) / 2 + NP + 1;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const int64_t want = std::max<int64_t>(1, (s.rows + kThreads - 1) / kThreads);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
+  if ((size_t)grid * Q > s.partials_doubles || (size_t)Q > s.out_doubles) return SO_ENOMEM;
+  kern<<<grid, kThreads, 0, s.stream>>>(s.X, s.y, s.rows, P, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+template <int FAM>
+int dispatch_small(const Shard& s, const Params& P) {
+#define SO_CASE(NPV) case NPV: return P.icpt ? launch_small<FAM, NPV, 1>(s, P) : launch_small<FAM, NPV, 0>(s, P);
+  switch (P.n) {
+    case 1: return P.icpt ? SO_EUNSUPPORTED : launch_small<FAM, 1, 0>(s, P);
+    SO_CASE(2) SO_CASE(3) SO_CASE(4) SO_CASE(5) SO_CASE(6) SO_CASE(7) SO_CASE(8)
+  }
+#undef SO_CASE
+  return SO_EUNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 8 < n, n + 1 <= 8 T <= 48: DMMA over the upper triangle of 8x8 tiles
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int T> __host__ __device__ constexpr int tri_tiles() { return T * (T + 1) / 2; }
+__host__ __device__ inline int tri_index(int T, int ta, int tb) { return ta * T - ta * (ta - 1) / 2 + (tb - ta); }
+
+template <int FAM, int T>
+__global__ void __launch_bounds__(kThreads, 2)
+k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+           double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+  constexpr int NT = tri_tiles<T>();
+  extern __shared__ double smem[];            // NT * 64 doubles: this block's tiles, lane-major
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rsel = lane & 3, csel = lane >> 2;
+  const int f = P.f, icpt = P.icpt, n = P.n;
+  const int col_one = icpt ? f : -1, col_res = f + icpt;
+  if (FAM == kLogistic) { exp_table_init(); __syncthreads(); }
+
+  double pz[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) pz[t] = (8 * t + csel < f) ? P.p[icpt + 8 * t + csel] : 0.0;
+  const double p0 = icpt ? P.p[0] : 0.0;
+  double acc[NT][2];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+
+  const int64_t nslabs = (rows + 3) >> 2;
+  const int64_t sstr = (int64_t)gridDim.x * kWarps;
+  int64_t slab = (int64_t)blockIdx.x * kWarps + warp;
+
+  double cur[T], nxt[T], ycur = 0.0, ynxt = 0.0;
+  bool vcur = false, vnxt = false;
+  auto load = [&](int64_t s, double (&fr)[T], double& yv, bool& valid) {
+    const int64_t row = 4 * s + rsel;
+    valid = row < rows;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int col = 8 * t + csel;
+      fr[t] = (valid && col < f) ? ld_stream(X + row * f + col) : 0.0;
+    }
+    yv = valid ? ld_stream(y + row) : 0.0;
+  };
+  if (slab < nslabs) load(slab, cur, ycur, vcur);
+  while (slab < nslabs) {
+    const int64_t ns = slab + sstr;
+    if (ns < nslabs) load(ns, nxt, ynxt, vnxt);
+    // linear predictor of the slab's 4 rows: lanes with equal lane%4 hold one row
+    double dot = 0.0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) dot = fma(pz[t], cur[t], dot);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 8);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+    const double z = dot + p0;
+    double res;
+    if (FAM == kLinear) {
+      res = ycur - z;
+    } else {
+      const double e = so_exp(-fabs(z));
+      const double inv = 1.0 / (1.0 + e);
+      res = ((z >= 0.0) ? inv : e * inv) - ycur;
+    }
+    if (!vcur) res = 0.0;
+    const double one = vcur ? 1.0 : 0.0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int col = 8 * t + csel;
+      if (col == col_one) cur[t] = one;
+      if (col == col_res) cur[t] = res;
+    }
+#pragma unroll
+    for (int ta = 0; ta < T; ++ta)
+#pragma unroll
+      for (int tb = ta; tb < T; ++tb) {
+        const int idx = ta * T - ta * (ta - 1) / 2 + (tb - ta);
+        dmma(acc[idx][0], acc[idx][1], cur[ta], cur[tb]);
+      }
+#pragma unroll
+    for (int t = 0; t < T; ++t) cur[t] = nxt[t];
+    ycur = ynxt; vcur = vnxt;
+    slab = ns;
+  }
+
+  // block sum in warp order (deterministic), lane-major tile storage: tile[idx][lane*2 + reg]
+  for (int w = 0; w < kWarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        double* tile = smem + i * 64 + lane * 2;
+        if (w == 0) { tile[0] = acc[i][0]; tile[1] = acc[i][1]; }
+        else { tile[0] += acc[i][0]; tile[1] += acc[i][1]; }
+      }
+    }
+    __syncthreads();
+  }
+  constexpr int QT = NT * 64;
+  for (int q = threadIdx.x; q < QT; q += kThreads) partials[(size_t)blockIdx.x * QT + q] = smem[q];
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    // emit the API layout: packed upper triangle over parameters (a <= b), then Jtr, then rtr.
+    // parameter a lives in Z column za = (icpt ? (a == 0 ? f : a - 1) : a); the residual in column col_res.
+    const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
+    for (int q = threadIdx.x; q < Qo; q += kThreads) {
+      int ca, cb;
+      double sgn = 1.0;
+      if (q < Tn) {
+        int a = 0, rem = q;                     // unpack (a, b) from the row-major packed index
+        while (rem >= n - a) { rem -= n - a; ++a; }
+        const int b = a + rem;
+        ca = icpt ? (a == 0 ? f : a - 1) : a;
+        cb = icpt ? (b == 0 ? f : b - 1) : b;
+      } else if (q < Tn + n) {
+        const int a = q - Tn;
+        ca = icpt ? (a == 0 ? f : a - 1) : a;
+        cb = col_res;
+        if (FAM == kLinear) sgn = -1.0;
+      } else {
+        ca = col_res; cb = col_res;
+      }
+      if (ca / 8 > cb / 8) { const int tmp = ca; ca = cb; cb = tmp; }
+      const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
+      const int off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
+      double s = 0.0;
+      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += __ldcg(&partials[(size_t)b2 * QT + off]);
+      out[q] = s * sgn;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+template <int FAM, int T>
+int launch_tri(const Shard& s, const Params& P) {
+  auto kern = k_gram_tri<FAM, T>;
+  constexpr int QT = tri_tiles<T>() * 64;
+  const size_t smem = sizeof(double) * QT;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int64_t nslabs = (s.rows + 3) / 4;
+  const int64_t want = std::max<int64_t>(1, (nslabs + kWarps - 1) / kWarps);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
+  const int Qo = P.n * (P.n + 1) / 2 + P.n + 1;
+  if ((size_t)grid * QT > s.partials_doubles || (size_t)Qo > s.out_doubles) return SO_ENOMEM;
+  kern<<<grid, kThreads, smem, s.stream>>>(s.X, s.y, s.rows, P, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+template <int FAM>
+int dispatch_tri(const Shard& s, const Params& P) {
+  const int T = (P.n + 1 + 7) / 8;
+  switch (T) {
+    case 2: return launch_tri<FAM, 2>(s, P);
+    case 3: return launch_tri<FAM, 3>(s, P);
+    case 4: return launch_tri<FAM, 4>(s, P);
+    case 5: return launch_tri<FAM, 5>(s, P);
+    case 6: return launch_tri<FAM, 6>(s, P);
+  }
+  return SO_EUNSUPPORTED;
+}
+
+}  // namespace
+
+size_t gram_partials_needed(int n, int f, int sm_count) {
+  (void)f;
+  if (n <= 8) return (size_t)sm_count * 8 * (size_t)(n * (n + 1) / 2 + n + 1);
+  const int T = (n + 1 + 7) / 8;
+  return (size_t)sm_count * 4 * (size_t)(T * (T + 1) / 2) * 64;
+}
+
+int launch_gram(const Shard& s, int fam, const Params& P) {
+  if (P.n <= 8) return fam == kLinear ? dispatch_small<kLinear>(s, P) : dispatch_small<kLogistic>(s, P);
+  if (P.n + 1 <= 48) return fam == kLinear ? dispatch_tri<kLinear>(s, P) : dispatch_tri<kLogistic>(s, P);
+  return SO_EUNSUPPORTED;
+}
+
+}  // namespace wide
+}  // namespace so

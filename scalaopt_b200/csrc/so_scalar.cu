@@ -19,6 +19,7 @@
 // kernels accumulate sums of u_a u_b, u_a rho, rho^2 and the last block applies D on the way out.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -34,16 +35,20 @@ constexpr double kInvSqrt2 = 0.70710678118654752;
 
 // ---------------------------------------------------------------------------------------------------
 // Families.  Pre = per-evaluation constants (kernel parameter space), u = derivative basis.
+// Evaluation is split in two so that the kernel can range-check all exp arguments of a group of rows with
+// one branch and then run the branch-free so_exp_fast on all of them (cross-row ILP on the FP64 pipe):
+//   args(pre, t, a)              -> the NE exp arguments of this row
+//   finish(pre, t, ex, f, u)     -> model value and derivative basis from the NE exponentials
 // ---------------------------------------------------------------------------------------------------
 struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarquardtSpec.scala:62-63
-  static constexpr int N = 2;
+  static constexpr int N = 2, NE = 1;
   struct Pre { double p0, p1; double D[N]; };
   static Pre prepare(const double* p) { Pre c; c.p0 = p[0]; c.p1 = p[1]; c.D[0] = 1.0; c.D[1] = p[0]; return c; }
-  __device__ static __forceinline__ void eval(const Pre& c, double t, const double* tab, double& f, double (&u)[N]) {
-    const double e = so_exp(c.p1 * t, tab);
-    u[0] = e;          // df/dp0 = e
-    u[1] = t * e;      // df/dp1 = p0 t e
-    f = c.p0 * e;
+  __device__ static __forceinline__ void args(const Pre& c, double t, double* a) { a[0] = c.p1 * t; }
+  __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
+    u[0] = ex[0];          // df/dp0 = e
+    u[1] = t * ex[0];      // df/dp1 = p0 t e
+    f = c.p0 * ex[0];
   }
   __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
     h[0] = u[1] * d[1];
@@ -52,20 +57,23 @@ struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarqua
 };
 
 struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma)
-  static constexpr int N = 3;
+  static constexpr int N = 3, NE = 1;
   struct Pre { double A, mu, s, sr2; double D[N]; };   // s = 1/sigma, sr2 = s/sqrt(2)
   static Pre prepare(const double* p) {
     Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2;
     c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2; c.D[2] = 2.0 * p[0] * c.s;
     return c;
   }
-  __device__ static __forceinline__ void eval(const Pre& c, double t, const double* tab, double& f, double (&u)[N]) {
+  __device__ static __forceinline__ void args(const Pre& c, double t, double* a) {
     const double zz = (t - c.mu) * c.sr2;          // z / sqrt(2),  z = (t - mu)/sigma
-    const double g = so_exp(-zz * zz, tab);
-    u[0] = g;              // df/dA     = g
-    u[1] = g * zz;         // df/dmu    = A g z / sigma      = (A s sqrt2) g zz
+    a[0] = -zz * zz;
+  }
+  __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
+    const double zz = (t - c.mu) * c.sr2;
+    u[0] = ex[0];          // df/dA     = g
+    u[1] = ex[0] * zz;     // df/dmu    = A g z / sigma      = (A s sqrt2) g zz
     u[2] = u[1] * zz;      // df/dsigma = A g z^2 / sigma    = (2 A s) g zz^2
-    f = c.A * g;
+    f = c.A * ex[0];
   }
   __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
     const double z = (t - c.mu) * c.s, g = u[0], z2 = z * z;
@@ -79,23 +87,26 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
 };
 
 struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),  p = (A, mu, sigma, B, lambda)
-  static constexpr int N = 5;   // functional form of stats/example/ExSignalPlusBackgroundFit.scala:78-114
+  static constexpr int N = 5, NE = 2;   // functional form of stats/example/ExSignalPlusBackgroundFit.scala:78-114
   struct Pre { double A, mu, s, sr2, B, nlam; double D[N]; };
   static Pre prepare(const double* p) {
     Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.B = p[3]; c.nlam = -p[4];
     c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2; c.D[2] = 2.0 * p[0] * c.s; c.D[3] = 1.0; c.D[4] = -p[3];
     return c;
   }
-  __device__ static __forceinline__ void eval(const Pre& c, double t, const double* tab, double& f, double (&u)[N]) {
+  __device__ static __forceinline__ void args(const Pre& c, double t, double* a) {
     const double zz = (t - c.mu) * c.sr2;
-    const double g = so_exp(-zz * zz, tab);
-    const double e = so_exp(c.nlam * t, tab);
-    u[0] = g;
-    u[1] = g * zz;
+    a[0] = -zz * zz;
+    a[1] = c.nlam * t;
+  }
+  __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
+    const double zz = (t - c.mu) * c.sr2;
+    u[0] = ex[0];
+    u[1] = ex[0] * zz;
     u[2] = u[1] * zz;
-    u[3] = e;              // df/dB      = e
-    u[4] = t * e;          // df/dlambda = -B t e
-    f = fma(c.A, g, c.B * e);
+    u[3] = ex[1];          // df/dB      = e
+    u[4] = t * ex[1];      // df/dlambda = -B t e
+    f = fma(c.A, ex[0], c.B * ex[1]);
   }
   __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
     const double z = (t - c.mu) * c.s, g = u[0], z2 = z * z;
@@ -112,10 +123,11 @@ struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),
 
 template <int NP>
 struct FamPoly {       // f = sum_k p_k t^k
-  static constexpr int N = NP;
+  static constexpr int N = NP, NE = 0;
   struct Pre { double p[N]; double D[N]; };
   static Pre prepare(const double* p) { Pre c; for (int k = 0; k < N; ++k) { c.p[k] = p[k]; c.D[k] = 1.0; } return c; }
-  __device__ static __forceinline__ void eval(const Pre& c, double t, const double*, double& f, double (&u)[N]) {
+  __device__ static __forceinline__ void args(const Pre&, double, double*) {}
+  __device__ static __forceinline__ void finish(const Pre& c, double t, const double*, double& f, double (&u)[N]) {
     u[0] = 1.0;
     double s = c.p[0];
 #pragma unroll
@@ -129,15 +141,16 @@ struct FamPoly {       // f = sum_k p_k t^k
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Per-kind row operators
+// Per-kind row operators.  NEXP exp arguments per row, G rows per range-checked group.
 // ---------------------------------------------------------------------------------------------------
 template <class Fam, bool GRAD>
 struct OpLossGrad {
-  static constexpr int N = Fam::N, Q = GRAD ? 1 + N : 1;
+  static constexpr int N = Fam::N, Q = GRAD ? 1 + N : 1, NEXP = Fam::NE, G = 4;
   struct Args { typename Fam::Pre pre; double scale[Q]; };
-  __device__ static __forceinline__ void row(const Args& a, double t, double y, const double* tab, double (&acc)[Q]) {
+  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
-    Fam::eval(a.pre, t, tab, f, u);
+    Fam::finish(a.pre, t, ex, f, u);
     const double rho = y - f;
     acc[0] = fma(rho, rho, acc[0]);
     if constexpr (GRAD) {
@@ -147,13 +160,14 @@ struct OpLossGrad {
   }
 };
 
-template <class Fam>
+template <class Fam, int GROUP = 4>
 struct OpNormalEq {
-  static constexpr int N = Fam::N, T = N * (N + 1) / 2, Q = T + N + 1;
+  static constexpr int N = Fam::N, T = N * (N + 1) / 2, Q = T + N + 1, NEXP = Fam::NE, G = GROUP;
   struct Args { typename Fam::Pre pre; double scale[Q]; };
-  __device__ static __forceinline__ void row(const Args& a, double t, double y, const double* tab, double (&acc)[Q]) {
+  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
-    Fam::eval(a.pre, t, tab, f, u);
+    Fam::finish(a.pre, t, ex, f, u);
     const double rho = y - f;
     int q = 0;
 #pragma unroll
@@ -168,13 +182,17 @@ struct OpNormalEq {
 
 template <class Fam, int KB>
 struct OpLine {
-  static constexpr int N = Fam::N, Q = 2 * KB;
+  static constexpr int N = Fam::N, Q = 2 * KB, NEXP = KB * Fam::NE, G = (KB <= 1 ? 4 : (KB <= 2 ? 2 : 1));
   struct Args { typename Fam::Pre pre[KB]; double dd[KB][N]; double scale[Q]; };   // dd = D(p + alpha d) o d
-  __device__ static __forceinline__ void row(const Args& a, double t, double y, const double* tab, double (&acc)[Q]) {
+  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) {
+#pragma unroll
+    for (int k = 0; k < KB; ++k) Fam::args(a.pre[k], t, ea + k * Fam::NE);
+  }
+  __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
       double f, u[N];
-      Fam::eval(a.pre[k], t, tab, f, u);
+      Fam::finish(a.pre[k], t, ex + k * Fam::NE, f, u);
       const double rho = y - f;
       double jd = 0.0;
 #pragma unroll
@@ -187,11 +205,12 @@ struct OpLine {
 
 template <class Fam>
 struct OpHessVec {
-  static constexpr int N = Fam::N, Q = N;
+  static constexpr int N = Fam::N, Q = N, NEXP = Fam::NE, G = 2;
   struct Args { typename Fam::Pre pre; double d[N]; double scale[Q]; };
-  __device__ static __forceinline__ void row(const Args& a, double t, double y, const double* tab, double (&acc)[Q]) {
+  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N], h[N], J[N];
-    Fam::eval(a.pre, t, tab, f, u);
+    Fam::finish(a.pre, t, ex, f, u);
     const double rho = y - f;
     double jd = 0.0;
 #pragma unroll
@@ -202,8 +221,61 @@ struct OpHessVec {
   }
 };
 
+// G rows: all exp arguments first, ONE range check, then branch-free exponentials, then the accumulation.
+template <class Op, int G>
+__device__ __forceinline__ void process_rows(const typename Op::Args& args, const double (&t)[G], const double (&y)[G],
+                                             double (&acc)[Op::Q]) {
+  constexpr int NE = Op::NEXP;
+  if constexpr (NE == 0) {
+#pragma unroll
+    for (int r = 0; r < G; ++r) Op::accum(args, t[r], y[r], nullptr, acc);
+  } else {
+    double ea[G][NE];
+    int mx = 0;
+#pragma unroll
+    for (int r = 0; r < G; ++r) {
+      Op::args(args, t[r], ea[r]);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) mx = max(mx, exp_abs_hi(ea[r][e]));
+    }
+    if (mx < kExpHiLimit) {
+#pragma unroll
+      for (int r = 0; r < G; ++r)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) ea[r][e] = so_exp_fast(ea[r][e]);
+    } else {      // some |arg| >= 708, inf or NaN in this group: full-range libdevice exp for the whole group
+#pragma unroll
+      for (int r = 0; r < G; ++r)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) ea[r][e] = exp_slow(ea[r][e]);
+    }
+#pragma unroll
+    for (int r = 0; r < G; ++r) Op::accum(args, t[r], y[r], ea[r], acc);
+  }
+}
+
+// a loop trip carries 4 rows (two 128-bit loads of t and of y); they are processed in groups of Op::G
+template <class Op>
+__device__ __forceinline__ void process4(const typename Op::Args& args, double2 ta, double2 ya, double2 tb, double2 yb,
+                                         double (&acc)[Op::Q]) {
+  constexpr int G = Op::G;
+  const double t4[4] = {ta.x, ta.y, tb.x, tb.y}, y4[4] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+  for (int g0 = 0; g0 < 4; g0 += G) {
+    double tg[G], yg[G];
+#pragma unroll
+    for (int r = 0; r < G; ++r) { tg[r] = t4[g0 + r]; yg[r] = y4[g0 + r]; }
+    process_rows<Op, G>(args, tg, yg, acc);
+  }
+}
+template <class Op>
+__device__ __forceinline__ void process1(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q]) {
+  const double tg[1] = {t}, yg[1] = {y};
+  process_rows<Op, 1>(args, tg, yg, acc);
+}
+
 // ---------------------------------------------------------------------------------------------------
-// The kernel: grid-stride over pairs of observations, 2 pairs in flight per thread.
+// The kernel: grid-stride over pairs of observations, 2 pairs (4 observations) in flight per thread.
 // ---------------------------------------------------------------------------------------------------
 template <class Op, int MINBLOCKS>
 __global__ void __launch_bounds__(kThreads, MINBLOCKS)
@@ -211,10 +283,11 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
          const __grid_constant__ typename Op::Args args,
          double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   constexpr int Q = Op::Q;
-  __shared__ double s_tab[kExpTableSize];
   __shared__ double s_red[(kThreads / 32) * Q];
-  exp_table_init(s_tab);
-  __syncthreads();
+  if constexpr (Op::NEXP > 0) {
+    exp_table_init();
+    __syncthreads();
+  }
 
   double acc[Q];
 #pragma unroll
@@ -233,18 +306,15 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
   for (; i + gstride < npairs; i += 2 * gstride) {
     const double2 ta = ld_stream2(t2 + i), ya = ld_stream2(y2 + i);
     const double2 tb = ld_stream2(t2 + i + gstride), yb = ld_stream2(y2 + i + gstride);
-    Op::row(args, ta.x, ya.x, s_tab, acc);
-    Op::row(args, ta.y, ya.y, s_tab, acc);
-    Op::row(args, tb.x, yb.x, s_tab, acc);
-    Op::row(args, tb.y, yb.y, s_tab, acc);
+    process4<Op>(args, ta, ya, tb, yb, acc);
   }
   if (i < npairs) {
     const double2 ta = ld_stream2(t2 + i), ya = ld_stream2(y2 + i);
-    Op::row(args, ta.x, ya.x, s_tab, acc);
-    Op::row(args, ta.y, ya.y, s_tab, acc);
+    process1<Op>(args, ta.x, ya.x, acc);
+    process1<Op>(args, ta.y, ya.y, acc);
   }
-  if (gtid == 0 && head) Op::row(args, t[0], y[0], s_tab, acc);
-  if (gtid == gstride - 1 && tail) Op::row(args, t[rows - 1], y[rows - 1], s_tab, acc);
+  if (gtid == 0 && head) process1<Op>(args, t[0], y[0], acc);
+  if (gtid == gstride - 1 && tail) process1<Op>(args, t[rows - 1], y[rows - 1], acc);
 
   grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket);
 }
@@ -292,7 +362,23 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       for (int i = 0; i < N; ++i) for (int j = i; j < N; ++j) a.scale[q++] = pre.D[i] * pre.D[j];
       for (int i = 0; i < N; ++i) a.scale[Op::T + i] = -pre.D[i];     // J = -sign(rho) df/dp, r = |rho|  =>  J r = -df/dp rho
       a.scale[Op::T + N] = 1.0;
-      return launch_op<Op, (Op::Q < 21 || std::is_same<Fam, FamGaussExpBkg>::value ? 3 : 2)>(s, a);
+      if constexpr (std::is_same<Fam, FamGaussExpBkg>::value) {
+        // tuning variants (rows per range-checked group x resident blocks per SM), SO_K2_VARIANT=0..3
+        const char* v = getenv("SO_K2_VARIANT");
+        const int var = v ? atoi(v) : 0;
+        auto relaunch = [&](auto optag, auto mbtag) -> int {
+          using Op2 = OpNormalEq<Fam, decltype(optag)::value>;
+          typename Op2::Args a2; a2.pre = a.pre;
+          for (int q2 = 0; q2 < Op2::Q; ++q2) a2.scale[q2] = a.scale[q2];
+          return launch_op<Op2, decltype(mbtag)::value>(s, a2);
+        };
+        if (var == 1) return relaunch(std::integral_constant<int, 2>(), std::integral_constant<int, 3>());
+        if (var == 2) return relaunch(std::integral_constant<int, 2>(), std::integral_constant<int, 2>());
+        if (var == 3) return relaunch(std::integral_constant<int, 1>(), std::integral_constant<int, 3>());
+        if (var == 4) return relaunch(std::integral_constant<int, 4>(), std::integral_constant<int, 3>());
+        return launch_op<Op, 2>(s, a);
+      }
+      return launch_op<Op, (Op::Q < 21 ? 3 : 2)>(s, a);
     }
     case kLine: {
       // batches of up to 8 step sizes per pass; longer schedules take several passes into consecutive out slots

@@ -1,6 +1,215 @@
-// so_wide.cu — placeholder; replaced below in this commit series
-#include "so_internal.h"
+// so_wide.cu — K1 (fused loss + gradient) and K4 (Hessian-vector) for the linear-predictor families.
+// See so_wide.cuh for the thread mapping.  Replaces (paths relative to
+// core/src/main/scala/com/github/bruneli/scalaopt/core/ and std-apps/.../learning/nnet/):
+//   K1  function/MSEFunction.scala:33-36,138-140 ; FFNeuralNetworkTrainer.scala:59-69,119-125
+//   K4  function/ObjectiveFunctionWithGradient.scala:41-47 ; FFNeuralNetworkTrainer.scala:76-80
+// Bytes per observation: 8 (f + 1); flops per observation ~ 4 f: HBM-bound.
+#include <algorithm>
+
+#include "so_wide.cuh"
+
 namespace so {
-size_t wide_partials_needed(Kind, int, int, int, int, int) { return 1; }
-int launch_wide(Kind, const Shard&, int, const double*, const double*, int, const double*, int, int) { return SO_EUNSUPPORTED; }
+namespace wide {
+namespace {
+
+enum { kModeLossGrad = 0, kModeHessVec = 1 };
+
+template <int FAM, int MODE, int L, int C, int V, bool PF>
+__global__ void __launch_bounds__(kThreads, 2)
+k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+       int want_grad, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+  extern __shared__ double smem[];
+  constexpr int RW = 32 / L, CV = C * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane & (L - 1), r = lane / L;
+  const int f = P.f, icpt = P.icpt;
+  const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
+  if (FAM == kLogistic) { exp_table_init(); __syncthreads(); }
+
+  double pj[CV], dj[CV], g[CV];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int col = (c * L + q) * V + v;
+      pj[c * V + v] = (col < f) ? P.p[icpt + col] : 0.0;
+      dj[c * V + v] = (MODE == kModeHessVec && col < f) ? P.d[icpt + col] : 0.0;
+      g[c * V + v] = 0.0;
+    }
+  const double p0 = icpt ? P.p[0] : 0.0, d0 = (icpt && MODE == kModeHessVec) ? P.d[0] : 0.0;
+  double g0 = 0.0, loss = 0.0;
+
+  const int64_t ngroups = (rows + RW - 1) / RW;
+  const int64_t gstr = (int64_t)gridDim.x * kWarps;
+  int64_t grp = (int64_t)blockIdx.x * kWarps + warp;
+
+  auto step = [&](const Frag<C, V>& fr, double yv, bool valid) {
+    double w;
+    if (MODE == kModeLossGrad) {
+      double dot = 0.0;
+#pragma unroll
+      for (int i = 0; i < CV; ++i) dot = fma(pj[i], fr.x[i], dot);
+      const double z = row_sum<L>(dot) + p0;
+      double l;
+      link<FAM>(z, yv, l, w);
+      if (!valid) { w = 0.0; l = 0.0; }
+      if (q == 0) { loss += l; g0 += w; }
+      if (!want_grad) return;
+    } else {
+      double dv = 0.0;
+#pragma unroll
+      for (int i = 0; i < CV; ++i) dv = fma(dj[i], fr.x[i], dv);
+      dv = row_sum<L>(dv) + d0;
+      if (FAM == kLogistic) {
+        double dot = 0.0;
+#pragma unroll
+        for (int i = 0; i < CV; ++i) dot = fma(pj[i], fr.x[i], dot);
+        const double z = row_sum<L>(dot) + p0;
+        w = curvature<FAM>(z) * dv;
+      } else {
+        w = dv;
+      }
+      if (!valid) w = 0.0;
+      if (q == 0) g0 += w;
+    }
+#pragma unroll
+    for (int i = 0; i < CV; ++i) g[i] = fma(w, fr.x[i], g[i]);
+  };
+
+  if (PF) {
+    // software pipeline: the next row group's loads are in flight while this one is reduced
+    Frag<C, V> cur, nxt;
+    double ycur = 0.0, ynxt = 0.0;
+    bool vcur = false, vnxt = false;
+    if (grp < ngroups) {
+      const int64_t row = grp * RW + r;
+      vcur = row < rows;
+      load_frag<L, C, V>(cur, X, row, vcur, f, q);
+      ycur = vcur ? ld_stream(y + row) : 0.0;
+    }
+    while (grp < ngroups) {
+      const int64_t ng = grp + gstr;
+      if (ng < ngroups) {
+        const int64_t row = ng * RW + r;
+        vnxt = row < rows;
+        load_frag<L, C, V>(nxt, X, row, vnxt, f, q);
+        ynxt = vnxt ? ld_stream(y + row) : 0.0;
+      }
+      step(cur, ycur, vcur);
+      cur = nxt; ycur = ynxt; vcur = vnxt;
+      grp = ng;
+    }
+  } else {
+    for (; grp < ngroups; grp += gstr) {
+      Frag<C, V> cur;
+      const int64_t row = grp * RW + r;
+      const bool valid = row < rows;
+      load_frag<L, C, V>(cur, X, row, valid, f, q);
+      const double yv = valid ? ld_stream(y + row) : 0.0;
+      step(cur, yv, valid);
+    }
+  }
+
+  // ---- block reduction in warp order -> per-block partials -> last block adds in block order ----
+  double* wsum = smem;                 // [kWarps][Q]
+  double* vals = smem + kWarps * Q;    // [Q]
+  const int base = (MODE == kModeLossGrad) ? 1 : 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const double s = col_sum<L>(g[c * V + v]);
+      const int col = (c * L + q) * V + v;
+      if (r == 0 && col < f) wsum[warp * Q + base + icpt + col] = s;
+    }
+  {
+    const double s0 = col_sum<L>(g0), sl = col_sum<L>(loss);
+    if (lane == 0) {
+      if (MODE == kModeLossGrad) wsum[warp * Q] = sl;
+      if (icpt) wsum[warp * Q + base] = s0;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Q; j += kThreads) {
+    double s = 0.0;
+    for (int w2 = 0; w2 < kWarps; ++w2) s += wsum[w2 * Q + j];
+    vals[j] = s;
+  }
+  __syncthreads();
+  finish_grid(vals, Q, (MODE == kModeLossGrad) ? 1 : 0, P.scale0, partials, out, ticket);
 }
+
+template <int FAM, int MODE, int L, int C, int V>
+int launch_lcv(const Shard& s, const Params& P, int want_grad) {
+  constexpr bool PF = (C <= 4);
+  auto kern = k_wide<FAM, MODE, L, C, V, PF>;
+  const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
+  const size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  constexpr int RW = 32 / L;
+  const int64_t ngroups = (s.rows + RW - 1) / RW;
+  const int64_t want = std::max<int64_t>(1, (ngroups + kWarps - 1) / kWarps);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
+  if ((size_t)grid * Q > s.partials_doubles || (size_t)Q > s.out_doubles) return SO_ENOMEM;
+  kern<<<grid, kThreads, smem, s.stream>>>(s.X, s.y, s.rows, P, want_grad, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+template <int FAM, int MODE>
+int launch_mapped(const Shard& s, const Params& P, int want_grad) {
+  const Mapping m = choose_mapping(P.f);
+#define SO_CASE(LL, CC, VV) if (m.L == LL && m.C == CC && m.V == VV) return launch_lcv<FAM, MODE, LL, CC, VV>(s, P, want_grad);
+  SO_CASE(1, 4, 1) SO_CASE(2, 4, 1) SO_CASE(4, 4, 1) SO_CASE(8, 4, 1) SO_CASE(16, 4, 1) SO_CASE(32, 4, 1)
+  SO_CASE(32, 8, 1) SO_CASE(32, 16, 1)
+  SO_CASE(1, 4, 2) SO_CASE(2, 4, 2) SO_CASE(4, 4, 2) SO_CASE(8, 4, 2) SO_CASE(16, 4, 2) SO_CASE(32, 4, 2)
+  SO_CASE(32, 8, 2)
+#undef SO_CASE
+  return SO_EUNSUPPORTED;
+}
+
+}  // namespace
+
+int launch_line(const Shard& s, int fam, const Params& P);                      // so_wide_line.cu
+int launch_gram(const Shard& s, int fam, const Params& P);                      // so_gram.cu
+size_t gram_partials_needed(int n, int f, int sm_count);                        // so_gram.cu
+
+}  // namespace wide
+
+size_t wide_partials_needed(Kind kind, int family, int n, int f, int k, int sm_count) {
+  (void)family;
+  if (kind == kNormalEq) return wide::gram_partials_needed(n, f, sm_count);
+  const size_t Q = (size_t)std::max(n + 1, 2 * std::max(k, 1));
+  return (size_t)sm_count * 8 * Q;    // at most 8 resident blocks per SM
+}
+
+int launch_wide(Kind kind, const Shard& s, int family, const double* p, const double* d, int n,
+                const double* alpha, int k, int want_grad) {
+  using namespace wide;
+  if (family != SO_FAMILY_LINEAR && family != SO_FAMILY_LINEAR_NOINT && family != SO_FAMILY_LOGISTIC) return SO_EUNSUPPORTED;
+  if (s.f < 1 || s.f > SO_MAX_FEATURES) return SO_EUNSUPPORTED;
+  Params P;
+  P.n = n; P.f = s.f; P.icpt = (family == SO_FAMILY_LINEAR_NOINT) ? 0 : 1; P.k = k;
+  if (n != s.f + P.icpt) return SO_EINVAL;
+  for (int i = 0; i < n; ++i) { P.p[i] = p[i]; P.d[i] = d ? d[i] : 0.0; }
+  for (int i = 0; i < k && i < SO_MAX_ALPHAS; ++i) P.alpha[i] = alpha[i];
+  const int fam = (family == SO_FAMILY_LOGISTIC) ? kLogistic : kLinear;
+  P.scale0 = (fam == kLinear) ? 0.5 : 1.0;
+  switch (kind) {
+    case kLossGrad:
+      return fam == kLinear ? launch_mapped<kLinear, kModeLossGrad>(s, P, want_grad)
+                            : launch_mapped<kLogistic, kModeLossGrad>(s, P, want_grad);
+    case kHessVec:
+      P.scale0 = 1.0;
+      return fam == kLinear ? launch_mapped<kLinear, kModeHessVec>(s, P, 1)
+                            : launch_mapped<kLogistic, kModeHessVec>(s, P, 1);
+    case kLine:
+      return launch_line(s, fam, P);
+    case kNormalEq:
+      return launch_gram(s, fam, P);
+  }
+  return SO_EINVAL;
+}
+
+}  // namespace so

@@ -1,0 +1,132 @@
+// so_wide.cuh — shared pieces of the linear-predictor ("wide row") kernels: linear regression with or
+// without intercept and logistic regression, f inputs per observation, row-major X[m x f] + y[m].
+//
+// Thread mapping ("L lanes per row"): a warp covers 32/L consecutive rows per step; lane (r, q) = (lane / L,
+// lane % L) holds columns (c*L + q)*V + v, c < C, v < V of row r in registers, loaded straight from global
+// memory with 64- or 128-bit streaming loads (V = 1 or 2).  Every 32-byte sector of X is requested exactly
+// once; a row's dot product is finished with log2(L) shuffle steps inside the row's L lanes, the per-row
+// scalar work (residual / sigmoid / loss) is done redundantly by those L lanes, and every lane accumulates
+// the gradient components of its own columns.  Nothing is staged through shared memory: the only reuse
+// of a row is register-level (dot product, then rank-1 update with the same registers).
+#pragma once
+#include "so_device.cuh"
+#include "so_internal.h"
+
+namespace so {
+namespace wide {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// parameter block passed by value in the kernel argument buffer (CUDA 12.1+: up to 32 KB of arguments)
+struct Params {
+  double p[SO_MAX_FEATURES + 1];
+  double d[SO_MAX_FEATURES + 1];
+  double alpha[SO_MAX_ALPHAS];
+  int n, f, icpt, k;
+  double scale0;    // factor applied to out[0] (loss sum) on the way out
+};
+
+enum { kLinear = 0, kLogistic = 1 };
+
+// loss and dloss/dz at linear predictor z.
+//   linear   : loss = (z - y)^2 (x 1/2 on the way out), w = z - y        MSEFunction.scala:45-48
+//   logistic : o = 1/(1+exp(-z)); loss = CE(o, y); w = o - y             FFNeuralNetwork.scala:80-88,174-179
+template <int FAM>
+__device__ __forceinline__ void link(double z, double y, double& loss, double& w) {
+  if (FAM == kLinear) {
+    w = z - y;
+    loss = w * w;
+  } else {
+    const double e = so_exp(-fabs(z));                  // in (0, 1]
+    const double inv = 1.0 / (1.0 + e);
+    const double o = (z >= 0.0) ? inv : e * inv;
+    w = o - y;
+    // -y log(o/y) - (1-y) log((1-o)/(1-y)) = softplus(-z) + (1-y) z + [y log y + (1-y) log(1-y)]
+    double l = log1p(e) + fmax(-z, 0.0) + (1.0 - y) * z;
+    if (y > 0.0 && y < 1.0) l += y * log(y) + (1.0 - y) * log(1.0 - y);
+    loss = l;
+  }
+}
+
+// curvature weight d2loss/dz2: 1 (linear) or o (1 - o) (logistic, LogisticFunction.derivative :26)
+template <int FAM>
+__device__ __forceinline__ double curvature(double z) {
+  if (FAM == kLinear) return 1.0;
+  const double e = so_exp(-fabs(z));
+  const double inv = 1.0 / (1.0 + e);
+  return e * inv * inv;
+}
+
+template <int L>
+__device__ __forceinline__ double row_sum(double v) {       // sum over the L lanes of a row
+#pragma unroll
+  for (int o = L / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int L>
+__device__ __forceinline__ double col_sum(double v) {       // sum over the 32/L rows held by a warp
+#pragma unroll
+  for (int o = L; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// registers of one lane for one row step
+template <int C, int V>
+struct Frag { double x[C * V]; };
+
+template <int L, int C, int V>
+__device__ __forceinline__ void load_frag(Frag<C, V>& fr, const double* __restrict__ X, int64_t row, bool valid,
+                                          int f, int q) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int col = (c * L + q) * V;
+    if (V == 2) {
+      double2 v = make_double2(0.0, 0.0);
+      if (valid && col < f) v = ld_stream2(reinterpret_cast<const double2*>(X + row * f + col));
+      fr.x[c * V] = v.x;
+      fr.x[c * V + 1] = v.y;
+    } else {
+      fr.x[c * V] = (valid && col < f) ? ld_stream(X + row * f + col) : 0.0;
+    }
+  }
+}
+
+// After the row loop: block-level sums in warp order, per-block partials, last block adds in block order.
+// vals[Q] in shared memory holds this block's sums; out[0 .. nscaled) is scaled by scale0.
+__device__ __forceinline__ void finish_grid(const double* vals, int Q, int nscaled, double scale0,
+                                            double* __restrict__ partials, double* __restrict__ out,
+                                            unsigned int* ticket) {
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) partials[(size_t)blockIdx.x * Q + q] = vals[q];
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+      double s = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * Q + q]);
+      out[q] = (q < nscaled) ? s * scale0 : s;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// lane-mapping choice for f inputs
+struct Mapping { int L, C, V; };
+inline Mapping choose_mapping(int f) {
+  Mapping m;
+  m.V = (f % 2 == 0) ? 2 : 1;
+  const int units = (f + m.V - 1) / m.V;      // V-wide column units per row
+  m.C = 4;
+  m.L = 1;
+  while (m.L < 32 && units > m.L * 4) m.L *= 2;
+  if (units > m.L * m.C) m.C = 8;
+  if (units > m.L * m.C) m.C = 16;
+  return m;
+}
+
+}  // namespace wide
+}  // namespace so

@@ -1,0 +1,163 @@
+// so_wide_line.cu — K3: k step sizes scored in ONE pass over the observations, linear-predictor families.
+// phi(alpha) = loss(p + alpha d), phi'(alpha) = grad(p + alpha d) . d  (variable/Point.scala:54-57 as asked for
+// by linesearch/StrongWolfe.scala:96-118,214-217).  For these families the linear predictor is affine in alpha:
+// z(alpha) = x~.p + alpha x~.d, so a row costs two dot products (4 f flops) whatever k is, and the k evaluations of
+// the scalar link are spread over the L lanes that share the row (lane q takes alpha_q, alpha_{q+L}, ...).
+#include <algorithm>
+
+#include "so_wide.cuh"
+
+namespace so {
+namespace wide {
+namespace {
+
+template <int FAM, int L, int C, int V, int KPL, bool PF>
+__global__ void __launch_bounds__(kThreads, 2)
+k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+            double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+  extern __shared__ double smem[];
+  constexpr int RW = 32 / L, CV = C * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane & (L - 1), r = lane / L;
+  const int f = P.f, icpt = P.icpt, k = P.k;
+  const int Q = 2 * k;
+  if (FAM == kLogistic) { exp_table_init(); __syncthreads(); }
+
+  double pj[CV], dj[CV];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int col = (c * L + q) * V + v;
+      pj[c * V + v] = (col < f) ? P.p[icpt + col] : 0.0;
+      dj[c * V + v] = (col < f) ? P.d[icpt + col] : 0.0;
+    }
+  const double p0 = icpt ? P.p[0] : 0.0, d0 = icpt ? P.d[0] : 0.0;
+  double al[KPL], phi[KPL], dphi[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int a = q + i * L;
+    al[i] = P.alpha[a < k ? a : k - 1];
+    phi[i] = 0.0; dphi[i] = 0.0;
+  }
+
+  const int64_t ngroups = (rows + RW - 1) / RW;
+  const int64_t gstr = (int64_t)gridDim.x * kWarps;
+  int64_t grp = (int64_t)blockIdx.x * kWarps + warp;
+
+  auto step = [&](const Frag<C, V>& fr, double yv, bool valid) {
+    double u = 0.0, dv = 0.0;
+#pragma unroll
+    for (int i = 0; i < CV; ++i) { u = fma(pj[i], fr.x[i], u); dv = fma(dj[i], fr.x[i], dv); }
+    u = row_sum<L>(u) + p0;
+    dv = row_sum<L>(dv) + d0;
+    if (!valid) return;              // lanes of one row agree on `valid`; no shuffles below
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      double l, w;
+      link<FAM>(fma(al[i], dv, u), yv, l, w);
+      phi[i] += l;
+      dphi[i] = fma(w, dv, dphi[i]);
+    }
+  };
+
+  if (PF) {
+    Frag<C, V> cur, nxt;
+    double ycur = 0.0, ynxt = 0.0;
+    bool vcur = false, vnxt = false;
+    if (grp < ngroups) {
+      const int64_t row = grp * RW + r;
+      vcur = row < rows;
+      load_frag<L, C, V>(cur, X, row, vcur, f, q);
+      ycur = vcur ? ld_stream(y + row) : 0.0;
+    }
+    while (grp < ngroups) {
+      const int64_t ng = grp + gstr;
+      if (ng < ngroups) {
+        const int64_t row = ng * RW + r;
+        vnxt = row < rows;
+        load_frag<L, C, V>(nxt, X, row, vnxt, f, q);
+        ynxt = vnxt ? ld_stream(y + row) : 0.0;
+      }
+      step(cur, ycur, vcur);
+      cur = nxt; ycur = ynxt; vcur = vnxt;
+      grp = ng;
+    }
+  } else {
+    for (; grp < ngroups; grp += gstr) {
+      Frag<C, V> cur;
+      const int64_t row = grp * RW + r;
+      const bool valid = row < rows;
+      load_frag<L, C, V>(cur, X, row, valid, f, q);
+      const double yv = valid ? ld_stream(y + row) : 0.0;
+      step(cur, yv, valid);
+    }
+  }
+
+  double* wsum = smem;                 // [kWarps][Q]
+  double* vals = smem + kWarps * Q;    // [Q]
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const double sp = col_sum<L>(phi[i]), sd = col_sum<L>(dphi[i]);
+    const int a = q + i * L;
+    if (r == 0 && a < k) { wsum[warp * Q + a] = sp; wsum[warp * Q + k + a] = sd; }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Q; j += kThreads) {
+    double s = 0.0;
+    for (int w2 = 0; w2 < kWarps; ++w2) s += wsum[w2 * Q + j];
+    vals[j] = s;
+  }
+  __syncthreads();
+  finish_grid(vals, Q, k, P.scale0, partials, out, ticket);
+}
+
+template <int FAM, int L, int C, int V, int KPL>
+int launch_one(const Shard& s, const Params& P) {
+  constexpr bool PF = (C <= 4);
+  auto kern = k_wide_line<FAM, L, C, V, KPL, PF>;
+  const int Q = 2 * P.k;
+  const size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  constexpr int RW = 32 / L;
+  const int64_t ngroups = (s.rows + RW - 1) / RW;
+  const int64_t want = std::max<int64_t>(1, (ngroups + kWarps - 1) / kWarps);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
+  if ((size_t)grid * Q > s.partials_doubles || (size_t)Q > s.out_doubles) return SO_ENOMEM;
+  kern<<<grid, kThreads, smem, s.stream>>>(s.X, s.y, s.rows, P, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+template <int FAM, int L, int C, int V>
+int launch_kpl(const Shard& s, const Params& P) {
+  const int kpl = (P.k + L - 1) / L;      // step sizes per lane
+  if (kpl <= 1) return launch_one<FAM, L, C, V, 1>(s, P);
+  if (kpl <= 2) return launch_one<FAM, L, C, V, 2>(s, P);
+  if (kpl <= 4) return launch_one<FAM, L, C, V, 4>(s, P);
+  if (kpl <= 8) return launch_one<FAM, L, C, V, 8>(s, P);
+  return SO_EINVAL;                        // the API layer sends at most 8 step sizes per pass
+}
+
+template <int FAM>
+int launch_mapped(const Shard& s, const Params& P) {
+  const Mapping m = choose_mapping(P.f);
+#define SO_CASE(LL, CC, VV) if (m.L == LL && m.C == CC && m.V == VV) return launch_kpl<FAM, LL, CC, VV>(s, P);
+  SO_CASE(1, 4, 1) SO_CASE(2, 4, 1) SO_CASE(4, 4, 1) SO_CASE(8, 4, 1) SO_CASE(16, 4, 1) SO_CASE(32, 4, 1)
+  SO_CASE(32, 8, 1) SO_CASE(32, 16, 1)
+  SO_CASE(1, 4, 2) SO_CASE(2, 4, 2) SO_CASE(4, 4, 2) SO_CASE(8, 4, 2) SO_CASE(16, 4, 2) SO_CASE(32, 4, 2)
+  SO_CASE(32, 8, 2)
+#undef SO_CASE
+  return SO_EUNSUPPORTED;
+}
+
+}  // namespace
+
+int launch_line(const Shard& s, int fam, const Params& P) {
+  if (P.k < 1 || P.k > 8) return SO_EINVAL;
+  return fam == kLinear ? launch_mapped<kLinear>(s, P) : launch_mapped<kLogistic>(s, P);
+}
+
+}  // namespace wide
+}  // namespace so
