@@ -1,10 +1,10 @@
 // so_scalar.cu — evaluation kernels for the single-input ("scalar t") model families:
 //   exponential decay, Gaussian peak, Gaussian peak + exponential background, polynomial.
 //
-// Data layout: t[m], y[m] as two fp64 device arrays (16 B per observation).  One thread owns whole
-// observations: each loop trip loads two 128-bit words of t and two of y (4 observations), coalesced,
-// streaming (ld.global.cs), evaluates the model and its parameter derivatives in registers and adds the
-// row's contribution to per-thread accumulators.  Nothing but the Q-double result ever leaves the SM.
+// Data layout: t[m], y[m] as two fp64 device arrays (16 B per observation).  Blocks stream chunks of 1024
+// observations through a shared-memory ring filled by TMA bulk copies; one thread owns whole observations
+// (4 per chunk), evaluates the model and its parameter derivatives in registers and adds the row's
+// contribution to per-thread accumulators.  Nothing but the Q-double result ever leaves the SM.
 //
 // The per-observation algebra replaces (reference paths relative to
 // core/src/main/scala/com/github/bruneli/scalaopt/core/):
@@ -50,6 +50,7 @@ struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarqua
     u[1] = t * ex[0];      // df/dp1 = p0 t e
     f = c.p0 * ex[0];
   }
+  __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) { return fma(-c.p0, ex[0], y); }
   __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
     h[0] = u[1] * d[1];
     h[1] = fma(c.p0 * t * u[1], d[1], u[1] * d[0]);
@@ -75,6 +76,7 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
     u[2] = u[1] * zz;      // df/dsigma = A g z^2 / sigma    = (2 A s) g zz^2
     f = c.A * ex[0];
   }
+  __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) { return fma(-c.A, ex[0], y); }
   __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
     const double z = (t - c.mu) * c.s, g = u[0], z2 = z * z;
     const double gs = g * c.s, Ags2 = c.A * gs * c.s;
@@ -108,6 +110,10 @@ struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),
     u[4] = t * ex[1];      // df/dlambda = -B t e
     f = fma(c.A, ex[0], c.B * ex[1]);
   }
+  // y - f in two FMAs (the accumulating kernels only need the residual)
+  __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) {
+    return fma(-c.B, ex[1], fma(-c.A, ex[0], y));
+  }
   __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
     const double z = (t - c.mu) * c.s, g = u[0], z2 = z * z;
     const double gs = g * c.s, Ags2 = c.A * gs * c.s;
@@ -134,6 +140,7 @@ struct FamPoly {       // f = sum_k p_k t^k
     for (int k = 1; k < N; ++k) { u[k] = u[k - 1] * t; s = fma(c.p[k], u[k], s); }
     f = s;
   }
+  __device__ static __forceinline__ double residual(const Pre&, double y, const double*, double f) { return y - f; }
   __device__ static __forceinline__ void hdir(const Pre&, double, const double (&)[N], const double*, double (&h)[N]) {
 #pragma unroll
     for (int k = 0; k < N; ++k) h[k] = 0.0;
@@ -151,7 +158,7 @@ struct OpLossGrad {
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
     Fam::finish(a.pre, t, ex, f, u);
-    const double rho = y - f;
+    const double rho = Fam::residual(a.pre, y, ex, f);
     acc[0] = fma(rho, rho, acc[0]);
     if constexpr (GRAD) {
 #pragma unroll
@@ -168,7 +175,7 @@ struct OpNormalEq {
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
     Fam::finish(a.pre, t, ex, f, u);
-    const double rho = y - f;
+    const double rho = Fam::residual(a.pre, y, ex, f);
     int q = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -193,7 +200,7 @@ struct OpLine {
     for (int k = 0; k < KB; ++k) {
       double f, u[N];
       Fam::finish(a.pre[k], t, ex + k * Fam::NE, f, u);
-      const double rho = y - f;
+      const double rho = Fam::residual(a.pre[k], y, ex + k * Fam::NE, f);
       double jd = 0.0;
 #pragma unroll
       for (int i = 0; i < N; ++i) jd = fma(a.dd[k][i], u[i], jd);
@@ -211,7 +218,7 @@ struct OpHessVec {
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N], h[N], J[N];
     Fam::finish(a.pre, t, ex, f, u);
-    const double rho = y - f;
+    const double rho = Fam::residual(a.pre, y, ex, f);
     double jd = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) { J[i] = a.pre.D[i] * u[i]; jd = fma(J[i], a.d[i], jd); }
@@ -275,68 +282,137 @@ __device__ __forceinline__ void process1(const typename Op::Args& args, double t
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The kernel: grid-stride over pairs of observations, 2 pairs (4 observations) in flight per thread.
+// The kernel.  A block walks chunks of 4 * TPB observations (grid-stride, fixed assignment, so the summation
+// order is fixed).  A chunk's t and y (2 x 8 KB at TPB = 256) are brought into a 4-deep shared-memory ring by
+// TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) issued by thread 0: the loads cost no
+// registers and no issue slots in the compute warps, and 32-48 KB per block are in flight whatever the
+// occupancy.  Consumers signal "stage read" on an `empty` mbarrier (one arrive per warp); only the producer
+// thread ever waits on it, and it refills a stage one iteration after the block consumed it, so there is no
+// block-wide barrier in the loop and the warps of a block are free to drift out of phase.
+// What ncu showed on the way here (profiles/):
+//   direct LDG.128                     FP64 pipe 63% busy, top stall long_scoreboard        r1_k2_v1_direct_ldg.json
+//   ring + __syncthreads per chunk     FP64 pipe 70% busy, 9% of samples on the barrier     r1_k2_v2_block_ring.json
+//   warp-private rings (1 KB copies)   slower than the block ring (54% vs 64% of roofline)  DESIGN.md
 // ---------------------------------------------------------------------------------------------------
-template <class Op, int MINBLOCKS>
-__global__ void __launch_bounds__(kThreads, MINBLOCKS)
+__host__ __device__ constexpr int stages_for(int rpt) { return rpt >= 8 ? 3 : 4; }
+constexpr size_t ring_bytes(int tpb, int rpt) { return (size_t)stages_for(rpt) * tpb * rpt * 16; }
+
+template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4>
+__global__ void __launch_bounds__(TPB, MINBLOCKS)
 k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t rows,
          const __grid_constant__ typename Op::Args args,
          double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  constexpr int Q = Op::Q;
-  __shared__ double s_red[(kThreads / 32) * Q];
-  if constexpr (Op::NEXP > 0) {
-    exp_table_init();
-    __syncthreads();
+  constexpr int Q = Op::Q, WPB = TPB / 32, kChunkRows = TPB * RPT, kStages = stages_for(RPT);
+  constexpr size_t kStageBytes = (size_t)kChunkRows * 16;
+  extern __shared__ __align__(128) unsigned char s_ring[];      // [kStages][ t: kChunkRows doubles | y: kChunkRows doubles ]
+  __shared__ double s_red[WPB * Q];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  // a slice may start on an odd row: peel it so that every bulk copy source is 16-byte aligned
+  const int head = (int)((reinterpret_cast<uintptr_t>(t) >> 3) & 1) && rows > 0 ? 1 : 0;
+  const double* tb = t + head;
+  const double* yb = y + head;
+  const int64_t body = (rows - head) & ~(int64_t)1;             // even number of rows handled through the ring
+  const int tail = (int)((rows - head) & 1);
+  const int64_t nchunks = (body + kChunkRows - 1) / kChunkRows;
+
+  auto issue = [&](int64_t chunk, int stage) {                  // one thread: arm the barrier, start both copies
+    const int64_t r0 = chunk * kChunkRows;
+    const uint32_t nr = (uint32_t)min((int64_t)kChunkRows, body - r0);
+    double* st = reinterpret_cast<double*>(s_ring + (size_t)stage * kStageBytes);
+    mbar_arrive_expect_tx(&s_full[stage], nr * 16u);
+    bulk_g2s(st, tb + r0, nr * 8u, &s_full[stage]);
+    bulk_g2s(st + kChunkRows, yb + r0, nr * 8u, &s_full[stage]);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WPB); }
+    mbar_fence_init();
+  }
+  if constexpr (Op::NEXP > 0) exp_table_init();
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const int64_t c = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (c < nchunks) issue(c, s);
+    }
   }
 
   double acc[Q];
 #pragma unroll
   for (int q = 0; q < Q; ++q) acc[q] = 0.0;
 
-  // a slice may start on an odd row: peel it so the 128-bit loads stay aligned
-  const int head = (int)((reinterpret_cast<uintptr_t>(t) >> 3) & 1) && rows > 0 ? 1 : 0;
-  const double2* __restrict__ t2 = reinterpret_cast<const double2*>(t + head);
-  const double2* __restrict__ y2 = reinterpret_cast<const double2*>(y + head);
-  const int64_t npairs = (rows - head) >> 1;
-  const int tail = (int)((rows - head) & 1);
-  const int64_t gtid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const int64_t gstride = (int64_t)gridDim.x * kThreads;
-
-  int64_t i = gtid;
-  for (; i + gstride < npairs; i += 2 * gstride) {
-    const double2 ta = ld_stream2(t2 + i), ya = ld_stream2(y2 + i);
-    const double2 tb = ld_stream2(t2 + i + gstride), yb = ld_stream2(y2 + i + gstride);
-    process4<Op>(args, ta, ya, tb, yb, acc);
+  int it = 0;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+    const int stage = it % kStages;
+    mbar_wait(&s_full[stage], (uint32_t)((it / kStages) & 1));
+    const double* st = reinterpret_cast<const double*>(s_ring + (size_t)stage * kStageBytes);
+    const int npairs = (int)(min((int64_t)kChunkRows, body - chunk * kChunkRows) >> 1);
+    // thread tid owns pairs tid + j*TPB of the chunk: conflict-free LDS.128
+    double2 tv[RPT / 2], yv[RPT / 2];
+#pragma unroll
+    for (int j = 0; j < RPT / 2; ++j) {
+      tv[j] = reinterpret_cast<const double2*>(st)[tid + j * TPB];
+      yv[j] = reinterpret_cast<const double2*>(st + kChunkRows)[tid + j * TPB];
+    }
+    if (MODE == 0) {
+      __syncthreads();                                          // every thread holds its rows: the stage can be refilled
+      if (tid == 0) {
+        const int64_t nc = chunk + (int64_t)kStages * gridDim.x;
+        if (nc < nchunks) issue(nc, stage);
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);             // this warp holds its rows of `stage`
+      if (tid == 0 && it >= 1) {
+        // refill the stage the block consumed in the previous iteration (its readers are done or nearly so)
+        const int ps = (it - 1) % kStages;
+        const int64_t nc = chunk + (int64_t)(kStages - 1) * gridDim.x;
+        if (nc < nchunks) {
+          mbar_wait(&s_empty[ps], (uint32_t)(((it - 1) / kStages) & 1));
+          issue(nc, ps);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT / 2; j += 2) {
+      if (tid + (j + 1) * TPB < npairs) {
+        process4<Op>(args, tv[j], yv[j], tv[j + 1], yv[j + 1], acc);
+      } else {
+        if (tid + j * TPB < npairs) { process1<Op>(args, tv[j].x, yv[j].x, acc); process1<Op>(args, tv[j].y, yv[j].y, acc); }
+      }
+    }
   }
-  if (i < npairs) {
-    const double2 ta = ld_stream2(t2 + i), ya = ld_stream2(y2 + i);
-    process1<Op>(args, ta.x, ya.x, acc);
-    process1<Op>(args, ta.y, ya.y, acc);
-  }
-  if (gtid == 0 && head) process1<Op>(args, t[0], y[0], acc);
-  if (gtid == gstride - 1 && tail) process1<Op>(args, t[rows - 1], y[rows - 1], acc);
+  if (blockIdx.x == 0 && tid == 0 && head) process1<Op>(args, t[0], y[0], acc);
+  if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op>(args, t[rows - 1], y[rows - 1], acc);
 
   grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket);
 }
 
-int grid_for(const void* kernel, const Shard& s) {
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-  if (per_sm < 1) per_sm = 1;
-  int64_t want = (s.rows / 2 + kThreads - 1) / kThreads;
-  int64_t cap = (int64_t)per_sm * s.sm_count;
-  if (want < 1) want = 1;
-  return (int)std::min<int64_t>(want, cap);
+template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4>
+int launch_op_cfg(const Shard& s, const typename Op::Args& args) {
+  auto kern = k_scalar<Op, TPB, MINBLOCKS, MODE, RPT>;
+  constexpr size_t smem = ring_bytes(TPB, RPT);
+  static int per_sm = 0;             // per instantiation
+  if (per_sm == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SO_ECUDA;
+    int v = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, TPB, smem);
+    per_sm = v < 1 ? 1 : v;
+  }
+  constexpr int kChunkRows = TPB * RPT;
+  const int64_t want = std::max<int64_t>(1, (s.rows + kChunkRows - 1) / kChunkRows);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
+  if ((size_t)grid * Op::Q > s.partials_doubles || (size_t)Op::Q > s.out_doubles) return SO_ENOMEM;
+  kern<<<grid, TPB, smem, s.stream>>>(s.X, s.y, s.rows, args, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
 }
 
 template <class Op, int MINBLOCKS>
-int launch_op(const Shard& s, const typename Op::Args& args) {
-  auto kern = k_scalar<Op, MINBLOCKS>;
-  const int grid = grid_for(reinterpret_cast<const void*>(kern), s);
-  if ((size_t)grid * Op::Q > s.partials_doubles || (size_t)Op::Q > s.out_doubles) return SO_ENOMEM;
-  kern<<<grid, kThreads, 0, s.stream>>>(s.X, s.y, s.rows, args, s.partials, s.out, s.ticket);
-  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
-}
+int launch_op(const Shard& s, const typename Op::Args& args) { return launch_op_cfg<Op, kThreads, MINBLOCKS, 0, (MINBLOCKS <= 2 ? 8 : 4)>(s, args); }
 
 template <class Fam>
 int launch_family(Kind kind, const Shard& s, const double* p, const double* d, const double* alpha, int k, int want_grad) {
@@ -363,20 +439,23 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       for (int i = 0; i < N; ++i) a.scale[Op::T + i] = -pre.D[i];     // J = -sign(rho) df/dp, r = |rho|  =>  J r = -df/dp rho
       a.scale[Op::T + N] = 1.0;
       if constexpr (std::is_same<Fam, FamGaussExpBkg>::value) {
-        // tuning variants (rows per range-checked group x resident blocks per SM), SO_K2_VARIANT=0..3
+        // tuning variants: rows per range-checked group x threads per block x resident blocks per SM (SO_K2_VARIANT)
         const char* v = getenv("SO_K2_VARIANT");
         const int var = v ? atoi(v) : 0;
-        auto relaunch = [&](auto optag, auto mbtag) -> int {
-          using Op2 = OpNormalEq<Fam, decltype(optag)::value>;
+        auto relaunch = [&](auto gtag, auto modetag, auto rpttag) -> int {
+          using Op2 = OpNormalEq<Fam, decltype(gtag)::value>;
           typename Op2::Args a2; a2.pre = a.pre;
           for (int q2 = 0; q2 < Op2::Q; ++q2) a2.scale[q2] = a.scale[q2];
-          return launch_op<Op2, decltype(mbtag)::value>(s, a2);
+          return launch_op_cfg<Op2, 256, 2, decltype(modetag)::value, decltype(rpttag)::value>(s, a2);
         };
-        if (var == 1) return relaunch(std::integral_constant<int, 2>(), std::integral_constant<int, 3>());
-        if (var == 2) return relaunch(std::integral_constant<int, 2>(), std::integral_constant<int, 2>());
-        if (var == 3) return relaunch(std::integral_constant<int, 1>(), std::integral_constant<int, 3>());
-        if (var == 4) return relaunch(std::integral_constant<int, 4>(), std::integral_constant<int, 3>());
-        return launch_op<Op, 2>(s, a);
+        using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>; using I8 = std::integral_constant<int, 8>;
+        if (var == 1) return relaunch(I4(), I1(), I4());   // empty-mbarrier ring
+        if (var == 2) return relaunch(I4(), I0(), I8());   // __syncthreads ring, 8 rows per thread per chunk
+        if (var == 3) return relaunch(I4(), I1(), I8());   // empty-mbarrier ring, 8 rows per thread per chunk
+        if (var == 4) return relaunch(I2(), I0(), I4());   // 2 rows per range-checked group
+        if (var == 5) return relaunch(I2(), I0(), I8());
+        return relaunch(I2(), I0(), I8());
       }
       return launch_op<Op, (Op::Q < 21 ? 3 : 2)>(s, a);
     }

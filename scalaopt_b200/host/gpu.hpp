@@ -1,0 +1,222 @@
+// gpu.hpp — the GPU-backed data set and objective functions: what a user of the reference switches to.
+//
+//   GpuDataSet      extends DataSet[DataPoint]   (DataSet.scala:27-145)  observations resident in HBM
+//   GpuMSEFunction  extends MSEFunction          (function/MSEFunction.scala:12-76; precedent for a custom
+//                   MSEFunction with analytic derivatives: std-apps/.../nnet/FFNeuralNetworkTrainer.scala:36-144)
+//
+// Every evaluation is one call into libscalaopt_cuda.so (include/scalaopt_cuda.h); nothing is computed on
+// the host except O(n^3) algebra on the n x n results.  There is no CPU fallback: closure-taking DataSet methods
+// stream a bounded number of rows back or throw UnsupportedOperationException.
+#pragma once
+#include <cstring>
+#include <list>
+
+#include "../../include/scalaopt_cuda.h"
+#include "scalaopt_host.hpp"
+
+namespace scalaopt {
+
+struct GpuError : std::runtime_error { int code; GpuError(int c, const std::string& m) : std::runtime_error(m), code(c) {} };
+
+class GpuDataSet : public DataSet<DataPoint> {
+ public:
+  static constexpr int64_t kCollectLimit = 1 << 20;      // rows a closure-taking method may stream back
+  so_ctx* ctx; so_dataset* ds; int f; bool owns;
+  GpuDataSet(so_ctx* c, so_dataset* d, int f_, bool owns_ = false) : ctx(c), ds(d), f(f_), owns(owns_) {}
+  ~GpuDataSet() override { if (owns && ds) so_dataset_free(ds); }
+  void check(int rc) const { if (rc != SO_OK) throw GpuError(rc, so_last_error(ctx)); }
+
+  int64_t size() const override { int64_t m = 0; check(so_dataset_size(ds, &m)); return m; }                 // DataSet.scala:126
+  DataPoint head() const override { DataPoint p; p.x.resize(f); check(so_dataset_head(ds, p.x.data(), &p.y)); return p; }   // :82
+  std::vector<DataPoint> collect() const override {                                                           // :51, bounded
+    const int64_t m = size();
+    if (m > kCollectLimit) throw UnsupportedOperationException("GpuDataSet.collect: data set too large to materialise on the host");
+    std::vector<double> X((size_t)m * f), y((size_t)m);
+    check(so_dataset_read(ds, 0, m, X.data(), y.data()));
+    std::vector<DataPoint> out((size_t)m);
+    for (int64_t i = 0; i < m; ++i) { out[i].x.assign(X.begin() + i * f, X.begin() + (i + 1) * f); out[i].y = y[i]; }
+    return out;
+  }
+  // closures cannot run on the device: bounded host streaming or an exception (no silent CPU evaluation path)
+  void aggregate_raw(const std::function<void(const DataPoint&)>& seqop) const override { for (const DataPoint& p : collect()) seqop(p); }
+  void foreach (const std::function<void(const DataPoint&)>& fn) const override { for (const DataPoint& p : collect()) fn(p); }
+  std::shared_ptr<DataSet<DataPoint>> filter(const std::function<bool(const DataPoint&)>& p) const override {
+    return SeqDataSet<DataPoint>(collect()).filter(p);
+  }
+  std::shared_ptr<DataSet<DataPoint>> map(const std::function<DataPoint(const DataPoint&)>& fn) const override {
+    return SeqDataSet<DataPoint>(collect()).map(fn);
+  }
+  std::shared_ptr<DataSet<DataPoint>> concat(const DataSet<DataPoint>& that) const override {                // ++ :36
+    const auto rows = that.collect();
+    const int64_t m0 = size(), m1 = (int64_t)rows.size();
+    so_dataset* nd = nullptr;
+    check(so_dataset_create(ctx, m0 + m1, f, &nd));
+    auto out = std::make_shared<GpuDataSet>(ctx, nd, f, true);
+    const int64_t CH = 1 << 20;
+    std::vector<double> X, y;
+    for (int64_t b = 0; b < m0; b += CH) {
+      const int64_t e = std::min(m0, b + CH);
+      X.resize((size_t)(e - b) * f); y.resize((size_t)(e - b));
+      check(so_dataset_read(ds, b, e - b, X.data(), y.data()));
+      check(so_dataset_append(nd, X.data(), y.data(), e - b));
+    }
+    X.resize((size_t)m1 * f); y.resize((size_t)m1);
+    for (int64_t i = 0; i < m1; ++i) { std::copy(rows[i].x.begin(), rows[i].x.end(), X.begin() + i * f); y[i] = rows[i].y; }
+    if (m1) check(so_dataset_append(nd, X.data(), y.data(), m1));
+    return out;
+  }
+};
+
+// Counters of what the objective asked the device to do (the reference has no metrics).
+struct GpuCounters {
+  int64_t loss_calls = 0, gradient_calls = 0, dirder_calls = 0, hessvec_calls = 0, jacobian_calls = 0;   // requests from the optimizer
+  int64_t k1_passes = 0, k2_passes = 0, k3_passes = 0, k4_passes = 0;                                     // passes over the data
+  int64_t cache_hits = 0, line_hits = 0;
+};
+
+class GpuMSEFunction : public MSEFunction {
+ public:
+  std::shared_ptr<GpuDataSet> data; int family; int n;
+  int line_batch = 3;               // step sizes scored per K3 pass once a line search needs a second trial point
+  mutable GpuCounters counters;
+  GpuMSEFunction(std::shared_ptr<GpuDataSet> d, int family_, int n_) : data(std::move(d)), family(family_), n(n_) {}
+
+  // ---- ObjectiveFunction.apply: loss at x (MSEFunction.scala:33-36 = sum r^2/2 / m; logistic: mean cross-entropy) ----
+  double apply(const Vec& x) const override {
+    counters.loss_calls++;
+    if (const Entry* e = find(x)) { counters.cache_hits++; return e->loss; }
+    if (const LineEntry* le = find_on_ray(x)) { counters.line_hits++; return le->phi; }
+    if (on_ray_beta(x)) return score_ray(x).phi;
+    if (loss_only_mode) {
+      double loss = 0.0;
+      check(so_eval_loss_grad(data->ds, family, x.data(), n, &loss, nullptr));
+      counters.k1_passes++;
+      remember(x, loss, nullptr);
+      return loss;
+    }
+    return fused(x).loss;
+  }
+  Vec gradient(const Vec& x) const override {
+    counters.gradient_calls++;
+    if (const Entry* e = find(x)) if (e->has_grad) { counters.cache_hits++; return e->grad; }
+    return fused(x).grad;
+  }
+  // dirder = gradient(x) dot d (ObjectiveFunctionWithGradient.scala:37-39); also tells the objective which ray
+  // the line search is walking, so that further trial points on it can be scored in batches (K3)
+  double dirder(const Vec& x, const Vec& d) const override {
+    counters.dirder_calls++;
+    if (const Entry* e = find(x)) if (e->has_grad) { counters.cache_hits++; note_ray(x, d); return dot(e->grad, d); }
+    if (same_dir(d)) if (const LineEntry* le = find_on_ray(x)) { counters.line_hits++; return le->dphi; }
+    const Vec g = fused(x).grad;
+    note_ray(x, d);
+    return dot(g, d);
+  }
+  Vec dirHessian(const Vec& x, const Vec& d) const override {   // exact product (K4), not the 2-gradient finite difference
+    counters.hessvec_calls++;
+    Vec out(n);
+    check(so_eval_hess_vec(data->ds, family, x.data(), d.data(), n, out.data()));
+    counters.k4_passes++;
+    return out;
+  }
+  // The (n+1)-row system with the same R, Q^T b, column norms and ||b|| (up to row signs) as the m-row
+  // Jacobian/residual matrix of MSEFunction.scala:132-136: rows (R_chol[i,:] | q_i), then (0 | rho).
+  std::shared_ptr<DataSet<AugmentedRow>> jacobianAndResidualsMatrix(const Vec& p) const override {
+    counters.jacobian_calls++;
+    loss_only_mode = true;          // Levenberg-Marquardt only ever asks for the loss between Jacobians
+    std::vector<double> JtJ((size_t)n * n), Jtr(n);
+    double rtr = 0.0;
+    check(so_eval_normal_eq(data->ds, family, p.data(), n, JtJ.data(), Jtr.data(), &rtr));
+    counters.k2_passes++;
+    if (family != SO_FAMILY_LOGISTIC) { int64_t m = data->size(); remember(p, rtr / (2.0 * (double)m), nullptr); }
+    // Cholesky JtJ = R^T R (upper R), q = R^-T Jtr, rho = sqrt(max(0, rtr - q.q)); O(n^3) on the host
+    std::vector<Vec> R(n, Vec(n, 0.0));
+    Vec q(n, 0.0);
+    for (int i = 0; i < n; ++i) {
+      double dsum = JtJ[(size_t)i * n + i];
+      for (int k = 0; k < i; ++k) dsum -= R[k][i] * R[k][i];
+      if (!(dsum > 0.0)) continue;                               // rank-deficient column: zero row -> rDiag = 0 downstream
+      const double rii = std::sqrt(dsum);
+      R[i][i] = rii;
+      for (int j = i + 1; j < n; ++j) {
+        double s = JtJ[(size_t)i * n + j];
+        for (int k = 0; k < i; ++k) s -= R[k][i] * R[k][j];
+        R[i][j] = s / rii;
+      }
+      double s = Jtr[i];
+      for (int k = 0; k < i; ++k) s -= R[k][i] * q[k];
+      q[i] = s / rii;
+    }
+    const double rho = std::sqrt(std::max(0.0, rtr - inner(q, q)));
+    std::vector<AugmentedRow> rows;
+    for (int i = 0; i < n; ++i) rows.emplace_back(R[i], q[i], (int64_t)i);
+    rows.emplace_back(Vec(n, 0.0), rho, (int64_t)n);
+    return std::make_shared<SeqDataSet<AugmentedRow>>(std::move(rows));
+  }
+
+ private:
+  struct Entry { Vec x; double loss; bool has_grad; Vec grad; };
+  struct LineEntry { double beta, phi, dphi; };
+  mutable std::list<Entry> cache;                 // most recent first; keyed on the bit pattern of x
+  mutable bool loss_only_mode = false;
+  mutable bool have_ray = false;
+  mutable Vec ray_origin, ray_d;
+  mutable int ray_trials = 0;                      // distinct points evaluated on the current ray
+  mutable std::vector<LineEntry> line;
+
+  void check(int rc) const { if (rc != SO_OK) throw GpuError(rc, so_last_error(data->ctx)); }
+  static bool same_bits(const Vec& a, const Vec& b) { return a.size() == b.size() && std::memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0; }
+  const Entry* find(const Vec& x) const { for (const Entry& e : cache) if (same_bits(e.x, x)) return &e; return nullptr; }
+  void remember(const Vec& x, double loss, const Vec* g) const {
+    for (Entry& e : cache) if (same_bits(e.x, x)) { e.loss = loss; if (g) { e.has_grad = true; e.grad = *g; } return; }
+    cache.push_front(Entry{x, loss, g != nullptr, g ? *g : Vec()});
+    if (cache.size() > 8) cache.pop_back();
+  }
+  const Entry& fused(const Vec& x) const {          // K1: loss and gradient in one pass
+    double loss = 0.0; Vec g(n);
+    check(so_eval_loss_grad(data->ds, family, x.data(), n, &loss, g.data()));
+    counters.k1_passes++;
+    remember(x, loss, &g);
+    if (on_ray_beta(x)) ray_trials++;
+    return *find(x);
+  }
+  bool same_dir(const Vec& d) const { return have_ray && same_bits(d, ray_d); }
+  void note_ray(const Vec& x, const Vec& d) const {
+    if (same_dir(d)) return;
+    have_ray = true; ray_origin = x; ray_d = d; ray_trials = 1; line.clear();
+  }
+  // x = origin + beta d ?  (tolerance: a few ulp of the point's magnitude)
+  std::optional<double> on_ray_beta(const Vec& x) const {
+    if (!have_ray) return std::nullopt;
+    const double dd = dot(ray_d, ray_d);
+    if (!(dd > 0.0)) return std::nullopt;
+    Vec diff = sub(x, ray_origin);
+    const double beta = dot(diff, ray_d) / dd;
+    double err = 0.0, scale = 0.0;
+    for (int i = 0; i < n; ++i) { err = std::max(err, std::fabs(diff[i] - beta * ray_d[i])); scale = std::max(scale, std::fabs(x[i]) + std::fabs(beta * ray_d[i])); }
+    if (err > 64.0 * std::numeric_limits<double>::epsilon() * std::max(scale, 1e-300)) return std::nullopt;
+    return beta;
+  }
+  const LineEntry* find_on_ray(const Vec& x) const {
+    if (line.empty()) return nullptr;
+    const auto beta = on_ray_beta(x);
+    if (!beta) return nullptr;
+    for (const LineEntry& le : line) if (std::fabs(le.beta - *beta) <= 1e-12 * std::max(1.0, std::fabs(*beta))) return &le;
+    return nullptr;
+  }
+  // second and later trial points of a line search: one K3 pass scores this step size together with the
+  // continuation of the bracket schedule alpha <- c3 alpha (StrongWolfe.scala:114), i.e. beta <- 2 beta + 1
+  const LineEntry& score_ray(const Vec& x) const {
+    const double beta = *on_ray_beta(x);
+    std::vector<double> al{beta};
+    double b = beta;
+    for (int i = 1; i < line_batch && ray_trials >= 1; ++i) { b = 2.0 * b + 1.0; al.push_back(b); }
+    std::vector<double> phi(al.size()), dphi(al.size());
+    check(so_eval_line(data->ds, family, ray_origin.data(), ray_d.data(), n, al.data(), (int)al.size(), phi.data(), dphi.data()));
+    counters.k3_passes++;
+    for (size_t i = 0; i < al.size(); ++i) line.push_back(LineEntry{al[i], phi[i], dphi[i]});
+    ray_trials++;
+    return line[line.size() - al.size()];
+  }
+};
+
+}  // namespace scalaopt
