@@ -1,0 +1,61 @@
+"""Multi-GPU parity (needs >= 2 visible B200s; skipped otherwise): one process driving G GPUs through so_init(G),
+row shards + NCCL all-reduce, against the CPU oracle on the whole data set."""
+import numpy as np
+import pytest
+
+from parity import assert_gram, assert_loss, assert_vec
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+@pytest.mark.parametrize("m", [100_003, 7])
+def test_sharded_evaluation_matches_oracle(native, oracle, G, m):
+    if _ngpus() < G:
+        pytest.skip(f"needs {G} GPUs")
+    fam = oracle.GAUSS_EXPBKG
+    truth = np.array([2.0, 0.5, 0.05, 1.0, 3.0])
+    X, y = oracle.generate(fam, m, 1, truth, noise_sigma=0.05, total_rows=max(m, 8))
+    with native.Context(G) as ctx:
+        ds = native.Dataset(ctx, m, 1).append(X, y)
+        assert ds.size() == m
+        Xr, yr = ds.read(0, m)
+        np.testing.assert_array_equal(Xr, X); np.testing.assert_array_equal(yr, y)
+        p = truth * 1.1
+        loss, grad = ds.loss_grad(fam, p)
+        assert_loss(loss, oracle.apply(fam, X, y, p))
+        assert_vec(grad, oracle.gradient(fam, X, y, p))
+        JtJ, Jtr, rtr = ds.normal_eq(fam, p)
+        JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p)
+        assert_gram(JtJ, JtJ_o); assert_vec(Jtr, Jtr_o, what="Jtr"); assert_loss(rtr, rtr_o)
+        d = -grad
+        phi, dphi = ds.line(fam, p, d, [0.0, 1.0, 2.0])
+        phi_o, dphi_o = oracle.line(fam, X, y, p, d, [0.0, 1.0, 2.0])
+        assert_vec(phi, phi_o, what="phi"); assert_vec(dphi, dphi_o, rtol=1e-11, what="dphi")
+        assert_vec(ds.hess_vec(fam, p, d), oracle.hess_vec(fam, X, y, p, d), rtol=1e-11, what="Hd")
+        # device-side generation across shards continues the global row counter
+        ds2 = native.Dataset(ctx, m, 1).generate(fam, truth, noise_sigma=0.05)
+        X2, _ = ds2.read(0, m)
+        np.testing.assert_array_equal(X2[:, 0], (np.arange(m) + 0.5) / m)
+        ds2.free(); ds.free()
+
+
+@pytest.mark.parametrize("G", [2])
+def test_sharded_wide_family(native, oracle, G):
+    if _ngpus() < G:
+        pytest.skip(f"needs {G} GPUs")
+    fam = oracle.LOGISTIC
+    truth = np.array([(((j % 7) - 3) / 4.0) for j in range(33)])
+    X, y = oracle.generate(fam, 30_001, 32, truth)
+    with native.Context(G) as ctx:
+        ds = native.Dataset(ctx, 30_001, 32).append(X, y)
+        p = truth * 0.9
+        loss, grad = ds.loss_grad(fam, p)
+        assert_loss(loss, oracle.apply(fam, X, y, p))
+        assert_vec(grad, oracle.gradient(fam, X, y, p))
+        ds.free()
