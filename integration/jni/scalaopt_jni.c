@@ -1,0 +1,99 @@
+/*
+ * scalaopt_jni.c — JNI glue between com.github.bruneli.scalaopt.gpu.NativeLib and libscalaopt_cuda.so.
+ * Compiled only where a JDK is present (this image has none): UNVERIFIED.
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include scalaopt_jni.c \
+ *       -L../../scalaopt_b200 -lscalaopt_cuda -o libscalaopt_jni.so
+ */
+#if defined(__has_include)
+#if __has_include(<jni.h>)
+#include <jni.h>
+#include "scalaopt_cuda.h"
+
+#define JFN(name) Java_com_github_bruneli_scalaopt_gpu_NativeLib_00024_##name
+
+JNIEXPORT jlong JNICALL JFN(init)(JNIEnv* e, jobject o, jint ngpus, jintArray ids) {
+  so_ctx* ctx = 0;
+  jint* p = ids ? (*e)->GetIntArrayElements(e, ids, 0) : 0;
+  int rc = so_init(ngpus, (const int*)p, &ctx);
+  if (p) (*e)->ReleaseIntArrayElements(e, ids, p, JNI_ABORT);
+  return rc == SO_OK ? (jlong)(intptr_t)ctx : 0;
+}
+JNIEXPORT void JNICALL JFN(shutdown)(JNIEnv* e, jobject o, jlong ctx) { so_shutdown((so_ctx*)(intptr_t)ctx); }
+JNIEXPORT jstring JNICALL JFN(lastError)(JNIEnv* e, jobject o, jlong ctx) {
+  return (*e)->NewStringUTF(e, so_last_error((so_ctx*)(intptr_t)ctx));
+}
+JNIEXPORT jlong JNICALL JFN(datasetCreate)(JNIEnv* e, jobject o, jlong ctx, jlong m, jint f) {
+  so_dataset* ds = 0;
+  return so_dataset_create((so_ctx*)(intptr_t)ctx, m, f, &ds) == SO_OK ? (jlong)(intptr_t)ds : 0;
+}
+JNIEXPORT jint JNICALL JFN(datasetAppend)(JNIEnv* e, jobject o, jlong ds, jdoubleArray x, jdoubleArray y, jlong rows) {
+  double* px = (*e)->GetPrimitiveArrayCritical(e, x, 0);
+  double* py = (*e)->GetPrimitiveArrayCritical(e, y, 0);
+  int rc = so_dataset_append((so_dataset*)(intptr_t)ds, px, py, rows);
+  (*e)->ReleasePrimitiveArrayCritical(e, y, py, JNI_ABORT);
+  (*e)->ReleasePrimitiveArrayCritical(e, x, px, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jint JNICALL JFN(datasetRead)(JNIEnv* e, jobject o, jlong ds, jlong b, jlong rows, jdoubleArray x, jdoubleArray y) {
+  double* px = (*e)->GetPrimitiveArrayCritical(e, x, 0);
+  double* py = (*e)->GetPrimitiveArrayCritical(e, y, 0);
+  int rc = so_dataset_read((so_dataset*)(intptr_t)ds, b, rows, px, py);
+  (*e)->ReleasePrimitiveArrayCritical(e, y, py, 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, x, px, 0);
+  return rc;
+}
+JNIEXPORT jlong JNICALL JFN(datasetSize)(JNIEnv* e, jobject o, jlong ds) {
+  int64_t m = -1; so_dataset_size((so_dataset*)(intptr_t)ds, &m); return m;
+}
+JNIEXPORT void JNICALL JFN(datasetFree)(JNIEnv* e, jobject o, jlong ds) { so_dataset_free((so_dataset*)(intptr_t)ds); }
+JNIEXPORT jint JNICALL JFN(evalLossGrad)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray out, jboolean g) {
+  jsize n = (*e)->GetArrayLength(e, p);
+  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  int rc = so_eval_loss_grad((so_dataset*)(intptr_t)ds, fam, pp, n, po, g ? po + 1 : 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jint JNICALL JFN(evalNormalEq)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray out) {
+  jsize n = (*e)->GetArrayLength(e, p);
+  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  int rc = so_eval_normal_eq((so_dataset*)(intptr_t)ds, fam, pp, n, po, po + n * n, po + n * n + n);
+  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jint JNICALL JFN(evalLine)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray d, jdoubleArray a, jdoubleArray out) {
+  jsize n = (*e)->GetArrayLength(e, p), k = (*e)->GetArrayLength(e, a);
+  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  double* pd = (*e)->GetPrimitiveArrayCritical(e, d, 0);
+  double* pa = (*e)->GetPrimitiveArrayCritical(e, a, 0);
+  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  int rc = so_eval_line((so_dataset*)(intptr_t)ds, fam, pp, pd, n, pa, k, po, po + k);
+  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, a, pa, JNI_ABORT);
+  (*e)->ReleasePrimitiveArrayCritical(e, d, pd, JNI_ABORT);
+  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jint JNICALL JFN(evalHessVec)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray d, jdoubleArray out) {
+  jsize n = (*e)->GetArrayLength(e, p);
+  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  double* pd = (*e)->GetPrimitiveArrayCritical(e, d, 0);
+  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  int rc = so_eval_hess_vec((so_dataset*)(intptr_t)ds, fam, pp, pd, n, po);
+  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, d, pd, JNI_ABORT);
+  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jint JNICALL JFN(datasetGenerate)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jlong seed, jdouble sigma, jlong off) {
+  jsize n = (*e)->GetArrayLength(e, p);
+  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  int rc = so_dataset_generate((so_dataset*)(intptr_t)ds, fam, pp, n, (uint64_t)seed, sigma, off);
+  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  return rc;
+}
+#endif
+#endif

@@ -396,13 +396,17 @@ template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4>
 int launch_op_cfg(const Shard& s, const typename Op::Args& args) {
   auto kern = k_scalar<Op, TPB, MINBLOCKS, MODE, RPT>;
   constexpr size_t smem = ring_bytes(TPB, RPT);
-  static int per_sm = 0;             // per instantiation
-  if (per_sm == 0) {
+  static int per_sm_dev[64] = {0};   // per instantiation and per device: function attributes are per-device state
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (per_sm_dev[dev] == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SO_ECUDA;
     int v = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, TPB, smem);
-    per_sm = v < 1 ? 1 : v;
+    per_sm_dev[dev] = v < 1 ? 1 : v;
   }
+  const int per_sm = per_sm_dev[dev];
   constexpr int kChunkRows = TPB * RPT;
   const int64_t want = std::max<int64_t>(1, (s.rows + kChunkRows - 1) / kChunkRows);
   const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
