@@ -13,7 +13,7 @@
 //               Z[row0 + l%4][8t + l/4] — so a slab costs T 64-bit loads per lane, straight from global memory.
 //               Measured on this pool's B200: DMMA 37.2 TFLOP/s vs 33.8 for register-resident DFMA
 //               (profiles/r1_fp64_peak.json), and one DMMA replaces 8 DFMA issue slots + their operand traffic.
-//   larger n    not in this file yet (returns SO_EUNSUPPORTED; see DESIGN.md "next")
+//   larger n    shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_big below), n <= 513
 #include <algorithm>
 
 #include "so_wide.cuh"
@@ -104,7 +104,6 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 template <int T> __host__ __device__ constexpr int tri_tiles() { return T * (T + 1) / 2; }
-__host__ __device__ inline int tri_index(int T, int ta, int tb) { return ta * T - ta * (ta - 1) / 2 + (tb - ta); }
 
 template <int FAM, int T>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -265,19 +264,224 @@ int dispatch_tri(const Shard& s, const Params& P) {
   return SO_EUNSUPPORTED;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// n + 1 > 48 (up to 514 columns): shared-memory staged DMMA SYRK.
+//   * the upper triangle of 8x8 tiles is cut into 4x4-tile patches (32x32 entries); a warp owns one patch
+//     (16 DMMA accumulators = 64 registers), a 512-thread block owns up to 16 patches ("tile group");
+//   * the grid is (tile groups) x (row workers); tile group is the fastest block index so that the blocks that
+//     stream the same rows run together and share them through L2 (the kernel is FP64-bound by 2-6x: n = 256
+//     needs 66 306 flop per 2 056-byte row);
+//   * rows are staged 16 at a time into shared memory with cp.async (LDGSTS; 8-byte granules, so any f and any
+//     alignment), double buffered, row pitch 8T+4 doubles so that the 4 rows x 8 columns of an MMA fragment hit
+//     distinct banks; the intercept's 1-column and the residual column are appended in shared memory, after
+//     which every fragment is one plain LDS.64;
+//   * per 4-row slab a warp loads 4 + 4 fragments and issues 16 DMMAs (diagonal patches waste 6 of them).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBigThreads = 512, kBigWarps = 16, kBigRows = 16, kPatch = 4;
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src, bool valid) {
+  const unsigned int sz = valid ? 8u : 0u;      // src-size 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(dst_smem)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int FAM>
+__global__ void __launch_bounds__(kBigThreads, 1)
+k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+           int T, int npatches, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+  extern __shared__ __align__(16) double sm[];
+  const int f = P.f, icpt = P.icpt, n = P.n;
+  const int PW = 8 * T + 4;                            // row pitch in doubles
+  double* ps = sm;                                     // [8T] parameters in Z-column order (0 beyond f)
+  double* stage0 = sm + 8 * T;                         // 2 stages of kBigRows x PW
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rsel = lane & 3, csel = lane >> 2;
+  const int col_one = icpt ? f : -1, col_res = f + icpt;
+  if (FAM == kLogistic) exp_table_init();
+  for (int c = tid; c < 8 * T; c += kBigThreads) ps[c] = (c < f) ? P.p[icpt + c] : 0.0;
+  for (int i = tid; i < 2 * kBigRows * PW; i += kBigThreads) stage0[i] = 0.0;     // padding columns stay zero
+  __syncthreads();
+  const double p0 = icpt ? P.p[0] : 0.0;
+
+  // this warp's patch: the patch-th (pa <= pb) pair in row-major order over PT x PT
+  const int PT = (T + kPatch - 1) / kPatch;
+  const int patch = blockIdx.x * kBigWarps + warp;
+  int pa = 0, pb = 0;
+  const bool active = patch < npatches;
+  if (active) { int rem = patch; while (rem >= PT - pa) { rem -= PT - pa; ++pa; } pb = pa + rem; }
+
+  double acc[kPatch][kPatch][2];
+#pragma unroll
+  for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+    for (int j = 0; j < kPatch; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  const int64_t nchunks = (rows + kBigRows - 1) / kBigRows;
+  auto load_stage = [&](int64_t chunk, int stage) {
+    double* st = stage0 + (size_t)stage * kBigRows * PW;
+    const int64_t r0 = chunk * kBigRows;
+    for (int e = tid; e < kBigRows * f; e += kBigThreads) {
+      const int r = e / f, c = e - r * f;
+      const bool valid = r0 + r < rows;
+      cp_async8(st + r * PW + c, X + (valid ? (r0 + r) * (int64_t)f + c : 0), valid);
+    }
+    cp_async_commit();
+  };
+
+  int64_t chunk = blockIdx.y;
+  int it = 0;
+  if (chunk < nchunks) load_stage(chunk, 0);
+  for (; chunk < nchunks; chunk += gridDim.y, ++it) {
+    const int stage = it & 1;
+    const int64_t nxt = chunk + gridDim.y;
+    if (nxt < nchunks) { load_stage(nxt, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    double* st = stage0 + (size_t)stage * kBigRows * PW;
+    // residual and intercept columns: warp w finishes row w of the stage
+    {
+      const int r = warp;
+      const int64_t row = chunk * kBigRows + r;
+      const bool valid = row < rows;
+      double dot = 0.0;
+      for (int c = lane; c < f; c += 32) dot = fma(ps[c], st[r * PW + c], dot);
+      dot = warp_sum(dot);
+      if (lane == 0) {
+        const double z = dot + p0;
+        double res;
+        if (FAM == kLinear) {
+          res = (valid ? ld_stream(y + row) : 0.0) - z;
+        } else {
+          const double e = so_exp(-fabs(z));
+          const double inv = 1.0 / (1.0 + e);
+          res = ((z >= 0.0) ? inv : e * inv) - (valid ? ld_stream(y + row) : 0.0);
+        }
+        if (col_one >= 0) st[r * PW + col_one] = valid ? 1.0 : 0.0;
+        st[r * PW + col_res] = valid ? res : 0.0;
+      }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int slab = 0; slab < kBigRows / 4; ++slab) {
+        const double* base = st + (slab * 4 + rsel) * PW + csel;
+        double fa[kPatch], fb[kPatch];
+#pragma unroll
+        for (int i = 0; i < kPatch; ++i) {
+          const int ta = pa * kPatch + i, tb = pb * kPatch + i;
+          fa[i] = (ta < T) ? base[8 * ta] : 0.0;
+          fb[i] = (tb < T) ? base[8 * tb] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+          for (int j = 0; j < kPatch; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+      }
+    }
+    __syncthreads();      // everyone is done with `stage` before the next iteration refills it
+  }
+
+  // per-(row worker, patch) partials, lane-major tiles: [worker][patch][i][j][lane*2 + reg]
+  constexpr int kPatchDoubles = kPatch * kPatch * 64;
+  if (active) {
+    double* dst = partials + ((size_t)blockIdx.y * npatches + patch) * kPatchDoubles;
+#pragma unroll
+    for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+      for (int j = 0; j < kPatch; ++j) {
+        dst[(i * kPatch + j) * 64 + lane * 2] = acc[i][j][0];
+        dst[(i * kPatch + j) * 64 + lane * 2 + 1] = acc[i][j][1];
+      }
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  const unsigned int nblocks = gridDim.x * gridDim.y;
+  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == nblocks - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
+    for (int q = tid; q < Qo; q += kBigThreads) {
+      int ca, cb;
+      double sgn = 1.0;
+      if (q < Tn) {
+        // row-major packed upper index -> (a, b): solve a from q by the closed form, then fix up
+        int a = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * q)) * 0.5);
+        while (a > 0 && a * n - a * (a - 1) / 2 > q) --a;
+        while ((a + 1) * n - (a + 1) * a / 2 <= q) ++a;
+        const int b = a + (q - (a * n - a * (a - 1) / 2));
+        ca = icpt ? (a == 0 ? f : a - 1) : a;
+        cb = icpt ? (b == 0 ? f : b - 1) : b;
+      } else if (q < Tn + n) {
+        const int a = q - Tn;
+        ca = icpt ? (a == 0 ? f : a - 1) : a;
+        cb = col_res;
+        if (FAM == kLinear) sgn = -1.0;
+      } else {
+        ca = col_res; cb = col_res;
+      }
+      if (ca / (8 * kPatch) > cb / (8 * kPatch)) { const int tmp = ca; ca = cb; cb = tmp; }   // patch row <= patch col
+      const int qa = ca / (8 * kPatch), qb = cb / (8 * kPatch);
+      const int pidx = qa * PT - qa * (qa - 1) / 2 + (qb - qa);
+      const int ti = (ca >> 3) - qa * kPatch, tj = (cb >> 3) - qb * kPatch, i = ca & 7, j = cb & 7;
+      const size_t off = (size_t)pidx * kPatchDoubles + (ti * kPatch + tj) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
+      double s2 = 0.0;
+      for (unsigned w = 0; w < gridDim.y; ++w) s2 += __ldcg(&partials[(size_t)w * npatches * kPatchDoubles + off]);
+      out[q] = s2 * sgn;
+    }
+    if (tid == 0) *ticket = 0u;
+  }
+}
+
+struct BigPlan { int T, PT, npatches, groups, workers; size_t smem; };
+inline BigPlan big_plan(int n, int sm_count) {
+  BigPlan b;
+  b.T = (n + 1 + 7) / 8;
+  b.PT = (b.T + kPatch - 1) / kPatch;
+  b.npatches = b.PT * (b.PT + 1) / 2;
+  b.groups = (b.npatches + kBigWarps - 1) / kBigWarps;
+  b.workers = std::max(1, sm_count / b.groups);
+  b.smem = sizeof(double) * ((size_t)8 * b.T + 2 * (size_t)kBigRows * (8 * b.T + 4));
+  return b;
+}
+
+template <int FAM>
+int launch_big(const Shard& s, const Params& P) {
+  auto kern = k_gram_big<FAM>;
+  BigPlan b = big_plan(P.n, s.sm_count);
+  static bool attr[64] = {false};
+  int dev = 0; cudaGetDevice(&dev); dev &= 63;
+  if (!attr[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return SO_ECUDA;
+    attr[dev] = true;
+  }
+  const int64_t nchunks = (s.rows + kBigRows - 1) / kBigRows;
+  const int workers = (int)std::min<int64_t>(b.workers, std::max<int64_t>(1, nchunks));
+  const size_t need = (size_t)workers * b.npatches * kPatch * kPatch * 64;
+  const int Qo = P.n * (P.n + 1) / 2 + P.n + 1;
+  if (need > s.partials_doubles || (size_t)Qo > s.out_doubles) return SO_ENOMEM;
+  dim3 grid(b.groups, workers);
+  kern<<<grid, kBigThreads, b.smem, s.stream>>>(s.X, s.y, s.rows, P, b.T, b.npatches, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
 }  // namespace
 
 size_t gram_partials_needed(int n, int f, int sm_count) {
   (void)f;
   if (n <= 8) return (size_t)sm_count * 8 * (size_t)(n * (n + 1) / 2 + n + 1);
   const int T = (n + 1 + 7) / 8;
-  return (size_t)sm_count * 4 * (size_t)(T * (T + 1) / 2) * 64;
+  if (n + 1 <= 48) return (size_t)sm_count * 4 * (size_t)(T * (T + 1) / 2) * 64;
+  const BigPlan b = big_plan(n, sm_count);
+  return (size_t)b.workers * b.npatches * kPatch * kPatch * 64;
 }
 
 int launch_gram(const Shard& s, int fam, const Params& P) {
   if (P.n <= 8) return fam == kLinear ? dispatch_small<kLinear>(s, P) : dispatch_small<kLogistic>(s, P);
   if (P.n + 1 <= 48) return fam == kLinear ? dispatch_tri<kLinear>(s, P) : dispatch_tri<kLogistic>(s, P);
-  return SO_EUNSUPPORTED;
+  return fam == kLinear ? launch_big<kLinear>(s, P) : launch_big<kLogistic>(s, P);
 }
 
 }  // namespace wide

@@ -53,12 +53,17 @@ def test_loss_gradient_line_hessvec_match_oracle(native, oracle, gpu_ctx, name, 
 
 GRAM_CASES = [("LINEAR", 1), ("LINEAR", 3), ("LINEAR", 7), ("LINEAR_NOINT", 8), ("LINEAR", 8), ("LINEAR", 10),
               ("LINEAR", 31), ("LINEAR", 32), ("LINEAR_NOINT", 33), ("LINEAR_NOINT", 47), ("LINEAR", 46),
-              ("LOGISTIC", 2), ("LOGISTIC", 7), ("LOGISTIC", 32)]
+              ("LOGISTIC", 2), ("LOGISTIC", 7), ("LOGISTIC", 32),
+              # n + 1 > 48: shared-memory staged DMMA SYRK
+              ("LINEAR_NOINT", 48), ("LINEAR_NOINT", 64), ("LINEAR", 127), ("LINEAR_NOINT", 128), ("LINEAR", 256),
+              ("LINEAR_NOINT", 256), ("LOGISTIC", 64), ("LINEAR_NOINT", 511), ("LINEAR", 512)]
 
 
 @pytest.mark.parametrize("name,f", GRAM_CASES)
 @pytest.mark.parametrize("m", [30_001, 5])
 def test_normal_equations_match_oracle(native, oracle, gpu_ctx, name, f, m):
+    if f > 100 and m > 1000:
+        m = 3_001 if f > 300 else 6_001       # keep the O(m n^2) oracle fold in seconds
     fam = getattr(oracle, name)
     truth = _truth(name, f)
     X, y = oracle.generate(fam, m, f, truth)
@@ -77,12 +82,11 @@ def test_normal_equations_match_oracle(native, oracle, gpu_ctx, name, f, m):
     ds.free()
 
 
-def test_wide_gram_beyond_catalogue_is_an_error_not_a_fallback(native, oracle, gpu_ctx):
-    fam = oracle.LINEAR_NOINT
-    X, y = oracle.generate(fam, 64, 64, _truth("LINEAR_NOINT", 64))
-    ds = native.Dataset(gpu_ctx, 64, 64).append(X, y)
-    with pytest.raises(native.NativeError) as e:
-        ds.normal_eq(fam, np.ones(64))
+def test_shapes_beyond_the_catalogue_are_an_error_not_a_fallback(native, gpu_ctx):
+    ds = native.Dataset(gpu_ctx, 4, 513)
+    ds.append(np.ones((4, 513)), np.ones(4))
+    with pytest.raises(native.NativeError) as e:          # f > SO_MAX_FEATURES
+        ds.normal_eq(native.LINEAR_NOINT, np.ones(513))
     assert e.value.code == -5
     ds.free()
 
