@@ -88,6 +88,7 @@ int so_init(int ngpus, const int* device_ids, so_ctx** out);
 int so_nccl_unique_id(void* out_uid, size_t bytes);
 int so_init_rank(int device_id, int rank, int world, const void* nccl_uid, size_t uid_bytes, so_ctx** out);
 
+/* Data sets of the context must be freed (so_dataset_free) BEFORE so_shutdown; handles are invalid afterwards. */
 void so_shutdown(so_ctx* ctx);
 
 /* Message of the last failing call on `ctx` (ctx may be NULL: last so_init* failure of this thread). */

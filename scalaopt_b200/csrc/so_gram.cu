@@ -278,7 +278,7 @@ int dispatch_tri(const Shard& s, const Params& P) {
 //     which every fragment is one plain LDS.64;
 //   * per 4-row slab a warp loads 4 + 4 fragments and issues 16 DMMAs (diagonal patches waste 6 of them).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kBigThreads = 512, kBigWarps = 16, kBigRows = 16, kPatch = 4;
+constexpr int kBigThreads = 512, kBigWarps = 16, kPatch = 4, kBigStages = 3;
 
 __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src, bool valid) {
   const unsigned int sz = valid ? 8u : 0u;      // src-size 0: zero fill
@@ -287,30 +287,35 @@ __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src, bool 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-template <int FAM>
+// RPW = rows per warp per chunk (chunk = 16 * RPW rows).  Warp w copies rows w, w+16, ... of a chunk itself and
+// finishes their residual / intercept columns itself, so the only block barrier per chunk is the one that
+// publishes the finished stage; with 3 stages that same barrier also protects the stage being refilled.
+template <int FAM, int RPW>
 __global__ void __launch_bounds__(kBigThreads, 1)
 k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
-           int T, int npatches, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+           int PT, int npatches, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   extern __shared__ __align__(16) double sm[];
+  constexpr int kRows = kBigWarps * RPW;
   const int f = P.f, icpt = P.icpt, n = P.n;
-  const int PW = 8 * T + 4;                            // row pitch in doubles
-  double* ps = sm;                                     // [8T] parameters in Z-column order (0 beyond f)
-  double* stage0 = sm + 8 * T;                         // 2 stages of kBigRows x PW
+  const int W = 8 * kPatch * PT;                       // padded width: whole patches, zero beyond f + icpt + 1
+  const int PW = W + 4;                                // row pitch in doubles (4 rows x 8 cols of a fragment: distinct banks)
+  double* ps = sm;                                     // [W] parameters in Z-column order (0 beyond f)
+  double* stage0 = sm + W;                             // kBigStages stages of kRows x PW
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rsel = lane & 3, csel = lane >> 2;
   const int col_one = icpt ? f : -1, col_res = f + icpt;
   if (FAM == kLogistic) exp_table_init();
-  for (int c = tid; c < 8 * T; c += kBigThreads) ps[c] = (c < f) ? P.p[icpt + c] : 0.0;
-  for (int i = tid; i < 2 * kBigRows * PW; i += kBigThreads) stage0[i] = 0.0;     // padding columns stay zero
+  for (int c = tid; c < W; c += kBigThreads) ps[c] = (c < f) ? P.p[icpt + c] : 0.0;
+  for (int i = tid; i < kBigStages * kRows * PW; i += kBigThreads) stage0[i] = 0.0;     // padding columns stay zero
   __syncthreads();
   const double p0 = icpt ? P.p[0] : 0.0;
 
   // this warp's patch: the patch-th (pa <= pb) pair in row-major order over PT x PT
-  const int PT = (T + kPatch - 1) / kPatch;
   const int patch = blockIdx.x * kBigWarps + warp;
   int pa = 0, pb = 0;
   const bool active = patch < npatches;
   if (active) { int rem = patch; while (rem >= PT - pa) { rem -= PT - pa; ++pa; } pb = pa + rem; }
+  const int offa = 8 * kPatch * pa + csel, offb = 8 * kPatch * pb + csel;
 
   double acc[kPatch][kPatch][2];
 #pragma unroll
@@ -318,69 +323,78 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t r
 #pragma unroll
     for (int j = 0; j < kPatch; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-  const int64_t nchunks = (rows + kBigRows - 1) / kBigRows;
-  auto load_stage = [&](int64_t chunk, int stage) {
-    double* st = stage0 + (size_t)stage * kBigRows * PW;
-    const int64_t r0 = chunk * kBigRows;
-    for (int e = tid; e < kBigRows * f; e += kBigThreads) {
-      const int r = e / f, c = e - r * f;
-      const bool valid = r0 + r < rows;
-      cp_async8(st + r * PW + c, X + (valid ? (r0 + r) * (int64_t)f + c : 0), valid);
+  const int64_t nchunks = (rows + kRows - 1) / kRows;
+  auto load_stage = [&](int64_t chunk, int stage) {      // this warp's rows of the chunk; always commits a group
+    if (chunk < nchunks) {
+      double* st = stage0 + (size_t)stage * kRows * PW;
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) {
+        const int r = warp + k * kBigWarps;
+        const int64_t row = chunk * kRows + r;
+        const bool valid = row < rows;
+        const double* src = X + (valid ? row : 0) * (int64_t)f;
+        for (int c = lane; c < f; c += 32) cp_async8(st + r * PW + c, src + c, valid);
+      }
     }
     cp_async_commit();
   };
 
   int64_t chunk = blockIdx.y;
+  load_stage(chunk, 0);
+  load_stage(chunk + gridDim.y, 1);
   int it = 0;
-  if (chunk < nchunks) load_stage(chunk, 0);
   for (; chunk < nchunks; chunk += gridDim.y, ++it) {
-    const int stage = it & 1;
-    const int64_t nxt = chunk + gridDim.y;
-    if (nxt < nchunks) { load_stage(nxt, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    double* st = stage0 + (size_t)stage * kBigRows * PW;
-    // residual and intercept columns: warp w finishes row w of the stage
-    {
-      const int r = warp;
-      const int64_t row = chunk * kBigRows + r;
+    const int stage = it % kBigStages;
+    cp_async_wait<1>();                                  // this warp's copies of `chunk` have landed
+    __syncwarp();
+    double* st = stage0 + (size_t)stage * kRows * PW;
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {                      // residual and intercept columns of this warp's rows
+      const int r = warp + k * kBigWarps;
+      const int64_t row = chunk * kRows + r;
       const bool valid = row < rows;
       double dot = 0.0;
       for (int c = lane; c < f; c += 32) dot = fma(ps[c], st[r * PW + c], dot);
       dot = warp_sum(dot);
       if (lane == 0) {
         const double z = dot + p0;
+        const double yv = valid ? ld_stream(y + row) : 0.0;
         double res;
         if (FAM == kLinear) {
-          res = (valid ? ld_stream(y + row) : 0.0) - z;
+          res = yv - z;
         } else {
           const double e = so_exp(-fabs(z));
           const double inv = 1.0 / (1.0 + e);
-          res = ((z >= 0.0) ? inv : e * inv) - (valid ? ld_stream(y + row) : 0.0);
+          res = ((z >= 0.0) ? inv : e * inv) - yv;
         }
         if (col_one >= 0) st[r * PW + col_one] = valid ? 1.0 : 0.0;
         st[r * PW + col_res] = valid ? res : 0.0;
       }
     }
-    __syncthreads();
+    __syncthreads();     // stage complete for everyone; everyone has also finished computing on the previous chunk
+    load_stage(chunk + 2 * (int64_t)gridDim.y, (it + 2) % kBigStages);
     if (active) {
-#pragma unroll
-      for (int slab = 0; slab < kBigRows / 4; ++slab) {
-        const double* base = st + (slab * 4 + rsel) * PW + csel;
+#pragma unroll 2
+      for (int slab = 0; slab < kRows / 4; ++slab) {
+        const double* base = st + (slab * 4 + rsel) * PW;
         double fa[kPatch], fb[kPatch];
 #pragma unroll
-        for (int i = 0; i < kPatch; ++i) {
-          const int ta = pa * kPatch + i, tb = pb * kPatch + i;
-          fa[i] = (ta < T) ? base[8 * ta] : 0.0;
-          fb[i] = (tb < T) ? base[8 * tb] : 0.0;
+        for (int i = 0; i < kPatch; ++i) { fa[i] = base[offa + 8 * i]; fb[i] = base[offb + 8 * i]; }
+        if (pa != pb) {
+#pragma unroll
+          for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+            for (int j = 0; j < kPatch; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        } else {            // diagonal patch: only tiles on or above the diagonal are ever read back
+#pragma unroll
+          for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+            for (int j = i; j < kPatch; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
         }
-#pragma unroll
-        for (int i = 0; i < kPatch; ++i)
-#pragma unroll
-          for (int j = 0; j < kPatch; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
       }
     }
-    __syncthreads();      // everyone is done with `stage` before the next iteration refills it
   }
+  cp_async_wait<0>();
 
   // per-(row worker, patch) partials, lane-major tiles: [worker][patch][i][j][lane*2 + reg]
   constexpr int kPatchDoubles = kPatch * kPatch * 64;
@@ -407,7 +421,7 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t r
       int ca, cb;
       double sgn = 1.0;
       if (q < Tn) {
-        // row-major packed upper index -> (a, b): solve a from q by the closed form, then fix up
+        // row-major packed upper index -> (a, b): closed form, then fix up
         int a = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * q)) * 0.5);
         while (a > 0 && a * n - a * (a - 1) / 2 > q) --a;
         while ((a + 1) * n - (a + 1) * a / 2 <= q) ++a;
@@ -435,36 +449,46 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t r
   }
 }
 
-struct BigPlan { int T, PT, npatches, groups, workers; size_t smem; };
+struct BigPlan { int PT, npatches, groups, workers, rpw; size_t smem; };
 inline BigPlan big_plan(int n, int sm_count) {
   BigPlan b;
-  b.T = (n + 1 + 7) / 8;
-  b.PT = (b.T + kPatch - 1) / kPatch;
+  const int T = (n + 1 + 7) / 8;
+  b.PT = (T + kPatch - 1) / kPatch;
   b.npatches = b.PT * (b.PT + 1) / 2;
   b.groups = (b.npatches + kBigWarps - 1) / kBigWarps;
   b.workers = std::max(1, sm_count / b.groups);
-  b.smem = sizeof(double) * ((size_t)8 * b.T + 2 * (size_t)kBigRows * (8 * b.T + 4));
+  const size_t W = (size_t)8 * kPatch * b.PT;
+  auto bytes = [&](int rpw) { return sizeof(double) * (W + (size_t)kBigStages * kBigWarps * rpw * (W + 4)); };
+  b.rpw = (bytes(2) <= 229000) ? 2 : 1;   // 227 KB per block minus ~3 KB of static shared memory
+  b.smem = bytes(b.rpw);
   return b;
 }
 
-template <int FAM>
-int launch_big(const Shard& s, const Params& P) {
-  auto kern = k_gram_big<FAM>;
-  BigPlan b = big_plan(P.n, s.sm_count);
+template <int FAM, int RPW>
+int launch_big_rpw(const Shard& s, const Params& P, const BigPlan& b) {
+  auto kern = k_gram_big<FAM, RPW>;
   static bool attr[64] = {false};
   int dev = 0; cudaGetDevice(&dev); dev &= 63;
   if (!attr[dev]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return SO_ECUDA;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 229000) != cudaSuccess) return SO_ECUDA;
     attr[dev] = true;
   }
-  const int64_t nchunks = (s.rows + kBigRows - 1) / kBigRows;
+  constexpr int kRows = kBigWarps * RPW;
+  const int64_t nchunks = (s.rows + kRows - 1) / kRows;
   const int workers = (int)std::min<int64_t>(b.workers, std::max<int64_t>(1, nchunks));
   const size_t need = (size_t)workers * b.npatches * kPatch * kPatch * 64;
   const int Qo = P.n * (P.n + 1) / 2 + P.n + 1;
   if (need > s.partials_doubles || (size_t)Qo > s.out_doubles) return SO_ENOMEM;
   dim3 grid(b.groups, workers);
-  kern<<<grid, kBigThreads, b.smem, s.stream>>>(s.X, s.y, s.rows, P, b.T, b.npatches, s.partials, s.out, s.ticket);
+  kern<<<grid, kBigThreads, b.smem, s.stream>>>(s.X, s.y, s.rows, P, b.PT, b.npatches, s.partials, s.out, s.ticket);
   return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+template <int FAM>
+int launch_big(const Shard& s, const Params& P) {
+  const BigPlan b = big_plan(P.n, s.sm_count);
+  if (b.smem > 229000) return SO_EUNSUPPORTED;
+  return b.rpw == 2 ? launch_big_rpw<FAM, 2>(s, P, b) : launch_big_rpw<FAM, 1>(s, P, b);
 }
 
 }  // namespace

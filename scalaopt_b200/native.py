@@ -144,6 +144,7 @@ class Context:
             rc = L.so_init_rank(device_id, rank, world, buf, NCCL_UID_BYTES if buf else 0, C.byref(self._h))
         if rc != 0:
             raise NativeError(rc, L.so_last_error(None).decode())
+        self._datasets = []      # weak references: data sets are released before the context is shut down
 
     @staticmethod
     def nccl_unique_id() -> bytes:
@@ -164,6 +165,11 @@ class Context:
 
     def close(self):
         if self._h:
+            for ref in self._datasets:
+                ds = ref()
+                if ds is not None:
+                    ds.free()
+            self._datasets = []
             load().so_shutdown(self._h)
             self._h = C.c_void_p()
 
@@ -185,6 +191,8 @@ class Dataset:
         else:
             self._h = C.c_void_p()
             ctx.check(load().so_dataset_create(ctx._h, m, f, C.byref(self._h)))
+        import weakref
+        ctx._datasets.append(weakref.ref(self))
 
     def append(self, X, y):
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -263,7 +271,8 @@ class Dataset:
 
     def free(self):
         if self._h:
-            load().so_dataset_free(self._h)
+            if self.ctx._h:          # after so_shutdown the library has already released everything it owned
+                load().so_dataset_free(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
