@@ -436,7 +436,7 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t r
       } else {
         ca = col_res; cb = col_res;
       }
-      if (ca / (8 * kPatch) > cb / (8 * kPatch)) { const int tmp = ca; ca = cb; cb = tmp; }   // patch row <= patch col
+      if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }   // tile row <= tile col (hence patch row <= patch col)
       const int qa = ca / (8 * kPatch), qb = cb / (8 * kPatch);
       const int pidx = qa * PT - qa * (qa - 1) / 2 + (qb - qa);
       const int ti = (ca >> 3) - qa * kPatch, tj = (cb >> 3) - qb * kPatch, i = ca & 7, j = cb & 7;

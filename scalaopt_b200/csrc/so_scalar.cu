@@ -59,18 +59,18 @@ struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarqua
 
 struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma)
   static constexpr int N = 3, NE = 1;
-  struct Pre { double A, mu, s, sr2; double D[N]; };   // s = 1/sigma, sr2 = s/sqrt(2)
+  struct Pre { double A, mu, s, sr2, nmsr2; double D[N]; };   // s = 1/sigma, sr2 = s/sqrt(2), nmsr2 = -mu sr2
   static Pre prepare(const double* p) {
-    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2;
+    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.nmsr2 = -c.mu * c.sr2;
     c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2; c.D[2] = 2.0 * p[0] * c.s;
     return c;
   }
   __device__ static __forceinline__ void args(const Pre& c, double t, double* a) {
-    const double zz = (t - c.mu) * c.sr2;          // z / sqrt(2),  z = (t - mu)/sigma
+    const double zz = fma(t, c.sr2, c.nmsr2);      // z / sqrt(2),  z = (t - mu)/sigma, one FMA
     a[0] = -zz * zz;
   }
   __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
-    const double zz = (t - c.mu) * c.sr2;
+    const double zz = fma(t, c.sr2, c.nmsr2);
     u[0] = ex[0];          // df/dA     = g
     u[1] = ex[0] * zz;     // df/dmu    = A g z / sigma      = (A s sqrt2) g zz
     u[2] = u[1] * zz;      // df/dsigma = A g z^2 / sigma    = (2 A s) g zz^2
@@ -90,19 +90,19 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
 
 struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),  p = (A, mu, sigma, B, lambda)
   static constexpr int N = 5, NE = 2;   // functional form of stats/example/ExSignalPlusBackgroundFit.scala:78-114
-  struct Pre { double A, mu, s, sr2, B, nlam; double D[N]; };
+  struct Pre { double A, mu, s, sr2, nmsr2, B, nlam; double D[N]; };
   static Pre prepare(const double* p) {
-    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.B = p[3]; c.nlam = -p[4];
+    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.nmsr2 = -c.mu * c.sr2; c.B = p[3]; c.nlam = -p[4];
     c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2; c.D[2] = 2.0 * p[0] * c.s; c.D[3] = 1.0; c.D[4] = -p[3];
     return c;
   }
   __device__ static __forceinline__ void args(const Pre& c, double t, double* a) {
-    const double zz = (t - c.mu) * c.sr2;
+    const double zz = fma(t, c.sr2, c.nmsr2);
     a[0] = -zz * zz;
     a[1] = c.nlam * t;
   }
   __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
-    const double zz = (t - c.mu) * c.sr2;
+    const double zz = fma(t, c.sr2, c.nmsr2);
     u[0] = ex[0];
     u[1] = ex[0] * zz;
     u[2] = u[1] * zz;
