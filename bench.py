@@ -158,7 +158,7 @@ def reference_sample_rows(threads: int, target_s: float = 3.0) -> int:
     t0 = time.perf_counter()
     oracle.lm_reference_passes(fam, X, y, params_for_step(0), threads=threads)
     rate = m0 / (time.perf_counter() - t0)
-    return int(min(max(rate * target_s, m0), 50_000_000))
+    return int(min(max(rate * target_s, 200_000), 50_000_000))
 
 
 def run_reference(args):
@@ -173,7 +173,9 @@ def run_reference(args):
     oracle.build()
     threads = host_threads()
     fam = oracle.GAUSS_EXPBKG
-    m = reference_sample_rows(threads)
+    # bounded sample: the whole --steps/--warmup run is sized to ~2 minutes of CPU work
+    per_step_s = min(3.0, max(0.05, 120.0 / (args.steps + args.warmup)))
+    m = reference_sample_rows(threads, target_s=per_step_s)
     X, y = oracle.generate(fam, m, 1, TRUTH, SEED, NOISE)
     for i in range(args.warmup):
         oracle.lm_reference_passes(fam, X, y, params_for_step(i), threads=threads)

@@ -446,20 +446,23 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
         // tuning variants: rows per range-checked group x threads per block x resident blocks per SM (SO_K2_VARIANT)
         const char* v = getenv("SO_K2_VARIANT");
         const int var = v ? atoi(v) : 0;
-        auto relaunch = [&](auto gtag, auto modetag, auto rpttag) -> int {
+        auto relaunch = [&](auto gtag, auto tpbtag, auto mbtag, auto rpttag) -> int {
           using Op2 = OpNormalEq<Fam, decltype(gtag)::value>;
           typename Op2::Args a2; a2.pre = a.pre;
           for (int q2 = 0; q2 < Op2::Q; ++q2) a2.scale[q2] = a.scale[q2];
-          return launch_op_cfg<Op2, 256, 2, decltype(modetag)::value, decltype(rpttag)::value>(s, a2);
+          return launch_op_cfg<Op2, decltype(tpbtag)::value, decltype(mbtag)::value, 0, decltype(rpttag)::value>(s, a2);
         };
-        using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
-        using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>; using I8 = std::integral_constant<int, 8>;
-        if (var == 1) return relaunch(I4(), I1(), I4());   // empty-mbarrier ring
-        if (var == 2) return relaunch(I4(), I0(), I8());   // __syncthreads ring, 8 rows per thread per chunk
-        if (var == 3) return relaunch(I4(), I1(), I8());   // empty-mbarrier ring, 8 rows per thread per chunk
-        if (var == 4) return relaunch(I2(), I0(), I4());   // 2 rows per range-checked group
-        if (var == 5) return relaunch(I2(), I0(), I8());
-        return relaunch(I2(), I0(), I8());
+        using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>; using I3 = std::integral_constant<int, 3>;
+        using I4 = std::integral_constant<int, 4>; using I5 = std::integral_constant<int, 5>; using I6 = std::integral_constant<int, 6>;
+        using I8 = std::integral_constant<int, 8>;
+        using T128 = std::integral_constant<int, 128>; using T256 = std::integral_constant<int, 256>;
+        if (var == 1) return relaunch(I2(), T128(), I5(), I4());
+        if (var == 2) return relaunch(I1(), T256(), I3(), I4());
+        if (var == 3) return relaunch(I1(), T128(), I6(), I4());
+        if (var == 4) return relaunch(I2(), T128(), I4(), I8());
+        if (var == 5) return relaunch(I1(), T128(), I5(), I4());
+        if (var == 6) return relaunch(I4(), T128(), I4(), I8());
+        return relaunch(I2(), T256(), I2(), I8());
       }
       return launch_op<Op, (Op::Q < 21 ? 3 : 2)>(s, a);
     }
