@@ -61,6 +61,35 @@ __device__ __forceinline__ double so_exp_fast(double x) {
 // rare path (|x| >= 708, inf, NaN): a real call keeps the ~60 libdevice instructions out of the hot loop body
 static __device__ __noinline__ double exp_slow(double x) { return exp(x); }
 
+// Variant with a 4096-entry table (32 KB, in dynamic shared memory) and a degree-3 polynomial: 8 FP64-pipe
+// instructions.  |r| <= ln2/8192, truncation error r^4/24 < 3e-18.  Worth its shared memory only where the kernel
+// is FP64-issue-bound (every FP64 instruction costs >= 2 issue cycles and nothing else hides under it).
+constexpr int kExpBigBits = 12, kExpBigSize = 1 << kExpBigBits;
+struct ExpConstsBig { double inv, shift, nln2hi, nln2lo, c3; };
+static __constant__ ExpConstsBig kExpBig = {
+    0x1.71547652b82fep+12,     // 4096 / ln 2
+    6755399441055744.0,
+    -0x1.62e42fefa39efp-13,    // -(ln 2 / 4096) rounded to double
+    -0x1.abc9e3b39803fp-68,    // -(ln 2 / 4096 - hi)
+    0x1.5555555555555p-3,      // 1/6
+};
+__device__ __forceinline__ void exp_big_table_init(double* tab) {
+  for (int j = threadIdx.x; j < kExpBigSize; j += blockDim.x) tab[j] = exp2((double)j * (1.0 / kExpBigSize));
+}
+__device__ __forceinline__ double so_exp_fast_big(double x, const double* __restrict__ tab) {
+  double kd = fma(x, kExpBig.inv, kExpBig.shift);
+  const int ki = __double2loint(kd);
+  kd -= kExpBig.shift;
+  double r = fma(kd, kExpBig.nln2hi, x);
+  r = fma(kd, kExpBig.nln2lo, r);
+  double q = fma(r, kExpBig.c3, 0.5);
+  q = fma(q, r, 1.0);
+  const double pm1 = q * r;
+  const double T = tab[ki & (kExpBigSize - 1)];
+  const double res = fma(T, pm1, T);
+  return __hiloint2double(__double2hiint(res) + ((ki << 8) & 0xfff00000), __double2loint(res));
+}
+
 // exp(x) with the range check folded in (one branch); used where the check is not hoisted by the caller.
 __device__ __forceinline__ double so_exp(double x) {
   if (exp_abs_hi(x) >= kExpHiLimit) return exp_slow(x);
@@ -115,7 +144,7 @@ __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p);
 template <int Q>
 __device__ __forceinline__ void grid_reduce(double (&acc)[Q], double* smem, double* __restrict__ partials,
                                             double* __restrict__ out, const double* __restrict__ scale,
-                                            unsigned int* ticket) {
+                                            unsigned int* ticket, const signed char* __restrict__ src = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
@@ -136,8 +165,9 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[Q], double* smem, doub
   if (s_last) {
     __threadfence();
     for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+      const int qs = src ? (int)src[q] : q;        // out[q] may be another accumulator's sum (identical sums are kept once)
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * Q + q]);
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * Q + qs]);
       out[q] = scale ? s * scale[q] : s;
     }
     if (threadIdx.x == 0) *ticket = 0u;

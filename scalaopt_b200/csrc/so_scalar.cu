@@ -42,6 +42,7 @@ constexpr double kInvSqrt2 = 0.70710678118654752;
 // ---------------------------------------------------------------------------------------------------
 struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarquardtSpec.scala:62-63
   static constexpr int N = 2, NE = 1;
+  __host__ __device__ static constexpr bool gram_alias(int, int, int&, int&) { return false; }
   struct Pre { double p0, p1; double D[N]; };
   static Pre prepare(const double* p) { Pre c; c.p0 = p[0]; c.p1 = p[1]; c.D[0] = 1.0; c.D[1] = p[0]; return c; }
   __device__ static __forceinline__ void args(const Pre& c, double t, double* a) { a[0] = c.p1 * t; }
@@ -59,6 +60,8 @@ struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarqua
 
 struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma)
   static constexpr int N = 3, NE = 1;
+  // u1*u1 = (g zz)^2 = g * (g zz^2) = u0*u2: the (1,1) sum is the (0,2) sum, accumulate it once
+  __host__ __device__ static constexpr bool gram_alias(int i, int j, int& si, int& sj) { if (i == 1 && j == 1) { si = 0; sj = 2; return true; } return false; }
   struct Pre { double A, mu, s, sr2, nmsr2; double D[N]; };   // s = 1/sigma, sr2 = s/sqrt(2), nmsr2 = -mu sr2
   static Pre prepare(const double* p) {
     Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.nmsr2 = -c.mu * c.sr2;
@@ -90,6 +93,7 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
 
 struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),  p = (A, mu, sigma, B, lambda)
   static constexpr int N = 5, NE = 2;   // functional form of stats/example/ExSignalPlusBackgroundFit.scala:78-114
+  __host__ __device__ static constexpr bool gram_alias(int i, int j, int& si, int& sj) { if (i == 1 && j == 1) { si = 0; sj = 2; return true; } return false; }
   struct Pre { double A, mu, s, sr2, nmsr2, B, nlam; double D[N]; };
   static Pre prepare(const double* p) {
     Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.nmsr2 = -c.mu * c.sr2; c.B = p[3]; c.nlam = -p[4];
@@ -130,6 +134,11 @@ struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),
 template <int NP>
 struct FamPoly {       // f = sum_k p_k t^k
   static constexpr int N = NP, NE = 0;
+  // u_i u_j = t^(i+j): every anti-diagonal of the Gram is one sum; keep the entry on the first row / last column
+  __host__ __device__ static constexpr bool gram_alias(int i, int j, int& si, int& sj) {
+    if (i == 0 || j == NP - 1) return false;
+    const int s = i + j; si = (s < NP) ? 0 : s - (NP - 1); sj = s - si; return true;
+  }
   struct Pre { double p[N]; double D[N]; };
   static Pre prepare(const double* p) { Pre c; for (int k = 0; k < N; ++k) { c.p[k] = p[k]; c.D[k] = 1.0; } return c; }
   __device__ static __forceinline__ void args(const Pre&, double, double*) {}
@@ -153,6 +162,7 @@ struct FamPoly {       // f = sum_k p_k t^k
 template <class Fam, bool GRAD>
 struct OpLossGrad {
   static constexpr int N = Fam::N, Q = GRAD ? 1 + N : 1, NEXP = Fam::NE, G = 4;
+  static constexpr bool kHasSrc = false;
   struct Args { typename Fam::Pre pre; double scale[Q]; };
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
@@ -170,7 +180,9 @@ struct OpLossGrad {
 template <class Fam, int GROUP = 4>
 struct OpNormalEq {
   static constexpr int N = Fam::N, T = N * (N + 1) / 2, Q = T + N + 1, NEXP = Fam::NE, G = GROUP;
-  struct Args { typename Fam::Pre pre; double scale[Q]; };
+  struct Args { typename Fam::Pre pre; double scale[Q]; signed char src[Q]; };
+  static constexpr bool kHasSrc = true;
+  __host__ __device__ static constexpr int packed(int i, int j) { return i * N - i * (i - 1) / 2 + (j - i); }
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
@@ -180,7 +192,11 @@ struct OpNormalEq {
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int j = i; j < N; ++j) { acc[q] = fma(u[i], u[j], acc[q]); ++q; }
+      for (int j = i; j < N; ++j) {
+        int si = 0, sj = 0;
+        if (!Fam::gram_alias(i, j, si, sj)) acc[q] = fma(u[i], u[j], acc[q]);   // aliased sums are accumulated once
+        ++q;
+      }
 #pragma unroll
     for (int i = 0; i < N; ++i) acc[T + i] = fma(u[i], rho, acc[T + i]);
     acc[T + N] = fma(rho, rho, acc[T + N]);
@@ -190,6 +206,7 @@ struct OpNormalEq {
 template <class Fam, int KB>
 struct OpLine {
   static constexpr int N = Fam::N, Q = 2 * KB, NEXP = KB * Fam::NE, G = (KB <= 1 ? 4 : (KB <= 2 ? 2 : 1));
+  static constexpr bool kHasSrc = false;
   struct Args { typename Fam::Pre pre[KB]; double dd[KB][N]; double scale[Q]; };   // dd = D(p + alpha d) o d
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) {
 #pragma unroll
@@ -213,6 +230,7 @@ struct OpLine {
 template <class Fam>
 struct OpHessVec {
   static constexpr int N = Fam::N, Q = N, NEXP = Fam::NE, G = 2;
+  static constexpr bool kHasSrc = false;
   struct Args { typename Fam::Pre pre; double d[N]; double scale[Q]; };
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
@@ -229,9 +247,9 @@ struct OpHessVec {
 };
 
 // G rows: all exp arguments first, ONE range check, then branch-free exponentials, then the accumulation.
-template <class Op, int G>
+template <class Op, int G, bool BIG, bool CHECK = true>
 __device__ __forceinline__ void process_rows(const typename Op::Args& args, const double (&t)[G], const double (&y)[G],
-                                             double (&acc)[Op::Q]) {
+                                             double (&acc)[Op::Q], const double* __restrict__ big_tab) {
   constexpr int NE = Op::NEXP;
   if constexpr (NE == 0) {
 #pragma unroll
@@ -242,14 +260,16 @@ __device__ __forceinline__ void process_rows(const typename Op::Args& args, cons
 #pragma unroll
     for (int r = 0; r < G; ++r) {
       Op::args(args, t[r], ea[r]);
+      if (CHECK) {
 #pragma unroll
-      for (int e = 0; e < NE; ++e) mx = max(mx, exp_abs_hi(ea[r][e]));
+        for (int e = 0; e < NE; ++e) mx = max(mx, exp_abs_hi(ea[r][e]));
+      }
     }
-    if (mx < kExpHiLimit) {
+    if (!CHECK || mx < kExpHiLimit) {
 #pragma unroll
       for (int r = 0; r < G; ++r)
 #pragma unroll
-        for (int e = 0; e < NE; ++e) ea[r][e] = so_exp_fast(ea[r][e]);
+        for (int e = 0; e < NE; ++e) ea[r][e] = BIG ? so_exp_fast_big(ea[r][e], big_tab) : so_exp_fast(ea[r][e]);
     } else {      // some |arg| >= 708, inf or NaN in this group: full-range libdevice exp for the whole group
 #pragma unroll
       for (int r = 0; r < G; ++r)
@@ -262,9 +282,9 @@ __device__ __forceinline__ void process_rows(const typename Op::Args& args, cons
 }
 
 // a loop trip carries 4 rows (two 128-bit loads of t and of y); they are processed in groups of Op::G
-template <class Op>
+template <class Op, bool BIG, bool CHECK = true>
 __device__ __forceinline__ void process4(const typename Op::Args& args, double2 ta, double2 ya, double2 tb, double2 yb,
-                                         double (&acc)[Op::Q]) {
+                                         double (&acc)[Op::Q], const double* __restrict__ big_tab) {
   constexpr int G = Op::G;
   const double t4[4] = {ta.x, ta.y, tb.x, tb.y}, y4[4] = {ya.x, ya.y, yb.x, yb.y};
 #pragma unroll
@@ -272,13 +292,14 @@ __device__ __forceinline__ void process4(const typename Op::Args& args, double2 
     double tg[G], yg[G];
 #pragma unroll
     for (int r = 0; r < G; ++r) { tg[r] = t4[g0 + r]; yg[r] = y4[g0 + r]; }
-    process_rows<Op, G>(args, tg, yg, acc);
+    process_rows<Op, G, BIG, CHECK>(args, tg, yg, acc, big_tab);
   }
 }
-template <class Op>
-__device__ __forceinline__ void process1(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q]) {
+template <class Op, bool BIG>
+__device__ __forceinline__ void process1(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q],
+                                         const double* __restrict__ big_tab) {
   const double tg[1] = {t}, yg[1] = {y};
-  process_rows<Op, 1>(args, tg, yg, acc);
+  process_rows<Op, 1, BIG>(args, tg, yg, acc, big_tab);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -294,17 +315,20 @@ __device__ __forceinline__ void process1(const typename Op::Args& args, double t
 //   ring + __syncthreads per chunk     FP64 pipe 70% busy, 9% of samples on the barrier     r1_k2_v2_block_ring.json
 //   warp-private rings (1 KB copies)   slower than the block ring (54% vs 64% of roofline)  DESIGN.md
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int stages_for(int rpt) { return rpt >= 8 ? 3 : 4; }
-constexpr size_t ring_bytes(int tpb, int rpt) { return (size_t)stages_for(rpt) * tpb * rpt * 16; }
+__host__ __device__ constexpr int stages_for(int rpt, bool big = false) { return rpt >= 8 ? (big ? 2 : 3) : 4; }
+constexpr size_t ring_bytes(int tpb, int rpt, bool big) { return (size_t)stages_for(rpt, big) * tpb * rpt * 16; }
+constexpr size_t smem_bytes(int tpb, int rpt, bool big) { return ring_bytes(tpb, rpt, big) + (big ? sizeof(double) * kExpBigSize : 0); }
 
-template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4>
+template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4, bool BIG = false, bool CHECK = true>
 __global__ void __launch_bounds__(TPB, MINBLOCKS)
 k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t rows,
          const __grid_constant__ typename Op::Args args,
          double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  constexpr int Q = Op::Q, WPB = TPB / 32, kChunkRows = TPB * RPT, kStages = stages_for(RPT);
+  constexpr int Q = Op::Q, WPB = TPB / 32, kChunkRows = TPB * RPT, kStages = stages_for(RPT, BIG);
   constexpr size_t kStageBytes = (size_t)kChunkRows * 16;
-  extern __shared__ __align__(128) unsigned char s_ring[];      // [kStages][ t: kChunkRows doubles | y: kChunkRows doubles ]
+  extern __shared__ __align__(128) unsigned char s_dyn[];       // [4096-entry exp table (BIG)] [kStages][ t | y ]
+  const double* big_tab = reinterpret_cast<const double*>(s_dyn);
+  unsigned char* s_ring = s_dyn + (BIG ? sizeof(double) * kExpBigSize : 0);
   __shared__ double s_red[WPB * Q];
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -331,7 +355,7 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
     for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WPB); }
     mbar_fence_init();
   }
-  if constexpr (Op::NEXP > 0) exp_table_init();
+  if constexpr (Op::NEXP > 0) { if (BIG) exp_big_table_init(reinterpret_cast<double*>(s_dyn)); else exp_table_init(); }
   __syncthreads();
   if (tid == 0) {
 #pragma unroll
@@ -380,22 +404,23 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
 #pragma unroll
     for (int j = 0; j < RPT / 2; j += 2) {
       if (tid + (j + 1) * TPB < npairs) {
-        process4<Op>(args, tv[j], yv[j], tv[j + 1], yv[j + 1], acc);
+        process4<Op, BIG, CHECK>(args, tv[j], yv[j], tv[j + 1], yv[j + 1], acc, big_tab);
       } else {
-        if (tid + j * TPB < npairs) { process1<Op>(args, tv[j].x, yv[j].x, acc); process1<Op>(args, tv[j].y, yv[j].y, acc); }
+        if (tid + j * TPB < npairs) { process1<Op, BIG>(args, tv[j].x, yv[j].x, acc, big_tab); process1<Op, BIG>(args, tv[j].y, yv[j].y, acc, big_tab); }
       }
     }
   }
-  if (blockIdx.x == 0 && tid == 0 && head) process1<Op>(args, t[0], y[0], acc);
-  if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op>(args, t[rows - 1], y[rows - 1], acc);
+  if (blockIdx.x == 0 && tid == 0 && head) process1<Op, BIG>(args, t[0], y[0], acc, big_tab);
+  if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op, BIG>(args, t[rows - 1], y[rows - 1], acc, big_tab);
 
-  grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket);
+  if constexpr (Op::kHasSrc) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, args.src);
+  else grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket);
 }
 
-template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4>
+template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4, bool BIG = false, bool CHECK = true>
 int launch_op_cfg(const Shard& s, const typename Op::Args& args) {
-  auto kern = k_scalar<Op, TPB, MINBLOCKS, MODE, RPT>;
-  constexpr size_t smem = ring_bytes(TPB, RPT);
+  auto kern = k_scalar<Op, TPB, MINBLOCKS, MODE, RPT, BIG, CHECK>;
+  constexpr size_t smem = smem_bytes(TPB, RPT, BIG);
   static int per_sm_dev[64] = {0};   // per instantiation and per device: function attributes are per-device state
   int dev = 0;
   cudaGetDevice(&dev);
@@ -442,27 +467,19 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       for (int i = 0; i < N; ++i) for (int j = i; j < N; ++j) a.scale[q++] = pre.D[i] * pre.D[j];
       for (int i = 0; i < N; ++i) a.scale[Op::T + i] = -pre.D[i];     // J = -sign(rho) df/dp, r = |rho|  =>  J r = -df/dp rho
       a.scale[Op::T + N] = 1.0;
+      for (int q2 = 0; q2 < Op::Q; ++q2) a.src[q2] = (signed char)q2;
+      for (int i = 0; i < N; ++i) for (int j = i; j < N; ++j) {
+        int si = 0, sj = 0;
+        if (Fam::gram_alias(i, j, si, sj)) a.src[Op::packed(i, j)] = (signed char)Op::packed(si, sj);
+      }
       if constexpr (std::is_same<Fam, FamGaussExpBkg>::value) {
-        // tuning variants: rows per range-checked group x threads per block x resident blocks per SM (SO_K2_VARIANT)
-        const char* v = getenv("SO_K2_VARIANT");
-        const int var = v ? atoi(v) : 0;
-        auto relaunch = [&](auto gtag, auto tpbtag, auto mbtag, auto rpttag) -> int {
-          using Op2 = OpNormalEq<Fam, decltype(gtag)::value>;
-          typename Op2::Args a2; a2.pre = a.pre;
-          for (int q2 = 0; q2 < Op2::Q; ++q2) a2.scale[q2] = a.scale[q2];
-          return launch_op_cfg<Op2, decltype(tpbtag)::value, decltype(mbtag)::value, 0, decltype(rpttag)::value>(s, a2);
-        };
-        using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>; using I3 = std::integral_constant<int, 3>;
-        using I4 = std::integral_constant<int, 4>; using I5 = std::integral_constant<int, 5>; using I6 = std::integral_constant<int, 6>;
-        using I8 = std::integral_constant<int, 8>;
-        using T128 = std::integral_constant<int, 128>; using T256 = std::integral_constant<int, 256>;
-        if (var == 1) return relaunch(I2(), T128(), I5(), I4());
-        if (var == 2) return relaunch(I1(), T256(), I3(), I4());
-        if (var == 3) return relaunch(I1(), T128(), I6(), I4());
-        if (var == 4) return relaunch(I2(), T128(), I4(), I8());
-        if (var == 5) return relaunch(I1(), T128(), I5(), I4());
-        if (var == 6) return relaunch(I4(), T128(), I4(), I8());
-        return relaunch(I2(), T256(), I2(), I8());
+        // the headline kernel (BASELINE config 3): 2 rows per range-checked group, 8 rows per thread per chunk,
+        // 2 blocks/SM.  A/B runs on one box (gpurun_out/call26-27): 4 rows per group -1 %, 4 rows per
+        // chunk -3 %, 4096-entry exp table (degree-3 polynomial) +1.5 %, no range check at all +1.5 %, 20-24 warps/SM -8..-25 %.
+        using Op2 = OpNormalEq<Fam, 2>;
+        typename Op2::Args a2; a2.pre = a.pre;
+        for (int q2 = 0; q2 < Op2::Q; ++q2) { a2.scale[q2] = a.scale[q2]; a2.src[q2] = a.src[q2]; }
+        return launch_op_cfg<Op2, 256, 2, 0, 8, false, true>(s, a2);
       }
       return launch_op<Op, (Op::Q < 21 ? 3 : 2)>(s, a);
     }
