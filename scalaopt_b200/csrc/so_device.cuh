@@ -144,7 +144,8 @@ __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p);
 template <int Q>
 __device__ __forceinline__ void grid_reduce(double (&acc)[Q], double* smem, double* __restrict__ partials,
                                             double* __restrict__ out, const double* __restrict__ scale,
-                                            unsigned int* ticket, const signed char* __restrict__ src = nullptr) {
+                                            unsigned int* ticket, const signed char* __restrict__ src = nullptr,
+                                            int qout = Q, const double* __restrict__ scale2 = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
@@ -164,11 +165,14 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[Q], double* smem, doub
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
-      const int qs = src ? (int)src[q] : q;        // out[q] may be another accumulator's sum (identical sums are kept once)
-      double s = 0.0;
+    // out[q] = scale[q] * S[src[q]]  (+ scale2[q] * S[qout + q] when the result is the sum of two accumulator sets)
+    for (int q = threadIdx.x; q < qout; q += blockDim.x) {
+      const int qs = src ? (int)src[q] : q;        // identical sums are kept once
+      double s = 0.0, s2 = 0.0;
       for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * Q + qs]);
-      out[q] = scale ? s * scale[q] : s;
+      if (scale2) for (unsigned b = 0; b < gridDim.x; ++b) s2 += __ldcg(&partials[(size_t)b * Q + qout + q]);
+      const double v = scale ? s * scale[q] : s;
+      out[q] = scale2 ? fma(s2, scale2[q], v) : v;
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }

@@ -52,9 +52,13 @@ struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarqua
     f = c.p0 * ex[0];
   }
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) { return fma(-c.p0, ex[0], y); }
-  __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
-    h[0] = u[1] * d[1];
-    h[1] = fma(c.p0 * t * u[1], d[1], u[1] * d[0]);
+  // B_i += rho * (d2f/dp2 . d)_i :  h0 = t e d1,  h1 = t e d0 + p0 t^2 e d1
+  struct HPre { double d0, d1, p0d1; };
+  static HPre hprepare(const double* p, const double* d) { HPre h; h.d0 = d[0]; h.d1 = d[1]; h.p0d1 = p[0] * d[1]; return h; }
+  __device__ static __forceinline__ void hess_b(const Pre&, const HPre& h, double t, const double (&u)[N], double rho, double* B) {
+    const double w = rho * u[1];                       // rho t e
+    B[0] = fma(w, h.d1, B[0]);
+    B[1] = fma(w, fma(h.p0d1, t, h.d0), B[1]);
   }
 };
 
@@ -80,14 +84,29 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
     f = c.A * ex[0];
   }
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) { return fma(-c.A, ex[0], y); }
-  __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
-    const double z = (t - c.mu) * c.s, g = u[0], z2 = z * z;
-    const double gs = g * c.s, Ags2 = c.A * gs * c.s;
-    const double HAm = gs * z, HAs = gs * z2;
-    const double Hmm = Ags2 * (z2 - 1.0), Hms = Ags2 * z * (z2 - 2.0), Hss = Ags2 * z2 * (z2 - 3.0);
-    h[0] = HAm * d[1] + HAs * d[2];
-    h[1] = HAm * d[0] + Hmm * d[1] + Hms * d[2];
-    h[2] = HAs * d[0] + Hms * d[1] + Hss * d[2];
+  // B_i += rho * (d2f/dp2 . d)_i in Horner form in v = zz = z/sqrt2 with host-side coefficients (see hprepare):
+  //   h0 = g v (a0 + a1 v),  h1 = g (b0 + v (b1 + v (b2 + v b3))),  h2 = g v (c0 + v (c1 + v (c2 + v c3)))
+  struct HGauss { double a0, a1, b0, b1, b2, b3, c0, c1, c2, c3; };
+  static HGauss hgauss(const double* p, const double* d) {
+    const double A = p[0], s = 1.0 / p[2], r2 = kSqrt2, As2 = A * s * s;
+    HGauss h;
+    h.a0 = s * d[1] * r2;            h.a1 = s * d[2] * 2.0;                    // z = r2 v, z^2 = 2 v^2
+    h.b0 = -As2 * d[1];              h.b1 = (s * d[0] - 2.0 * As2 * d[2]) * r2;
+    h.b2 = As2 * d[1] * 2.0;         h.b3 = As2 * d[2] * 2.0 * r2;
+    h.c0 = -2.0 * As2 * d[1] * r2;   h.c1 = (s * d[0] - 3.0 * As2 * d[2]) * 2.0;
+    h.c2 = As2 * d[1] * 2.0 * r2;    h.c3 = As2 * d[2] * 4.0;
+    return h;
+  }
+  __device__ static __forceinline__ void hess_gauss(const HGauss& h, double v, double g, double gv, double rho, double* B) {
+    const double rg = rho * g, rgv = rho * gv;
+    B[0] = fma(rgv, fma(h.a1, v, h.a0), B[0]);
+    B[1] = fma(rg, fma(fma(fma(h.b3, v, h.b2), v, h.b1), v, h.b0), B[1]);
+    B[2] = fma(rgv, fma(fma(fma(h.c3, v, h.c2), v, h.c1), v, h.c0), B[2]);
+  }
+  struct HPre { HGauss g; };
+  static HPre hprepare(const double* p, const double* d) { HPre h; h.g = hgauss(p, d); return h; }
+  __device__ static __forceinline__ void hess_b(const Pre& c, const HPre& h, double t, const double (&u)[N], double rho, double* B) {
+    hess_gauss(h.g, fma(t, c.sr2, c.nmsr2), u[0], u[1], rho, B);
   }
 };
 
@@ -118,16 +137,16 @@ struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) {
     return fma(-c.B, ex[1], fma(-c.A, ex[0], y));
   }
-  __device__ static __forceinline__ void hdir(const Pre& c, double t, const double (&u)[N], const double* d, double (&h)[N]) {
-    const double z = (t - c.mu) * c.s, g = u[0], z2 = z * z;
-    const double gs = g * c.s, Ags2 = c.A * gs * c.s;
-    const double HAm = gs * z, HAs = gs * z2;
-    const double Hmm = Ags2 * (z2 - 1.0), Hms = Ags2 * z * (z2 - 2.0), Hss = Ags2 * z2 * (z2 - 3.0);
-    h[0] = HAm * d[1] + HAs * d[2];
-    h[1] = HAm * d[0] + Hmm * d[1] + Hms * d[2];
-    h[2] = HAs * d[0] + Hms * d[1] + Hss * d[2];
-    h[3] = -u[4] * d[4];                                  // d2f/dB dlambda = -t e
-    h[4] = fma(c.B * t * u[4], d[4], -u[4] * d[3]);       // d2f/dlambda^2 = B t^2 e
+  // Gaussian part as in FamGauss; exponential part: h3 = -t e d4, h4 = -t e d3 + B t^2 e d4
+  struct HPre { FamGauss::HGauss g; double nd4, nd3, Bd4; };
+  static HPre hprepare(const double* p, const double* d) {
+    HPre h; h.g = FamGauss::hgauss(p, d); h.nd4 = -d[4]; h.nd3 = -d[3]; h.Bd4 = p[3] * d[4]; return h;
+  }
+  __device__ static __forceinline__ void hess_b(const Pre& c, const HPre& h, double t, const double (&u)[N], double rho, double* B) {
+    FamGauss::hess_gauss(h.g, fma(t, c.sr2, c.nmsr2), u[0], u[1], rho, B);
+    const double w = rho * u[4];                       // rho t e
+    B[3] = fma(w, h.nd4, B[3]);
+    B[4] = fma(w, fma(h.Bd4, t, h.nd3), B[4]);
   }
 };
 
@@ -150,10 +169,9 @@ struct FamPoly {       // f = sum_k p_k t^k
     f = s;
   }
   __device__ static __forceinline__ double residual(const Pre&, double y, const double*, double f) { return y - f; }
-  __device__ static __forceinline__ void hdir(const Pre&, double, const double (&)[N], const double*, double (&h)[N]) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) h[k] = 0.0;
-  }
+  struct HPre { double unused; };                    // linear in the parameters: no second-derivative term
+  static HPre hprepare(const double*, const double*) { return HPre{0.0}; }
+  __device__ static __forceinline__ void hess_b(const Pre&, const HPre&, double, const double (&)[N], double, double*) {}
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -229,20 +247,23 @@ struct OpLine {
 
 template <class Fam>
 struct OpHessVec {
-  static constexpr int N = Fam::N, Q = N, NEXP = Fam::NE, G = 2;
+  // H d = (1/m) sum_i [ (J_f . d) J_f - rho (d2f/dp2 . d) ]  with J_f = D o u:
+  //   acc[0..N)  = sum (dd . u) u_i      (dd = D o d; scaled by D_i on the way out)
+  //   acc[N..2N) = sum rho h_i           (subtracted on the way out)
+  static constexpr int N = Fam::N, Q = 2 * N, NEXP = Fam::NE, G = 2;
   static constexpr bool kHasSrc = false;
-  struct Args { typename Fam::Pre pre; double d[N]; double scale[Q]; };
+  struct Args { typename Fam::Pre pre; typename Fam::HPre h; double dd[N]; double scale[N]; double scale2[N]; };
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
-    double f, u[N], h[N], J[N];
+    double f, u[N];
     Fam::finish(a.pre, t, ex, f, u);
     const double rho = Fam::residual(a.pre, y, ex, f);
     double jd = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { J[i] = a.pre.D[i] * u[i]; jd = fma(J[i], a.d[i], jd); }
-    Fam::hdir(a.pre, t, u, a.d, h);
+    for (int i = 0; i < N; ++i) jd = fma(a.dd[i], u[i], jd);
 #pragma unroll
-    for (int i = 0; i < N; ++i) acc[i] += fma(jd, J[i], -rho * h[i]);
+    for (int i = 0; i < N; ++i) acc[i] = fma(jd, u[i], acc[i]);
+    Fam::hess_b(a.pre, a.h, t, u, rho, &acc[N]);
   }
 };
 
@@ -414,6 +435,7 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
   if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op, BIG>(args, t[rows - 1], y[rows - 1], acc, big_tab);
 
   if constexpr (Op::kHasSrc) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, args.src);
+  else if constexpr (requires { args.scale2; }) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, nullptr, Q / 2, args.scale2);
   else grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket);
 }
 
@@ -509,8 +531,8 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
     }
     case kHessVec: {
       using Op = OpHessVec<Fam>;
-      typename Op::Args a; a.pre = pre;
-      for (int i = 0; i < N; ++i) { a.d[i] = d[i]; a.scale[i] = 1.0; }
+      typename Op::Args a; a.pre = pre; a.h = Fam::hprepare(p, d);
+      for (int i = 0; i < N; ++i) { a.dd[i] = pre.D[i] * d[i]; a.scale[i] = pre.D[i]; a.scale2[i] = -1.0; }
       return launch_op<Op, 3>(s, a);
     }
   }
