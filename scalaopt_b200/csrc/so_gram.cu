@@ -105,16 +105,21 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 template <int T> __host__ __device__ constexpr int tri_tiles() { return T * (T + 1) / 2; }
 
-template <int FAM, int T>
+// EXTRA = true (f a multiple of 8): the tiles cover the f input columns only; the intercept's 1-column and the
+// residual column are NOT padded into a sixth tile column — their sums (sum x_c, sum x_c res, sum res, sum res^2,
+// row count) are accumulated with plain DADD/DFMA on the FP64 pipe, which is idle while the tensor pipe runs the
+// DMMAs.  For f = 32 that is 10 DMMAs per 4-row slab instead of 15.
+template <int FAM, int T, bool EXTRA>
 __global__ void __launch_bounds__(kThreads, 2)
 k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
            double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   constexpr int NT = tri_tiles<T>();
-  extern __shared__ double smem[];            // NT * 64 doubles: this block's tiles, lane-major
+  constexpr int QT = NT * 64 + (EXTRA ? 16 * T + 4 : 0);   // tiles, then [sum x_c] [sum x_c res] [cnt, sum res, sum res^2]
+  extern __shared__ double smem[];            // QT doubles: this block's tiles (lane-major) and extras
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rsel = lane & 3, csel = lane >> 2;
   const int f = P.f, icpt = P.icpt, n = P.n;
-  const int col_one = icpt ? f : -1, col_res = f + icpt;
+  const int col_one = (icpt && !EXTRA) ? f : -1, col_res = EXTRA ? -2 : f + icpt;
   if (FAM == kLogistic) { exp_table_init(); __syncthreads(); }
 
   double pz[T];
@@ -124,6 +129,9 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
   double acc[NT][2];
 #pragma unroll
   for (int i = 0; i < NT; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  double s_one[EXTRA ? T : 1], s_res[EXTRA ? T : 1], cnt = 0.0, sr = 0.0, rr = 0.0;
+#pragma unroll
+  for (int t = 0; t < (EXTRA ? T : 1); ++t) { s_one[t] = 0.0; s_res[t] = 0.0; }
 
   const int64_t nslabs = (rows + 3) >> 2;
   const int64_t sstr = (int64_t)gridDim.x * kWarps;
@@ -145,6 +153,15 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
   while (slab < nslabs) {
     const int64_t ns = slab + sstr;
     if (ns < nslabs) load(ns, nxt, ynxt, vnxt);
+    if (EXTRA) {       // the tiles depend on the loads only: issue them first, the residual chain overlaps with them
+#pragma unroll
+      for (int ta = 0; ta < T; ++ta)
+#pragma unroll
+        for (int tb = ta; tb < T; ++tb) {
+          const int idx = ta * T - ta * (ta - 1) / 2 + (tb - ta);
+          dmma(acc[idx][0], acc[idx][1], cur[ta], cur[tb]);
+        }
+    }
     // linear predictor of the slab's 4 rows: lanes with equal lane%4 hold one row
     double dot = 0.0;
 #pragma unroll
@@ -162,26 +179,42 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
       res = ((z >= 0.0) ? inv : e * inv) - ycur;
     }
     if (!vcur) res = 0.0;
-    const double one = vcur ? 1.0 : 0.0;
+    if (EXTRA) {
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const int col = 8 * t + csel;
-      if (col == col_one) cur[t] = one;
-      if (col == col_res) cur[t] = res;
-    }
+      for (int t = 0; t < T; ++t) { s_one[t] += cur[t]; s_res[t] = fma(cur[t], res, s_res[t]); }
+      if (csel == 0) { cnt += vcur ? 1.0 : 0.0; sr += res; rr = fma(res, res, rr); }
+    } else {
+      const double one = vcur ? 1.0 : 0.0;
 #pragma unroll
-    for (int ta = 0; ta < T; ++ta)
-#pragma unroll
-      for (int tb = ta; tb < T; ++tb) {
-        const int idx = ta * T - ta * (ta - 1) / 2 + (tb - ta);
-        dmma(acc[idx][0], acc[idx][1], cur[ta], cur[tb]);
+      for (int t = 0; t < T; ++t) {
+        const int col = 8 * t + csel;
+        if (col == col_one) cur[t] = one;
+        if (col == col_res) cur[t] = res;
       }
+    }
+    if (!EXTRA) {
+#pragma unroll
+      for (int ta = 0; ta < T; ++ta)
+#pragma unroll
+        for (int tb = ta; tb < T; ++tb) {
+          const int idx = ta * T - ta * (ta - 1) / 2 + (tb - ta);
+          dmma(acc[idx][0], acc[idx][1], cur[ta], cur[tb]);
+        }
+    }
 #pragma unroll
     for (int t = 0; t < T; ++t) cur[t] = nxt[t];
     ycur = ynxt; vcur = vnxt;
     slab = ns;
   }
 
+  if (EXTRA) {      // fold the 4 row slots of a column (lanes csel*4 + 0..3), and the per-row scalars over the warp
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      s_one[t] += __shfl_xor_sync(0xffffffffu, s_one[t], 1); s_one[t] += __shfl_xor_sync(0xffffffffu, s_one[t], 2);
+      s_res[t] += __shfl_xor_sync(0xffffffffu, s_res[t], 1); s_res[t] += __shfl_xor_sync(0xffffffffu, s_res[t], 2);
+    }
+    cnt = warp_sum(cnt); sr = warp_sum(sr); rr = warp_sum(rr);
+  }
   // block sum in warp order (deterministic), lane-major tile storage: tile[idx][lane*2 + reg]
   for (int w = 0; w < kWarps; ++w) {
     if (warp == w) {
@@ -191,10 +224,24 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
         if (w == 0) { tile[0] = acc[i][0]; tile[1] = acc[i][1]; }
         else { tile[0] += acc[i][0]; tile[1] += acc[i][1]; }
       }
+      if (EXTRA) {
+        double* ex = smem + NT * 64;
+        if (rsel == 0) {
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            if (w == 0) { ex[8 * t + csel] = s_one[t]; ex[8 * T + 8 * t + csel] = s_res[t]; }
+            else { ex[8 * t + csel] += s_one[t]; ex[8 * T + 8 * t + csel] += s_res[t]; }
+          }
+        }
+        if (lane == 0) {
+          double* sc = ex + 16 * T;
+          if (w == 0) { sc[0] = cnt; sc[1] = sr; sc[2] = rr; sc[3] = 0.0; }
+          else { sc[0] += cnt; sc[1] += sr; sc[2] += rr; }
+        }
+      }
     }
     __syncthreads();
   }
-  constexpr int QT = NT * 64;
   for (int q = threadIdx.x; q < QT; q += kThreads) partials[(size_t)blockIdx.x * QT + q] = smem[q];
   __threadfence();
   __syncthreads();
@@ -204,8 +251,10 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
   if (s_last) {
     __threadfence();
     // emit the API layout: packed upper triangle over parameters (a <= b), then Jtr, then rtr.
-    // parameter a lives in Z column za = (icpt ? (a == 0 ? f : a - 1) : a); the residual in column col_res.
+    // Z column of parameter a: (icpt ? (a == 0 ? ONE : a - 1) : a); ONE = the intercept's 1-column, RES = the residual.
+    constexpr int ONE = -1, RES = -2;
     const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
+    const double jsgn = (FAM == kLinear) ? -1.0 : 1.0;         // J r = -x~ rho for least squares
     for (int q = threadIdx.x; q < Qo; q += kThreads) {
       int ca, cb;
       double sgn = 1.0;
@@ -213,19 +262,37 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
         int a = 0, rem = q;                     // unpack (a, b) from the row-major packed index
         while (rem >= n - a) { rem -= n - a; ++a; }
         const int b = a + rem;
-        ca = icpt ? (a == 0 ? f : a - 1) : a;
-        cb = icpt ? (b == 0 ? f : b - 1) : b;
+        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
+        cb = icpt ? (b == 0 ? ONE : b - 1) : b;
       } else if (q < Tn + n) {
         const int a = q - Tn;
-        ca = icpt ? (a == 0 ? f : a - 1) : a;
-        cb = col_res;
-        if (FAM == kLinear) sgn = -1.0;
+        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
+        cb = RES;
+        sgn = jsgn;
       } else {
-        ca = col_res; cb = col_res;
+        ca = RES; cb = RES;
       }
-      if (ca / 8 > cb / 8) { const int tmp = ca; ca = cb; cb = tmp; }
-      const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
-      const int off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
+      int off;
+      if (EXTRA) {
+        const int ex = NT * 64;
+        if (ca >= 0 && cb >= 0) {
+          if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }
+          const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
+          off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
+        } else if (ca == ONE && cb == ONE) off = ex + 16 * T;                 // row count
+        else if (ca == RES && cb == RES) off = ex + 16 * T + 2;               // sum res^2
+        else if ((ca == ONE && cb == RES) || (ca == RES && cb == ONE)) off = ex + 16 * T + 1;   // sum res
+        else if (ca == ONE || cb == ONE) off = ex + (ca == ONE ? cb : ca);    // sum x_c
+        else off = ex + 8 * T + (ca == RES ? cb : ca);                        // sum x_c res
+      } else {
+        if (ca == ONE) ca = f;
+        if (cb == ONE) cb = f;
+        if (ca == RES) ca = f + icpt;
+        if (cb == RES) cb = f + icpt;
+        if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }
+        const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
+        off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
+      }
       double s = 0.0;
       for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += __ldcg(&partials[(size_t)b2 * QT + off]);
       out[q] = s * sgn;
@@ -234,10 +301,10 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
   }
 }
 
-template <int FAM, int T>
+template <int FAM, int T, bool EXTRA>
 int launch_tri(const Shard& s, const Params& P) {
-  auto kern = k_gram_tri<FAM, T>;
-  constexpr int QT = tri_tiles<T>() * 64;
+  auto kern = k_gram_tri<FAM, T, EXTRA>;
+  constexpr int QT = tri_tiles<T>() * 64 + (EXTRA ? 16 * T + 4 : 0);
   const size_t smem = sizeof(double) * QT;
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
@@ -253,17 +320,25 @@ int launch_tri(const Shard& s, const Params& P) {
 
 template <int FAM>
 int dispatch_tri(const Shard& s, const Params& P) {
+  if (P.f % 8 == 0) {                      // tiles over the inputs only, extras on the FP64 pipe
+    switch (P.f / 8) {
+      case 1: return launch_tri<FAM, 1, true>(s, P);
+      case 2: return launch_tri<FAM, 2, true>(s, P);
+      case 3: return launch_tri<FAM, 3, true>(s, P);
+      case 4: return launch_tri<FAM, 4, true>(s, P);
+      case 5: return launch_tri<FAM, 5, true>(s, P);
+    }
+  }
   const int T = (P.n + 1 + 7) / 8;
   switch (T) {
-    case 2: return launch_tri<FAM, 2>(s, P);
-    case 3: return launch_tri<FAM, 3>(s, P);
-    case 4: return launch_tri<FAM, 4>(s, P);
-    case 5: return launch_tri<FAM, 5>(s, P);
-    case 6: return launch_tri<FAM, 6>(s, P);
+    case 2: return launch_tri<FAM, 2, false>(s, P);
+    case 3: return launch_tri<FAM, 3, false>(s, P);
+    case 4: return launch_tri<FAM, 4, false>(s, P);
+    case 5: return launch_tri<FAM, 5, false>(s, P);
+    case 6: return launch_tri<FAM, 6, false>(s, P);
   }
   return SO_EUNSUPPORTED;
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // n + 1 > 48 (up to 514 columns): shared-memory staged DMMA SYRK.
@@ -497,7 +572,7 @@ size_t gram_partials_needed(int n, int f, int sm_count) {
   (void)f;
   if (n <= 8) return (size_t)sm_count * 8 * (size_t)(n * (n + 1) / 2 + n + 1);
   const int T = (n + 1 + 7) / 8;
-  if (n + 1 <= 48) return (size_t)sm_count * 4 * (size_t)(T * (T + 1) / 2) * 64;
+  if (n + 1 <= 48) return (size_t)sm_count * 4 * ((size_t)(T * (T + 1) / 2) * 64 + 16 * T + 4);
   const BigPlan b = big_plan(n, sm_count);
   return (size_t)b.workers * b.npatches * kPatch * kPatch * 64;
 }
