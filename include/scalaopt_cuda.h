@@ -110,9 +110,16 @@ void so_host_free(void* p);
  * used for the 1/m normalisation is the sum over ranks. */
 int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out);
 
-/* Append `rows` observations from host memory (H2D, chunked through pinned staging when the source is
- * pageable).  `DataSet.++` (DataSet.scala:36) / Seq -> data-set conversion (SeqDataSetConverter.scala:28). */
+/* Append `rows` observations from host memory.  Pinned sources (so_host_alloc, cudaHostRegister) are copied directly;
+ * pageable sources are staged through two pinned buffers so that the host-side memcpy overlaps the DMA.  `DataSet.++` (DataSet.scala:36) / Seq -> data-set conversion (SeqDataSetConverter.scala:28). */
 int so_dataset_append(so_dataset* ds, const double* X_rowmajor, const double* y, int64_t rows);
+
+/* Append `rows` observations from raw little-endian fp64 files: `path_X` holds row-major X (f doubles per row), `path_y`
+ * one double per row; reading starts `file_row_offset` rows into both files.  Chunks are read into two pinned staging
+ * buffers and copied to HBM asynchronously, so disk reads, H2D copies and (multi-GPU) the shards' copies overlap.
+ * The reference has no on-disk format (its data sets are Scala collections or RDDs); this is the converter a
+ * `SparkDataSet -> GpuDataSet` bridge would write partitions through. */
+int so_dataset_load_raw(so_dataset* ds, const char* path_X, const char* path_y, int64_t rows, int64_t file_row_offset);
 
 /* Forget the observations but keep the HBM reservation (re-ingest into the same data set). */
 int so_dataset_clear(so_dataset* ds);

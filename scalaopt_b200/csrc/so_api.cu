@@ -8,6 +8,8 @@
 // (spark-apps/.../SparkDataSetConverter.scala:42-45).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <nccl.h>   // types only: the library is dlopen'ed on first multi-GPU use (see NcclApi)
 
 #include <algorithm>
@@ -17,6 +19,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "so_internal.h"
@@ -80,6 +83,9 @@ struct Device {
   unsigned int* ticket = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   ncclComm_t comm = nullptr;
+  // ingest: two pinned staging buffers (allocated on first use) and the events that mark them free again
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
 };
 
 }  // namespace
@@ -171,6 +177,7 @@ void teardown(so_ctx* ctx) {
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
     if (d.ev2) cudaEventDestroy(d.ev2);
+    for (int k = 0; k < 2; ++k) { if (d.stage[k]) cudaFreeHost(d.stage[k]); if (d.stage_free[k]) cudaEventDestroy(d.stage_free[k]); }
     if (d.stream) cudaStreamDestroy(d.stream);
   }
 }
@@ -449,30 +456,147 @@ extern "C" void so_dataset_free(so_dataset* ds) {
   delete ds;
 }
 
-extern "C" int so_dataset_append(so_dataset* ds, const double* X, const double* y, int64_t rows) {
-  if (!ds) return SO_EINVAL;
+namespace {
+
+constexpr size_t kStageBytes = (size_t)64 << 20;      // per pinned staging buffer
+
+int ensure_staging(so_ctx* ctx, Device& dv) {
+  SO_CUDA(ctx, cudaSetDevice(dv.id));
+  for (int k = 0; k < 2; ++k) {
+    if (!dv.stage[k]) SO_CUDA(ctx, cudaHostAlloc(&dv.stage[k], kStageBytes, cudaHostAllocDefault));
+    if (!dv.stage_free[k]) SO_CUDA(ctx, cudaEventCreateWithFlags(&dv.stage_free[k], cudaEventDisableTiming));
+  }
+  return SO_OK;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// A source of rows: fills `dst` with `count` doubles starting `elem_offset` doubles into the X or y stream.
+struct RowSource {
+  virtual ~RowSource() = default;
+  virtual int fetch(bool is_y, int64_t elem_offset, int64_t count, double* dst) = 0;
+  virtual const double* direct(bool is_y, int64_t elem_offset) { (void)is_y; (void)elem_offset; return nullptr; }   // pinned: DMA straight from the source
+};
+// host-side part of a staged copy, split over a few threads: one core's memcpy / pread (~10-15 GB/s) is
+// well below what one PCIe 5 x16 link takes (~55 GB/s)
+constexpr int kIngestThreads = 6;
+template <class F>
+int parallel_chunks(int64_t count, F&& body) {      // body(begin, end) -> SO_* code
+  const int64_t grain = (int64_t)1 << 20;             // doubles
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(kIngestThreads, count / grain));
+  if (nt == 1) return body(0, count);
+  std::vector<std::thread> th;
+  std::vector<int> rc(nt, SO_OK);
+  for (int t = 0; t < nt; ++t) {
+    const int64_t b = count * t / nt, e = count * (t + 1) / nt;
+    th.emplace_back([&, t, b, e] { rc[t] = body(b, e); });
+  }
+  for (auto& x : th) x.join();
+  for (int r : rc) if (r != SO_OK) return r;
+  return SO_OK;
+}
+
+struct MemSource : RowSource {
+  const double* X; const double* y; bool pinned;
+  MemSource(const double* X_, const double* y_) : X(X_), y(y_), pinned(is_pinned(X_) && is_pinned(y_)) {}
+  int fetch(bool is_y, int64_t off, int64_t count, double* dst) override {
+    const double* src = (is_y ? y : X) + off;
+    return parallel_chunks(count, [&](int64_t b, int64_t e) { memcpy(dst + b, src + b, sizeof(double) * (size_t)(e - b)); return (int)SO_OK; });
+  }
+  const double* direct(bool is_y, int64_t off) override { return pinned ? (is_y ? y : X) + off : nullptr; }
+};
+struct FileSource : RowSource {
+  int fdx = -1, fdy = -1; int64_t base_rows = 0; int f = 1;
+  ~FileSource() override { if (fdx >= 0) close(fdx); if (fdy >= 0) close(fdy); }
+  int fetch(bool is_y, int64_t off, int64_t count, double* dst) override {
+    const int fd = is_y ? fdy : fdx;
+    const int64_t base = (int64_t)sizeof(double) * ((is_y ? base_rows : base_rows * f) + off);
+    return parallel_chunks(count, [&](int64_t b, int64_t e) {
+      char* out = reinterpret_cast<char*>(dst + b);
+      int64_t pos = base + (int64_t)sizeof(double) * b, left = (int64_t)sizeof(double) * (e - b);
+      while (left > 0) {
+        const ssize_t got = pread(fd, out, (size_t)left, (off_t)pos);
+        if (got <= 0) return (int)SO_EINVAL;           // error or end of file: the file is shorter than promised
+        out += got; pos += got; left -= got;
+      }
+      return (int)SO_OK;
+    });
+  }
+};
+
+// Copy `rows` rows from `src` into the data set, filling the shards in order.  Staged copies alternate between the
+// two pinned buffers of the destination device: while buffer k is in flight to the GPU, buffer k^1 is being filled.
+int ingest(so_dataset* ds, RowSource& src, int64_t rows) {
   so_ctx* ctx = ds->ctx;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_append: cannot append to a view");
-  if (rows < 0 || (rows > 0 && (!X || !y))) return fail(ctx, SO_EINVAL, "so_dataset_append: bad arguments");
   int64_t filled = 0;
   for (const ShardMem& sm : ds->shards) filled += sm.filled;
-  if (filled + rows > ds->m) return fail(ctx, SO_EINVAL, "so_dataset_append: %lld rows do not fit (%lld of %lld used)", (long long)rows, (long long)filled, (long long)ds->m);
+  if (filled + rows > ds->m) return fail(ctx, SO_EINVAL, "ingest: %lld rows do not fit (%lld of %lld used)", (long long)rows, (long long)filled, (long long)ds->m);
+  const int f = ds->f;
   int64_t done = 0;
+  int turn = 0;
   for (size_t g = 0; g < ds->shards.size() && done < rows; ++g) {
     ShardMem& sm = ds->shards[g];
     const int64_t take = std::min<int64_t>(sm.cap - sm.filled, rows - done);
     if (take <= 0) continue;
     Device& dv = ctx->devs[g];
     SO_CUDA(ctx, cudaSetDevice(dv.id));
-    SO_CUDA(ctx, cudaMemcpyAsync(sm.X + (size_t)sm.filled * ds->f, X + (size_t)done * ds->f, sizeof(double) * (size_t)take * ds->f, cudaMemcpyHostToDevice, dv.stream));
-    SO_CUDA(ctx, cudaMemcpyAsync(sm.y + sm.filled, y + done, sizeof(double) * (size_t)take, cudaMemcpyHostToDevice, dv.stream));
+    for (int pass = 0; pass < 2; ++pass) {               // X stream, then y stream
+      const bool is_y = pass == 1;
+      const int64_t width = is_y ? 1 : f;
+      double* dst = is_y ? sm.y + sm.filled : sm.X + (size_t)sm.filled * f;
+      const int64_t total = take * width, src_off = done * width;
+      if (const double* direct = src.direct(is_y, src_off)) {
+        SO_CUDA(ctx, cudaMemcpyAsync(dst, direct, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, dv.stream));
+        continue;
+      }
+      int rc = ensure_staging(ctx, dv);
+      if (rc) return rc;
+      const int64_t chunk = (int64_t)(kStageBytes / sizeof(double));
+      for (int64_t o = 0; o < total; o += chunk, turn ^= 1) {
+        const int64_t cnt = std::min(chunk, total - o);
+        SO_CUDA(ctx, cudaEventSynchronize(dv.stage_free[turn]));           // buffer `turn` has left for the GPU
+        rc = src.fetch(is_y, src_off + o, cnt, (double*)dv.stage[turn]);
+        if (rc) return fail(ctx, rc, "ingest: short read from the source");
+        SO_CUDA(ctx, cudaMemcpyAsync(dst + o, dv.stage[turn], sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, dv.stream));
+        SO_CUDA(ctx, cudaEventRecord(dv.stage_free[turn], dv.stream));
+      }
+    }
     sm.filled += take;
     done += take;
   }
   for (Device& dv : ctx->devs) { SO_CUDA(ctx, cudaSetDevice(dv.id)); SO_CUDA(ctx, cudaStreamSynchronize(dv.stream)); }
   ds->global_m = -1;
   return SO_OK;
+}
+
+}  // namespace
+
+extern "C" int so_dataset_append(so_dataset* ds, const double* X, const double* y, int64_t rows) {
+  if (!ds) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_append: cannot append to a view");
+  if (rows < 0 || (rows > 0 && (!X || !y))) return fail(ctx, SO_EINVAL, "so_dataset_append: bad arguments");
+  MemSource src(X, y);
+  return ingest(ds, src, rows);
+}
+
+extern "C" int so_dataset_load_raw(so_dataset* ds, const char* path_X, const char* path_y, int64_t rows, int64_t file_row_offset) {
+  if (!ds || !path_X || !path_y) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_load_raw: cannot load into a view");
+  if (rows < 0 || file_row_offset < 0) return fail(ctx, SO_EINVAL, "so_dataset_load_raw: bad arguments");
+  FileSource src;
+  src.fdx = open(path_X, O_RDONLY);
+  src.fdy = open(path_y, O_RDONLY);
+  src.base_rows = file_row_offset; src.f = ds->f;
+  if (src.fdx < 0 || src.fdy < 0) return fail(ctx, SO_EINVAL, "so_dataset_load_raw: cannot open %s / %s", path_X, path_y);
+  return ingest(ds, src, rows);
 }
 
 // empty the data set without releasing HBM (lets a caller re-ingest into the same reservation)

@@ -26,6 +26,27 @@ class GpuDataSet : public DataSet<DataPoint> {
   ~GpuDataSet() override { if (owns && ds) so_dataset_free(ds); }
   void check(int rc) const { if (rc != SO_OK) throw GpuError(rc, so_last_error(ctx)); }
 
+  // ---- converters: SeqDataSet / any DataSet[DataPoint] -> GpuDataSet, raw fp64 files -> GpuDataSet ----
+  static std::shared_ptr<GpuDataSet> from(so_ctx* ctx, const DataSet<DataPoint>& data) {
+    const std::vector<DataPoint> rows = data.collect();
+    if (rows.empty()) throw IllegalArgumentException("GpuDataSet.from: empty data set");
+    const int f = (int)rows.front().x.size();
+    so_dataset* nd = nullptr;
+    if (int rc = so_dataset_create(ctx, (int64_t)rows.size(), f, &nd)) throw GpuError(rc, so_last_error(ctx));
+    auto out = std::make_shared<GpuDataSet>(ctx, nd, f, true);
+    std::vector<double> X(rows.size() * (size_t)f), y(rows.size());
+    for (size_t i = 0; i < rows.size(); ++i) { std::copy(rows[i].x.begin(), rows[i].x.end(), X.begin() + i * f); y[i] = rows[i].y; }
+    out->check(so_dataset_append(nd, X.data(), y.data(), (int64_t)rows.size()));
+    return out;
+  }
+  static std::shared_ptr<GpuDataSet> fromRawFiles(so_ctx* ctx, const std::string& path_X, const std::string& path_y, int64_t rows, int f) {
+    so_dataset* nd = nullptr;
+    if (int rc = so_dataset_create(ctx, rows, f, &nd)) throw GpuError(rc, so_last_error(ctx));
+    auto out = std::make_shared<GpuDataSet>(ctx, nd, f, true);
+    out->check(so_dataset_load_raw(nd, path_X.c_str(), path_y.c_str(), rows, 0));
+    return out;
+  }
+
   int64_t size() const override { int64_t m = 0; check(so_dataset_size(ds, &m)); return m; }                 // DataSet.scala:126
   DataPoint head() const override { DataPoint p; p.x.resize(f); check(so_dataset_head(ds, p.x.data(), &p.y)); return p; }   // :82
   std::vector<DataPoint> collect() const override {                                                           // :51, bounded

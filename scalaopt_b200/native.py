@@ -24,7 +24,7 @@ NCCL_UID_BYTES = 128
 EXPORTS = [
     "so_init", "so_nccl_unique_id", "so_init_rank", "so_shutdown", "so_last_error", "so_abi_version",
     "so_host_alloc", "so_host_free",
-    "so_dataset_create", "so_dataset_append", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
+    "so_dataset_create", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
     "so_dataset_size", "so_dataset_head", "so_dataset_slice", "so_dataset_free",
     "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_line", "so_eval_hess_vec", "so_stats",
 ]
@@ -79,6 +79,7 @@ def load():
     L.so_host_free.restype = None
     L.so_dataset_create.argtypes = [vp, i64, i32, C.POINTER(vp)]
     L.so_dataset_append.argtypes = [vp, vp, vp, i64]
+    L.so_dataset_load_raw.argtypes = [vp, C.c_char_p, C.c_char_p, i64, i64]
     L.so_dataset_clear.argtypes = [vp]
     L.so_dataset_generate.argtypes = [vp, i32, _dp, i32, C.c_uint64, C.c_double, i64]
     L.so_dataset_read.argtypes = [vp, i64, i64, vp, vp]
@@ -204,6 +205,11 @@ class Dataset:
 
     def append_raw(self, x_addr: int, y_addr: int, rows: int):
         self.ctx.check(load().so_dataset_append(self._h, x_addr, y_addr, rows))
+        return self
+
+    def load_raw(self, path_x: str, path_y: str, rows: int, file_row_offset: int = 0):
+        """append rows from raw little-endian fp64 files (row-major X, y)"""
+        self.ctx.check(load().so_dataset_load_raw(self._h, os.fsencode(path_x), os.fsencode(path_y), rows, file_row_offset))
         return self
 
     def clear(self):
