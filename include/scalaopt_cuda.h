@@ -182,6 +182,15 @@ int so_eval_line(so_dataset* ds, int family, const double* p, const double* d, i
  * gradient/SteihaugCG.scala:101-111 and variable/Point.scala:75. */
 int so_eval_hess_vec(so_dataset* ds, int family, const double* p, const double* d, int n, double* Hd);
 
+/* Negative log-likelihood: *nll = sum_i -2 log pdf(p, x_i) over the data set's input column (f = 1; the
+ * y column is not read), NOT divided by m — `negLogLikelihood(pdf, data)(p)`, std-apps/.../stats/package.scala:97-103, the
+ * objective `maxLikelihoodFit` (:74-87) hands to Nelder-Mead / BFGS.  Probability-density catalogue:
+ *   SO_PDF_GAUSS_EXPBKG  p = (fSig, mu, sigma, lambda), consts = (xMin):
+ *                        N(x; mu, sigma) fSig + lambda exp(-lambda (x - xMin)) (1 - fSig)
+ *                        (std-apps/.../stats/example/ExSignalPlusBackgroundFit.scala:78-114) */
+typedef enum so_pdf { SO_PDF_GAUSS_EXPBKG = 0, SO_PDF_COUNT = 1 } so_pdf;
+int so_eval_nll(so_dataset* ds, int pdf, const double* p, int n, const double* consts, int nconsts, double* nll);
+
 /* ---------------------------------------------------------------------------------------------
  * Per-call counters (the reference has no metrics; new)
  * ------------------------------------------------------------------------------------------- */

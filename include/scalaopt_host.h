@@ -28,7 +28,8 @@ typedef enum soh_method {
   SOH_BFGS = 1,                 /* gradient/BFGS.scala:57-110 */
   SOH_CONJUGATE_GRADIENT = 2,   /* gradient/ConjugateGradient.scala:53-90 */
   SOH_NEWTON_CG = 3,            /* gradient/NewtonCG.scala:55-82 */
-  SOH_STEIHAUG_CG = 4           /* gradient/SteihaugCG.scala:51-91 */
+  SOH_STEIHAUG_CG = 4,          /* gradient/SteihaugCG.scala:51-91 */
+  SOH_NELDER_MEAD = 5           /* derivativefree/NelderMead.scala:45-65 (default method of stats.maxLikelihoodFit) */
 } soh_method;
 
 /* union of the reference's config case classes; soh_default_config fills the reference's defaults:
@@ -42,6 +43,7 @@ typedef struct soh_config {
   int32_t cg_method;              /* 0 = "FR", 1 = "PR", 2 = "PR+" */
   double delta0, delta_max, eta;  /* Steihaug */
   double x_tol, g_tol, ratio_tol, step_bound, epsmch; int32_t max_inner_iter, max_step_length_iter, use_pivoting;   /* LM */
+  double c_reflection, c_expansion, c_contraction, c_shrink, rel_delta, abs_delta;   /* NelderMeadConfig (NelderMead.scala:307-314) */
 } soh_config;
 int soh_default_config(int method, soh_config* out);
 
@@ -76,6 +78,10 @@ soh_objective* soh_objective_from_callbacks(int n, soh_apply_fn apply, soh_gradi
 /* GpuMSEFunction(family, GpuDataSet(ds)): the drop-in for SimpleMSEFunction (function/MSEFunction.scala:85-147) and for
  * FFNeuralNetworkTrainer's logistic case.  The data set must outlive the objective. */
 soh_objective* soh_objective_gpu(so_ctx* ctx, so_dataset* ds, int f, int family, int n);
+
+/* negLogLikelihood(pdf, GpuDataSet(ds)) _ (std-apps/.../stats/package.scala:97-103) with finite-difference derivatives
+ * (what the reference's implicit `toFunctionWoGradient` gives a plain closure, core/.../package.scala:74-77). */
+soh_objective* soh_objective_gpu_nll(so_ctx* ctx, so_dataset* ds, int pdf, int n, const double* consts, int nconsts);
 
 void soh_objective_free(soh_objective* f);
 int  soh_objective_counters(soh_objective* f, soh_counters* out);

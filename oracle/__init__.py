@@ -75,6 +75,11 @@ def lib():
         L.orc_hess_vec_fd.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_double,
                                       _Fold, _dp]
         L.orc_hess_vec.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, _dp, C.c_int, _Fold, _dp]
+        L.orc_pdf.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_double]
+        L.orc_pdf.restype = C.c_double
+        L.orc_nll.argtypes = [C.c_int, _dp, C.c_int64, _dp, C.c_int, _dp, _Fold]
+        L.orc_nll.restype = C.c_double
+        L.orc_nll_example_data.argtypes = [C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
         L.orc_lm_reference_passes.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_int]
         L.orc_lm_reference_passes.restype = C.c_double
         _lib = L
@@ -237,3 +242,24 @@ def lm_reference_passes(family, X, y, p, threads=1):
     X, y, m, f = _xy(X, y)
     p = _a(p)
     return lib().orc_lm_reference_passes(family, _p(X), _p(y), m, f, _p(p), p.size, threads)
+
+
+PDF_GAUSS_EXPBKG = 0
+
+
+def nll(pdf, x, p, consts, parts=1, threads=1):
+    """negLogLikelihood(pdf, data)(p) = sum -2 log pdf(p, x)   (stats/package.scala:97-103)"""
+    x, p, consts = _a(x).reshape(-1), _a(p), _a(consts)
+    return lib().orc_nll(pdf, _p(x), x.size, _p(p), p.size, _p(consts), _Fold(parts, threads))
+
+
+def pdf(pdf_id, p, consts, x):
+    p, consts = _a(p), _a(consts)
+    return lib().orc_pdf(pdf_id, _p(p), p.size, _p(consts), float(x))
+
+
+def nll_example_data(seed=12345, nb_events=2000, f_signal=0.3, mu=125.0, sigma=10.0, lam=1.0 / 20.0, x_min=50.0):
+    """the sample of ExSignalPlusBackgroundFit.scala:39-55"""
+    x = np.empty(nb_events)
+    lib().orc_nll_example_data(seed, nb_events, f_signal, mu, sigma, lam, x_min, _p(x))
+    return x

@@ -647,6 +647,43 @@ double orc_lm_reference_passes(int family, const double* X, const double* y, int
 }
 
 /* =============================================================================================
+ * Negative log-likelihood (std-apps/.../stats/package.scala:97-103)
+ * =========================================================================================== */
+double orc_pdf(int pdf, const double* p, int n, const double* consts, double x) {
+  (void)n;
+  if (pdf != ORC_PDF_GAUSS_EXPBKG) return NAN;
+  /* ExSignalPlusBackgroundFit.pdf (:78-88): pdfSignal(signalPars, x) * fSig + pdfBkg(bkgPars, x) * (1.0 - fSig) */
+  const double fSig = p[0], mu = p[1], sigma = p[2], lambda = p[3], xMin = consts[0];
+  const double z = (x - mu) / sigma;                                                   /* :101 */
+  const double sig = exp(-z * z / 2.0) / sqrt(2.0 * 3.14159265358979323846) / sigma;   /* :102 */
+  const double bkg = lambda * exp(-lambda * (x - xMin));                               /* :114 */
+  return sig * fSig + bkg * (1.0 - fSig);
+}
+
+typedef struct nll_ctx { int pdf; const double* p; int n; const double* consts; } nll_ctx;
+static void nll_row(const void* vctx, const double* x, double y, int64_t i, double* acc) {
+  const nll_ctx* c = (const nll_ctx*)vctx; (void)y; (void)i;
+  acc[0] = acc[0] - 2.0 * log(orc_pdf(c->pdf, c->p, c->n, c->consts, x[0]));   /* sum - 2.0 * Math.log(pdf(p, x)(0)) */
+}
+
+double orc_nll(int pdf, const double* x, int64_t m, const double* p, int n, const double* consts, orc_fold fold) {
+  nll_ctx c = { pdf, p, n, consts };
+  double acc;
+  fold_rows(nll_row, &c, x, x, m, 1, 1, fold, &acc);   /* the y stream is unused */
+  return acc;
+}
+
+void orc_nll_example_data(int64_t seed, int nb_events, double f_signal, double mu, double sigma, double lambda,
+                          double x_min, double* x) {
+  orc_jrandom r;
+  orc_jrandom_init(&r, seed);
+  for (int i = 0; i < nb_events; ++i) {                                       /* :48-55 */
+    if (orc_jrandom_next_double(&r) < f_signal) x[i] = orc_jrandom_next_gaussian(&r) * sigma + mu;
+    else x[i] = x_min - log(orc_jrandom_next_double(&r)) / lambda;
+  }
+}
+
+/* =============================================================================================
  * Synthetic observations — counter-based so any shard can be generated anywhere
  * =========================================================================================== */
 static uint64_t splitmix64(uint64_t z) {

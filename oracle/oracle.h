@@ -96,6 +96,19 @@ void orc_hess_vec_fd(int family, const double* X, const double* y, int64_t m, in
 void orc_hess_vec(int family, const double* X, const double* y, int64_t m, int f, const double* p, const double* d,
                   int n, orc_fold fold, double* Hd);
 
+/* ---- negative log-likelihood objective ----
+ * negLogLikelihood(pdf, data)(p) = data.aggregate(0.0)((sum, x) => sum - 2.0 * Math.log(pdf(p, x)(0)), _ + _)
+ * (std-apps/.../stats/package.scala:97-103; NOT divided by the data-set size), with the pdf of
+ * std-apps/.../stats/example/ExSignalPlusBackgroundFit.scala:78-114:
+ *   ORC_PDF_GAUSS_EXPBKG: p = (fSig, mu, sigma, lambda), consts = (xMin):
+ *   pdf = N(x; mu, sigma) * fSig + lambda exp(-lambda (x - xMin)) * (1 - fSig) */
+enum { ORC_PDF_GAUSS_EXPBKG = 0 };
+double orc_pdf(int pdf, const double* p, int n, const double* consts, double x);
+double orc_nll(int pdf, const double* x, int64_t m, const double* p, int n, const double* consts, orc_fold fold);
+/* the example's own sample (ExSignalPlusBackgroundFit.scala:39-55): java.util.Random(seed), nbEvents variates */
+void orc_nll_example_data(int64_t seed, int nb_events, double f_signal, double mu, double sigma, double lambda,
+                          double x_min, double* x);
+
 /* faithful multi-pass LM outer-iteration cost model for CPU timing: FD Jacobian matrix + 2n+1-pass QR + loss pass.
  * Returns bNorm. (LevenbergMarquardt.scala:124,164) */
 double orc_lm_reference_passes(int family, const double* X, const double* y, int64_t m, int f, const double* p, int n,

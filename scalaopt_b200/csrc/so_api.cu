@@ -221,10 +221,12 @@ int global_rows(so_dataset* ds, int64_t* m) {
 
 // Run one evaluation: launch per device, sum across devices/ranks, copy the (Q+1) doubles to host.
 // On return `res` holds the summed raw sums and res[Q] the global number of rows.
+struct NllCall { int pdf; const double* consts; int nconsts; };
+
 int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const double* d, int n, const double* alpha,
-             int k, int want_grad, int Q, std::vector<double>& res) {
+             int k, int want_grad, int Q, std::vector<double>& res, const NllCall* nll = nullptr) {
   so_ctx* ctx = ds->ctx;
-  const bool scalar = family_is_scalar_t(family);
+  const bool scalar = nll != nullptr || family_is_scalar_t(family);
   const int G = (int)ctx->devs.size();
   int64_t rows_local = 0, launches = 0;
   // data.size (DataSet.scala:126) is known on the host; in rank mode it is summed over ranks once and cached
@@ -249,8 +251,9 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
       sh.partials = dv.partials; sh.partials_doubles = dv.partials_cap;
       sh.out = dv.out; sh.out_doubles = dv.out_cap; sh.ticket = dv.ticket;
       sh.stream = dv.stream; sh.sm_count = dv.sm_count;
-      rc = scalar ? launch_scalar(kind, sh, family, p, d, n, alpha, k, want_grad)
-                  : launch_wide(kind, sh, family, p, d, n, alpha, k, want_grad);
+      rc = nll ? launch_nll(sh, nll->pdf, p, n, nll->consts, nll->nconsts)
+               : scalar ? launch_scalar(kind, sh, family, p, d, n, alpha, k, want_grad)
+                        : launch_wide(kind, sh, family, p, d, n, alpha, k, want_grad);
       if (rc < 0) {
         if (rc == SO_EUNSUPPORTED) return fail(ctx, rc, "family %d with n=%d, f=%d, k=%d is outside the kernel catalogue", family, n, ds->f, k);
         cudaError_t e = cudaGetLastError();
@@ -295,7 +298,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
   res.assign(ctx->devs[0].hout, ctx->devs[0].hout + Q);
   res.push_back((double)m_global);
   ctx->stats.rows = rows_local;
-  ctx->stats.bytes = rows_local * 8 * (int64_t)(ds->f + 1);
+  ctx->stats.bytes = rows_local * 8 * (int64_t)(nll ? 1 : ds->f + 1);
   ctx->stats.kernel_ms = kernel_ms;
   ctx->stats.device_ms = device_ms;
   ctx->stats.launches = launches;
@@ -760,6 +763,20 @@ extern "C" int so_eval_line(so_dataset* ds, int family, const double* p, const d
   }
   ctx->stats.kernel_ms = acc.kernel_ms; ctx->stats.device_ms = acc.device_ms; ctx->stats.launches = acc.launches;
   ctx->stats.rows = acc.rows; ctx->stats.bytes = acc.bytes;
+  return SO_OK;
+}
+
+extern "C" int so_eval_nll(so_dataset* ds, int pdf, const double* p, int n, const double* consts, int nconsts, double* nll) {
+  if (!ds || !p || !nll) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ds->f != 1) return fail(ctx, SO_EINVAL, "so_eval_nll: the data set must have one input per observation, has f=%d", ds->f);
+  if (pdf < 0 || pdf >= SO_PDF_COUNT) return fail(ctx, SO_EUNSUPPORTED, "so_eval_nll: unknown pdf %d", pdf);
+  NllCall call{pdf, consts, nconsts};
+  std::vector<double> res;
+  int rc = run_eval(ds, kNll, 0, p, nullptr, n, nullptr, 0, 0, 1, res, &call);
+  if (rc) return rc;
+  *nll = res[0];
   return SO_OK;
 }
 

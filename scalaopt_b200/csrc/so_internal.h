@@ -23,7 +23,7 @@ struct Shard {
   int sm_count = 148;
 };
 
-enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4 };
+enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4, kNll = 5 };
 
 // number of doubles each evaluation leaves in Shard::out (before the 1/m normalisation, which the
 // API layer applies after the cross-GPU sum):
@@ -37,6 +37,7 @@ inline int out_doubles(Kind kind, int n, int k) {
     case kNormalEq: return n * (n + 1) / 2 + n + 1;
     case kLine: return 2 * k;
     case kHessVec: return n;
+    case kNll: return 1;
   }
   return 0;
 }
@@ -51,6 +52,9 @@ int launch_scalar(Kind kind, const Shard& s, int family, const double* p, const 
                   const double* alpha, int k, int want_grad);
 int launch_wide(Kind kind, const Shard& s, int family, const double* p, const double* d, int n,
                 const double* alpha, int k, int want_grad);
+
+// sum_i -2 log pdf(p, x_i) -> out[0]; reads the X stream only
+int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* consts, int nconsts);
 
 // padded width KB of the kLine result of launch_scalar: phi at out[0,k), dphi at out[KB, KB+k)
 int scalar_line_block(int k);

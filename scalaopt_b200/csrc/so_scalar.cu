@@ -181,6 +181,7 @@ template <class Fam, bool GRAD>
 struct OpLossGrad {
   static constexpr int N = Fam::N, Q = GRAD ? 1 + N : 1, NEXP = Fam::NE, G = 4;
   static constexpr bool kHasSrc = false;
+  static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre; double scale[Q]; };
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
@@ -200,6 +201,7 @@ struct OpNormalEq {
   static constexpr int N = Fam::N, T = N * (N + 1) / 2, Q = T + N + 1, NEXP = Fam::NE, G = GROUP;
   struct Args { typename Fam::Pre pre; double scale[Q]; signed char src[Q]; };
   static constexpr bool kHasSrc = true;
+  static constexpr bool kNeedsY = true;
   __host__ __device__ static constexpr int packed(int i, int j) { return i * N - i * (i - 1) / 2 + (j - i); }
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
@@ -225,6 +227,7 @@ template <class Fam, int KB>
 struct OpLine {
   static constexpr int N = Fam::N, Q = 2 * KB, NEXP = KB * Fam::NE, G = (KB <= 1 ? 4 : (KB <= 2 ? 2 : 1));
   static constexpr bool kHasSrc = false;
+  static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre[KB]; double dd[KB][N]; double scale[Q]; };   // dd = D(p + alpha d) o d
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) {
 #pragma unroll
@@ -252,6 +255,7 @@ struct OpHessVec {
   //   acc[N..2N) = sum rho h_i           (subtracted on the way out)
   static constexpr int N = Fam::N, Q = 2 * N, NEXP = Fam::NE, G = 2;
   static constexpr bool kHasSrc = false;
+  static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre; typename Fam::HPre h; double dd[N]; double scale[N]; double scale2[N]; };
   __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
@@ -264,6 +268,69 @@ struct OpHessVec {
 #pragma unroll
     for (int i = 0; i < N; ++i) acc[i] = fma(jd, u[i], acc[i]);
     Fam::hess_b(a.pre, a.h, t, u, rho, &acc[N]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Negative log-likelihood: sum_i -2 log pdf(p, x_i), std-apps/.../stats/package.scala:97-103,
+// pdf = N(x; mu, sigma) fSig + lambda exp(-lambda (x - xMin)) (1 - fSig), .../example/ExSignalPlusBackgroundFit.scala:78-114.
+// Only x is read (8 B per observation).  The log is taken ONCE per thread: the kernel keeps the running product of the
+// pdf mantissas in a double and the sum of their exponents in an integer (log prod = sum log), which costs 1 DMUL and
+// ~6 integer instructions per observation instead of a ~40-instruction FP64 log.  A pdf value that is zero, subnormal,
+// inf or NaN takes the libdevice log on the spot (rare), so -2 log 0 = +inf propagates like in the reference.
+// ---------------------------------------------------------------------------------------------------
+struct PdfGaussExpBkg {
+  static constexpr int NE = 2;
+  struct Pre { double sr2, nmsr2, nlam, lamx, cS, cB; };
+  static Pre prepare(const double* p, const double* consts) {
+    Pre c;
+    const double fSig = p[0], mu = p[1], sigma = p[2], lambda = p[3], xMin = consts[0];
+    const double s = 1.0 / sigma;
+    c.sr2 = s * kInvSqrt2; c.nmsr2 = -mu * c.sr2;
+    c.nlam = -lambda; c.lamx = lambda * xMin;
+    c.cS = fSig * s * 0.3989422804014327;        // fSig / (sqrt(2 pi) sigma)
+    c.cB = (1.0 - fSig) * lambda;
+    return c;
+  }
+  __device__ static __forceinline__ void args(const Pre& c, double x, double* a) {
+    const double zz = fma(x, c.sr2, c.nmsr2);
+    a[0] = -zz * zz;                             // -z^2/2
+    a[1] = fma(x, c.nlam, c.lamx);               // -lambda (x - xMin)
+  }
+  __device__ static __forceinline__ double value(const Pre& c, const double* ex) { return fma(c.cS, ex[0], c.cB * ex[1]); }
+};
+
+template <class Pdf>
+struct OpNll {
+  // acc[0] = product of pdf mantissas (renormalised), acc[1] = exponent sum (as an integer in the low word),
+  // acc[2] = sum of logs taken on the slow path; finalize() folds them into acc[0] = sum log pdf
+  static constexpr int Q = 3, NEXP = Pdf::NE, G = 4;
+  static constexpr bool kHasSrc = false, kNeedsY = false;
+  struct Args { typename Pdf::Pre pre; double scale[Q]; };
+  __device__ static __forceinline__ void init(double (&acc)[Q]) { acc[0] = 1.0; acc[1] = 0.0; acc[2] = 0.0; }
+  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Pdf::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void accum(const Args& a, double, double, const double* ex, double (&acc)[Q]) {
+    const double v = Pdf::value(a.pre, ex);
+    const int hi = __double2hiint(v);
+    const unsigned e = (unsigned)hi >> 20;                         // sign + exponent field
+    if (e - 1u < 0x7feu) {                                         // positive normal number
+      const double mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+      acc[0] *= mant;
+      acc[1] = __hiloint2double(0, __double2loint(acc[1]) + (int)e - 1023);
+    } else {
+      acc[2] += log(v);
+    }
+  }
+  // keep the running product in [1, 2): called once per chunk (<= 8 multiplications by mantissas in [1, 2))
+  __device__ static __forceinline__ void renorm(double (&acc)[Q]) {
+    const int hi = __double2hiint(acc[0]);
+    const int e = (hi >> 20) - 1023;
+    acc[0] = __hiloint2double(hi - (e << 20), __double2loint(acc[0]));
+    acc[1] = __hiloint2double(0, __double2loint(acc[1]) + e);
+  }
+  __device__ static __forceinline__ void finalize(double (&acc)[Q]) {
+    acc[0] = fma((double)__double2loint(acc[1]), 0.6931471805599453, log(acc[0])) + acc[2];
+    acc[1] = 0.0; acc[2] = 0.0;
   }
 };
 
@@ -366,9 +433,9 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
     const int64_t r0 = chunk * kChunkRows;
     const uint32_t nr = (uint32_t)min((int64_t)kChunkRows, body - r0);
     double* st = reinterpret_cast<double*>(s_ring + (size_t)stage * kStageBytes);
-    mbar_arrive_expect_tx(&s_full[stage], nr * 16u);
+    mbar_arrive_expect_tx(&s_full[stage], Op::kNeedsY ? nr * 16u : nr * 8u);
     bulk_g2s(st, tb + r0, nr * 8u, &s_full[stage]);
-    bulk_g2s(st + kChunkRows, yb + r0, nr * 8u, &s_full[stage]);
+    if constexpr (Op::kNeedsY) bulk_g2s(st + kChunkRows, yb + r0, nr * 8u, &s_full[stage]);
   };
 
   if (tid == 0) {
@@ -389,6 +456,7 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
   double acc[Q];
 #pragma unroll
   for (int q = 0; q < Q; ++q) acc[q] = 0.0;
+  if constexpr (requires { Op::init(acc); }) Op::init(acc);
 
   int it = 0;
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
@@ -401,7 +469,7 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
 #pragma unroll
     for (int j = 0; j < RPT / 2; ++j) {
       tv[j] = reinterpret_cast<const double2*>(st)[tid + j * TPB];
-      yv[j] = reinterpret_cast<const double2*>(st + kChunkRows)[tid + j * TPB];
+      yv[j] = Op::kNeedsY ? reinterpret_cast<const double2*>(st + kChunkRows)[tid + j * TPB] : make_double2(0.0, 0.0);
     }
     if (MODE == 0) {
       __syncthreads();                                          // every thread holds its rows: the stage can be refilled
@@ -430,9 +498,11 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
         if (tid + j * TPB < npairs) { process1<Op, BIG>(args, tv[j].x, yv[j].x, acc, big_tab); process1<Op, BIG>(args, tv[j].y, yv[j].y, acc, big_tab); }
       }
     }
+    if constexpr (requires { Op::renorm(acc); }) Op::renorm(acc);
   }
-  if (blockIdx.x == 0 && tid == 0 && head) process1<Op, BIG>(args, t[0], y[0], acc, big_tab);
-  if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op, BIG>(args, t[rows - 1], y[rows - 1], acc, big_tab);
+  if (blockIdx.x == 0 && tid == 0 && head) process1<Op, BIG>(args, t[0], Op::kNeedsY ? y[0] : 0.0, acc, big_tab);
+  if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op, BIG>(args, t[rows - 1], Op::kNeedsY ? y[rows - 1] : 0.0, acc, big_tab);
+  if constexpr (requires { Op::finalize(acc); }) { Op::renorm(acc); Op::finalize(acc); }
 
   if constexpr (Op::kHasSrc) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, args.src);
   else if constexpr (requires { args.scale2; }) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, nullptr, Q / 2, args.scale2);
@@ -535,6 +605,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       for (int i = 0; i < N; ++i) { a.dd[i] = pre.D[i] * d[i]; a.scale[i] = pre.D[i]; a.scale2[i] = -1.0; }
       return launch_op<Op, 3>(s, a);
     }
+    case kNll: break;      // served by launch_nll
   }
   return SO_EINVAL;
 }
@@ -546,6 +617,17 @@ size_t scalar_partials_needed(Kind kind, int n, int k, int sm_count) {
   const int Q = std::max(out_doubles(kind, n, 8), 16);
   (void)k;
   return (size_t)sm_count * 8 * (size_t)Q;
+}
+
+int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* consts, int nconsts) {
+  if (s.f != 1) return SO_EINVAL;
+  if (pdf != SO_PDF_GAUSS_EXPBKG) return SO_EUNSUPPORTED;
+  if (n != 4 || nconsts < 1 || !consts) return SO_EINVAL;
+  using Op = OpNll<PdfGaussExpBkg>;
+  Op::Args a;
+  a.pre = PdfGaussExpBkg::prepare(p, consts);
+  a.scale[0] = -2.0; a.scale[1] = 0.0; a.scale[2] = 0.0;       // sum - 2.0 * Math.log(pdf)
+  return launch_op_cfg<Op, kThreads, 3, 0, 4>(s, a);
 }
 
 // padded width of the kLine result for the scalar families (so_api reads phi at [0,k) and dphi at [KB, KB+k))

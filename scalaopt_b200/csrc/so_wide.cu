@@ -208,6 +208,7 @@ int launch_wide(Kind kind, const Shard& s, int family, const double* p, const do
       return launch_line(s, fam, P);
     case kNormalEq:
       return launch_gram(s, fam, P);
+    case kNll: break;      // single-input pdfs only (launch_nll)
   }
   return SO_EINVAL;
 }

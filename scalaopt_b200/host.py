@@ -18,10 +18,10 @@ from . import native
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscalaopt_host.so")
 
-LEVENBERG_MARQUARDT, BFGS, CONJUGATE_GRADIENT, NEWTON_CG, STEIHAUG_CG = range(5)
+LEVENBERG_MARQUARDT, BFGS, CONJUGATE_GRADIENT, NEWTON_CG, STEIHAUG_CG, NELDER_MEAD = range(6)
 OK, MAX_ITER, ILLEGAL_ARG, GPU_ERROR, ERROR = range(5)
 
-EXPORTS = ["soh_default_config", "soh_objective_from_callbacks", "soh_objective_gpu", "soh_objective_free",
+EXPORTS = ["soh_default_config", "soh_objective_from_callbacks", "soh_objective_gpu", "soh_objective_gpu_nll", "soh_objective_free",
            "soh_objective_counters", "soh_objective_apply", "soh_objective_gradient", "soh_objective_dirder",
            "soh_objective_dir_hessian", "soh_objective_jacobian_rows", "soh_minimize", "soh_zoom_step_length",
            "soh_qr", "soh_last_error"]
@@ -42,7 +42,9 @@ class Config(C.Structure):
                 ("delta0", C.c_double), ("delta_max", C.c_double), ("eta", C.c_double),
                 ("x_tol", C.c_double), ("g_tol", C.c_double), ("ratio_tol", C.c_double), ("step_bound", C.c_double),
                 ("epsmch", C.c_double), ("max_inner_iter", C.c_int32), ("max_step_length_iter", C.c_int32),
-                ("use_pivoting", C.c_int32)]
+                ("use_pivoting", C.c_int32),
+                ("c_reflection", C.c_double), ("c_expansion", C.c_double), ("c_contraction", C.c_double),
+                ("c_shrink", C.c_double), ("rel_delta", C.c_double), ("abs_delta", C.c_double)]
 
 
 class Result(C.Structure):
@@ -82,6 +84,8 @@ def load():
     L.soh_objective_from_callbacks.restype = vp
     L.soh_objective_gpu.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.soh_objective_gpu.restype = vp
+    L.soh_objective_gpu_nll.argtypes = [vp, vp, C.c_int, C.c_int, _dp, C.c_int]
+    L.soh_objective_gpu_nll.restype = vp
     L.soh_objective_free.argtypes = [vp]
     L.soh_objective_free.restype = None
     L.soh_objective_counters.argtypes = [vp, C.POINTER(Counters)]
@@ -160,6 +164,13 @@ class Objective:
     def gpu(cls, ctx: native.Context, ds: native.Dataset, family: int, n: int):
         """GpuMSEFunction(family, GpuDataSet(ds))"""
         h = load().soh_objective_gpu(ctx._h, ds._h, ds.f, family, n)
+        return cls(h, n, keepalive=(ctx, ds))
+
+    @classmethod
+    def gpu_nll(cls, ctx: native.Context, ds: native.Dataset, pdf: int, n: int, consts):
+        """negLogLikelihood(pdf, GpuDataSet(ds)) _ with finite-difference derivatives"""
+        c = _vec(consts)
+        h = load().soh_objective_gpu_nll(ctx._h, ds._h, pdf, n, _ptr(c), c.size)
         return cls(h, n, keepalive=(ctx, ds))
 
     def _check(self, rc):

@@ -240,4 +240,32 @@ class GpuMSEFunction : public MSEFunction {
   }
 };
 
+// negLogLikelihood(pdf, data) _ as an objective (std-apps/.../stats/package.scala:74-103).  The reference hands this plain
+// closure to an optimizer through `toFunctionWoGradient` (core/.../package.scala:74-77), i.e. as an
+// ObjectiveFunctionFiniteDiffDerivatives: derivatives are forward differences of the (GPU-evaluated) objective.
+class GpuNllFunction : public MSEFunction {
+ public:
+  std::shared_ptr<GpuDataSet> data; int pdf; int n; Vec consts; ConfigPars config;
+  mutable GpuCounters counters;
+  GpuNllFunction(std::shared_ptr<GpuDataSet> d, int pdf_, int n_, Vec consts_) : data(std::move(d)), pdf(pdf_), n(n_), consts(std::move(consts_)) {}
+  double apply(const Vec& x) const override {
+    counters.loss_calls++; counters.k1_passes++;
+    double out = 0.0;
+    const int rc = so_eval_nll(data->ds, pdf, x.data(), n, consts.data(), (int)consts.size(), &out);
+    if (rc != SO_OK) throw GpuError(rc, so_last_error(data->ctx));
+    return out;
+  }
+  Vec gradient(const Vec& x) const override { counters.gradient_calls++; return fd_gradient([this](const Vec& v) { return apply(v); }, x, config.eps); }
+  double dirder(const Vec& x, const Vec& d) const override { counters.dirder_calls++; return (apply(add(x, mul(d, config.eps))) - apply(x)) / config.eps; }
+  Vec dirHessian(const Vec& x, const Vec& d) const override {
+    counters.hessvec_calls++;
+    const Vec gradx = gradient(x);
+    const Vec gradxd = gradient(add(x, mul(d, config.eps)));
+    return div(sub(gradxd, gradx), config.eps);
+  }
+  std::shared_ptr<DataSet<AugmentedRow>> jacobianAndResidualsMatrix(const Vec&) const override {
+    throw IllegalArgumentException("a negative log-likelihood is not an MSEFunction");
+  }
+};
+
 }  // namespace scalaopt

@@ -82,6 +82,7 @@ extern "C" int soh_default_config(int method, soh_config* o) {
   o->delta0 = 1.0; o->delta_max = 1.0e5; o->eta = 0.2;
   o->x_tol = 1.49012e-8; o->g_tol = 0.0; o->ratio_tol = 0.0001; o->step_bound = 100.0; o->epsmch = 2.22044604926e-16;
   o->max_inner_iter = 10; o->max_step_length_iter = 10; o->use_pivoting = 0;
+  o->c_reflection = 2.0; o->c_expansion = 1.0; o->c_contraction = 0.5; o->c_shrink = 0.5; o->rel_delta = 0.05; o->abs_delta = 0.00025;
   if (method == SOH_LEVENBERG_MARQUARDT) { o->tol = 1.49012e-8; o->max_iter = 10; }
   return SOH_OK;
 }
@@ -102,6 +103,16 @@ extern "C" soh_objective* soh_objective_gpu(so_ctx* ctx, so_dataset* ds, int f, 
   auto* g = new GpuMSEFunction(data, family, n);
   auto* o = new soh_objective();
   o->counters = &g->counters; o->n = n; o->has_jacobian = true;
+  o->fn.reset(g);
+  return o;
+}
+
+extern "C" soh_objective* soh_objective_gpu_nll(so_ctx* ctx, so_dataset* ds, int pdf, int n, const double* consts, int nconsts) {
+  if (!ctx || !ds || n < 1 || (nconsts > 0 && !consts)) { g_err = "soh_objective_gpu_nll: bad arguments"; return nullptr; }
+  auto data = std::make_shared<GpuDataSet>(ctx, ds, 1, false);
+  auto* g = new GpuNllFunction(data, pdf, n, Vec(consts, consts + nconsts));
+  auto* o = new soh_objective();
+  o->counters = &g->counters; o->n = n; o->has_jacobian = false;
   o->fn.reset(g);
   return o;
 }
@@ -185,6 +196,12 @@ extern "C" int soh_minimize(int method, soh_objective* f, const double* x0, int 
       case SOH_STEIHAUG_CG: {
         SteihaugCGConfig p; p.tol = c.tol; p.maxIter = c.max_iter; p.eps = c.eps; p.delta0 = c.delta0; p.deltaMax = c.delta_max; p.eta = c.eta;
         sol = SteihaugCG::minimize(*f->fn, start, p, &tr);
+        break;
+      }
+      case SOH_NELDER_MEAD: {
+        NelderMeadConfig p; p.tol = c.tol; p.maxIter = c.max_iter; p.eps = c.eps; p.cReflection = c.c_reflection; p.cExpansion = c.c_expansion;
+        p.cContraction = c.c_contraction; p.cShrink = c.c_shrink; p.relDelta = c.rel_delta; p.absDelta = c.abs_delta;
+        sol = NelderMead::minimize(*f->fn, start, p, &tr);
         break;
       }
       default: throw IllegalArgumentException("unknown method");

@@ -586,6 +586,87 @@ inline Vec minimize(const DifferentiableObjectiveFunction& f, const Vec& x0,
 }
 }  // namespace SteihaugCG
 
+
+// =====================================================================================================
+// NelderMead (derivativefree/NelderMead.scala:40-314): the default method of maxLikelihoodFit
+// (std-apps/.../stats/package.scala:74-87).  Consumes only f(x); every Vertex evaluates f once.
+// =====================================================================================================
+struct NelderMeadConfig : ConfigPars {                          // :307-314
+  double cReflection = 2.0, cExpansion = 1.0, cContraction = 0.5, cShrink = 0.5, relDelta = 0.05, absDelta = 0.00025;
+};
+
+namespace NelderMead {
+struct Vertex { Vec x; double fx; };
+inline Vec minimize(const DifferentiableObjectiveFunction& f, const Vec& x0, const NelderMeadConfig& pars = NelderMeadConfig(),
+                    IterationTrace* trace = nullptr) {
+  const int n = (int)x0.size();
+  auto vertex = [&](Vec x) { Vertex v; v.fx = f.apply(x); v.x = std::move(x); return v; };
+  auto barycenterOf = [&](const std::vector<Vertex>& vs) {      // Simplex.barycenter :286-291
+    Vec r = div(vs.front().x, (double)(n + 1));
+    for (size_t i = 1; i < vs.size(); ++i) r = add(r, div(vs[i].x, n + 1.0));
+    return r;
+  };
+  auto byValue = [](const Vertex& a, const Vertex& b) { return a.fx < b.fx; };
+  // Simplex.apply :272-283
+  std::vector<Vertex> vertices;
+  vertices.push_back(vertex(x0));
+  for (int i = 0; i < n; ++i) {                                 // Vertex.shift :73-84
+    Vec x = x0;
+    x[i] = (x0[i] == 0.0) ? x0[i] + pars.absDelta : x0[i] * pars.relDelta;
+    vertices.push_back(vertex(std::move(x)));
+  }
+  std::stable_sort(vertices.begin(), vertices.end(), byValue);
+  require(vertices.size() > 1, "There must be at least 2 vertices");
+  Vec barycenter = barycenterOf(vertices);
+  int iter = 0;
+  for (;;) {
+    if (trace) trace->iterations = iter;
+    const Vertex& vtxMin = vertices.front();
+    const Vertex vtxMax = vertices.back();
+    // barycenter(vtxMax) - vtxMax.x  :125-131
+    const Vec move = sub(sub(mul(barycenter, 1.0 + 1.0 / n), div(vtxMax.x, (double)n)), vtxMax.x);
+    if (norm(move) / std::sqrt((double)vertices.size()) < pars.tol) return vtxMin.x;      // stoppingRule :54-57
+    if (iter >= pars.maxIter * (int)vertices.size()) throw MaxIterException("Maximum number of iterations reached.");   // :233-236
+    auto update = [&](const Vertex& vtxNew) {                   // :245-259
+      barycenter = add(barycenter, div(sub(vtxNew.x, vtxMax.x), (double)(n + 1)));
+      std::vector<Vertex> init(vertices.begin(), vertices.end() - 1), out;
+      if (vtxNew.fx < vertices.front().fx) { out.push_back(vtxNew); out.insert(out.end(), init.begin(), init.end()); }
+      else if (vtxNew.fx > init.back().fx) { out = init; out.push_back(vtxNew); }
+      else {
+        size_t index = 0;
+        while (index < vertices.size() && !(vertices[index].fx >= vtxNew.fx)) ++index;
+        out.assign(vertices.begin(), vertices.begin() + index);
+        out.push_back(vtxNew);
+        if (index < init.size()) out.insert(out.end(), init.begin() + index, init.end());
+      }
+      vertices = std::move(out);
+    };
+    bool moved = false;
+    {                                                           // reflection :138-150
+      const Vertex vtxNew = vertex(add(vtxMax.x, mul(move, pars.cReflection)));
+      if (vtxNew.fx <= vtxMin.fx) {                             // expansion :160-167
+        const Vertex vtxExp = vertex(add(vtxNew.x, mul(move, pars.cExpansion)));
+        update(vtxExp.fx <= vtxMin.fx ? vtxExp : vtxNew);
+        moved = true;
+      } else if (vtxNew.fx <= vtxMax.fx) { update(vtxNew); moved = true; }
+    }
+    if (!moved) {                                               // contraction :178-185
+      const Vertex vtxNew = vertex(add(vtxMax.x, mul(move, pars.cContraction)));
+      if (vtxNew.fx <= vtxMax.fx) { update(vtxNew); moved = true; }
+    }
+    if (!moved) {                                               // shrinkage :196-212
+      const Vec xmin = vtxMin.x;
+      std::vector<Vertex> shrunk;
+      for (const Vertex& v : vertices) shrunk.push_back(vertex(add(xmin, mul(sub(v.x, xmin), pars.cShrink))));
+      std::stable_sort(shrunk.begin(), shrunk.end(), byValue);
+      vertices = std::move(shrunk);
+      barycenter = barycenterOf(vertices);
+    }
+    ++iter;
+  }
+}
+}  // namespace NelderMead
+
 // =====================================================================================================
 // LevenbergMarquardt (leastsquares/LevenbergMarquardt.scala:107-508): MINPACK lmder/lmpar/qrsolv as the
 // reference restates them, quirks included

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libscalaopt_cuda.so")
 LINEAR, LINEAR_NOINT, LOGISTIC, EXPDECAY, GAUSS, GAUSS_EXPBKG, POLY = range(7)
 FAMILY_NAMES = {LINEAR: "linear", LINEAR_NOINT: "linear_noint", LOGISTIC: "logistic", EXPDECAY: "expdecay",
                 GAUSS: "gauss", GAUSS_EXPBKG: "gauss_expbkg", POLY: "poly"}
+PDF_GAUSS_EXPBKG = 0
 MAX_ALPHAS = 32
 NCCL_UID_BYTES = 128
 
@@ -26,7 +27,7 @@ EXPORTS = [
     "so_host_alloc", "so_host_free",
     "so_dataset_create", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
     "so_dataset_size", "so_dataset_head", "so_dataset_slice", "so_dataset_free",
-    "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_line", "so_eval_hess_vec", "so_stats",
+    "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_line", "so_eval_hess_vec", "so_eval_nll", "so_stats",
 ]
 
 
@@ -92,6 +93,7 @@ def load():
     L.so_eval_normal_eq.argtypes = [vp, i32, _dp, i32, _dp, _dp, _dp]
     L.so_eval_line.argtypes = [vp, i32, _dp, _dp, i32, _dp, i32, _dp, _dp]
     L.so_eval_hess_vec.argtypes = [vp, i32, _dp, _dp, i32, _dp]
+    L.so_eval_nll.argtypes = [vp, i32, _dp, i32, _dp, i32, _dp]
     L.so_stats.argtypes = [vp, C.POINTER(CallStats)]
     _lib = L
     return L
@@ -274,6 +276,13 @@ class Dataset:
         out = np.empty(p.size)
         self.ctx.check(load().so_eval_hess_vec(self._h, family, _ptr(p), _ptr(d), p.size, _ptr(out)))
         return out
+
+    def nll(self, pdf, p, consts):
+        """sum_i -2 log pdf(p, x_i) (negLogLikelihood, stats/package.scala:97-103)"""
+        p, c = _vec(p), _vec(consts)
+        out = C.c_double()
+        self.ctx.check(load().so_eval_nll(self._h, pdf, _ptr(p), p.size, _ptr(c), c.size, C.byref(out)))
+        return out.value
 
     def free(self):
         if self._h:

@@ -164,3 +164,23 @@ def test_newton_cg_and_steihaug_on_linear_least_squares(host, oracle):
     cfg = host.default_config(host.STEIHAUG_CG, tol=0.05)
     x_st, _ = host.minimize(host.STEIHAUG_CG, f, ref + 0.01, cfg)
     assert np.linalg.norm(x_st - ref) <= cfg.tol
+
+
+def test_nelder_mead_spec(host):
+    """NelderMeadSpec.scala:49-62: the quadratic converges to tol, x0 + x1 runs into MaxIterException."""
+    x0 = np.array([0.5, 2.0])
+    f = host.Objective.from_callables(2, lambda x: float((x - x0) @ (x - x0)))
+    xmin, res = host.minimize(host.NELDER_MEAD, f, [1.0, -1.0])
+    assert float((xmin - x0) @ (xmin - x0)) < 1e-5 ** 2 * 10
+    assert f.counters()["loss_calls"] >= res.iterations + 3
+    with pytest.raises(host.MaxIterException):
+        host.minimize(host.NELDER_MEAD, host.Objective.from_callables(2, lambda x: float(x[0] + x[1])), [1.0, -1.0])
+    # a zero coordinate is shifted by absDelta, the others scaled by relDelta (Vertex.shift :96-106)
+    seen = []
+    g = host.Objective.from_callables(2, lambda x: (seen.append(np.array(x)), float(x @ x))[1])
+    cfg = host.default_config(host.NELDER_MEAD, max_iter=1)
+    try:
+        host.minimize(host.NELDER_MEAD, g, [0.0, 4.0], cfg)
+    except host.MaxIterException:
+        pass
+    np.testing.assert_allclose(seen[:3], [[0.0, 4.0], [0.00025, 4.0], [0.0, 0.2]])
