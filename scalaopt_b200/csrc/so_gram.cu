@@ -13,7 +13,7 @@
 //               Z[row0 + l%4][8t + l/4] — so a slab costs T 64-bit loads per lane, straight from global memory.
 //               Measured on this pool's B200: DMMA 37.2 TFLOP/s vs 33.8 for register-resident DFMA
 //               (profiles/r1_fp64_peak.json), and one DMMA replaces 8 DFMA issue slots + their operand traffic.
-//   larger n    shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_big below), n <= 513
+//   larger n    warp-specialised shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_ws below), f <= 512
 #include <algorithm>
 
 #include "so_wide.cuh"
@@ -341,147 +341,285 @@ int dispatch_tri(const Shard& s, const Params& P) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// n + 1 > 48 (up to 514 columns): shared-memory staged DMMA SYRK.
-//   * the upper triangle of 8x8 tiles is cut into 4x4-tile patches (32x32 entries); a warp owns one patch
-//     (16 DMMA accumulators = 64 registers), a 512-thread block owns up to 16 patches ("tile group");
-//   * the grid is (tile groups) x (row workers); tile group is the fastest block index so that the blocks that
-//     stream the same rows run together and share them through L2 (the kernel is FP64-bound by 2-6x: n = 256
-//     needs 66 306 flop per 2 056-byte row);
-//   * rows are staged 16 at a time into shared memory with cp.async (LDGSTS; 8-byte granules, so any f and any
-//     alignment), double buffered, row pitch 8T+4 doubles so that the 4 rows x 8 columns of an MMA fragment hit
-//     distinct banks; the intercept's 1-column and the residual column are appended in shared memory, after
-//     which every fragment is one plain LDS.64;
-//   * per 4-row slab a warp loads 4 + 4 fragments and issues 16 DMMAs (diagonal patches waste 6 of them).
+// n + 1 > 48 (f up to 512 inputs): warp-specialised, shared-memory staged DMMA SYRK (k_gram_ws).
+//   * The DMMA tiles cover the f INPUT columns only (T = ceil(f/8) tile columns).  The upper triangle of tiles is
+//     cut into 4x4-tile patches (32x32 entries); a consumer warp owns one patch (16 DMMA accumulators = 64
+//     registers).  4 producer warps + 12 consumer warps per 512-thread block, one block per SM.
+//   * The intercept's 1-column and the residual column are NOT padded into a further tile column.  The sums
+//     sum x_c and sum x_c res are 4 more DMMAs per slab on the DIAGONAL patches (X^T [1 res 0 ..] into their
+//     unused below-diagonal accumulators), which brings those warps from 10 to 14 DMMAs per slab next to the 16 of
+//     an off-diagonal patch.  n = 257: 560 DMMAs per 4-row slab instead of 666.
+//   * The residuals themselves need the linear predictor, a matrix-vector product that DMMA would do at 1/8
+//     efficiency; the producer warps compute it with DFMAs, ONE CHUNK AHEAD of the consumers.  FP64 instructions
+//     of other warps are starved by a saturated DMMA stream (measured: a lone DFMA waits for the whole DMMA
+//     phase), so that work effectively runs in the gap at the chunk barrier; it is kept short: 8 rows at a time
+//     per warp, f/32 DFMAs per row and lane, a transposing shuffle reduction (9 DADDs for 8 rows).
+//   * Rows are streamed into a 3-stage ring, row pitch 8T+4 doubles so that the 4 rows x 8 columns of an MMA
+//     fragment hit distinct banks.  f even: one TMA bulk copy per row (cp.async.bulk, 8f bytes), issued by a
+//     single producer warp and completed on the stage's mbarrier (complete_tx).  f odd (rows only 8-byte
+//     aligned): 8-byte cp.async by all producer threads, completed on the same mbarrier with
+//     cp.async.mbarrier.arrive.noinc.  One block barrier per chunk releases the stage.
+//   * grid = (tile groups) x (row workers); tile group is the fastest block index so that the blocks streaming
+//     the same rows run together and share them through L2 (the kernel is FP64-bound: n = 257 needs 66 306 flop
+//     per 2 056-byte row).  When all patches fit one group several consumer warps share a patch and split the
+//     slabs of a chunk between them ("reps").
 // ---------------------------------------------------------------------------------------------------
-constexpr int kBigThreads = 512, kBigWarps = 16, kPatch = 4, kBigStages = 3;
+constexpr int kWsConsumers = 12, kWsProducers = 4, kWsThreads = 32 * (kWsConsumers + kWsProducers);
+constexpr int kPatch = 4, kWsStages = 3, kWsMaxRows = 64;
+constexpr int kPatchDoubles = kPatch * kPatch * 64;
+// below-diagonal accumulator slots of a diagonal patch that hold X^T [1 res] of its tile rows 0..3
+__host__ __device__ constexpr int ws_extra_slot(int ti) { return ti == 0 ? 1 * kPatch + 0 : ti == 1 ? 2 * kPatch + 0 : ti == 2 ? 3 * kPatch + 0 : 2 * kPatch + 1; }
 
 __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src, bool valid) {
   const unsigned int sz = valid ? 8u : 0u;      // src-size 0: zero fill
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(dst_smem)), "l"(src), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void bar_block() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-// RPW = rows per warp per chunk (chunk = 16 * RPW rows).  Warp w copies rows w, w+16, ... of a chunk itself and
-// finishes their residual / intercept columns itself, so the only block barrier per chunk is the one that
-// publishes the finished stage; with 3 stages that same barrier also protects the stage being refilled.
-template <int FAM, int RPW>
-__global__ void __launch_bounds__(kBigThreads, 1)
-k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
-           int PT, int npatches, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+struct WsPlan { int T, PT, npatches, groups, reps, workers, krows, QE; size_t smem; };
+
+template <int FAM>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+          const __grid_constant__ WsPlan L, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int kRows = kBigWarps * RPW;
+  __shared__ double s_sc[kWsProducers][2];
+  __shared__ __align__(8) uint64_t s_full[kWsStages];
   const int f = P.f, icpt = P.icpt, n = P.n;
-  const int W = 8 * kPatch * PT;                       // padded width: whole patches, zero beyond f + icpt + 1
-  const int PW = W + 4;                                // row pitch in doubles (4 rows x 8 cols of a fragment: distinct banks)
-  double* ps = sm;                                     // [W] parameters in Z-column order (0 beyond f)
-  double* stage0 = sm + W;                             // kBigStages stages of kRows x PW
+  const bool bulk = (f & 1) == 0;                        // rows 16-byte aligned: TMA bulk copies
+  const int T = L.T, PT = L.PT, npatches = L.npatches, reps = L.reps, krows = L.krows;
+  const int W = 8 * T, PW = W + 4;                       // row pitch in doubles
+  double* ps = sm;                                       // [W] parameters of the input columns (0 beyond f)
+  double* res_s = sm + W;                                // [2][kWsMaxRows] residuals of the chunk consumed / the next one
+  double* stage0 = res_s + 2 * kWsMaxRows;               // kWsStages stages of krows x PW
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rsel = lane & 3, csel = lane >> 2;
-  const int col_one = icpt ? f : -1, col_res = f + icpt;
+  const int worker = blockIdx.y, nworkers = gridDim.y, group = blockIdx.x;
   if (FAM == kLogistic) exp_table_init();
-  for (int c = tid; c < W; c += kBigThreads) ps[c] = (c < f) ? P.p[icpt + c] : 0.0;
-  for (int i = tid; i < kBigStages * kRows * PW; i += kBigThreads) stage0[i] = 0.0;     // padding columns stay zero
+  for (int c = tid; c < W; c += kWsThreads) ps[c] = (c < f) ? P.p[icpt + c] : 0.0;
+  for (int i = tid; i < kWsStages * krows * PW; i += kWsThreads) stage0[i] = 0.0;     // padding columns stay zero
+  if (tid == 0) {
+    for (int st = 0; st < kWsStages; ++st) mbar_init(&s_full[st], bulk ? 1 : kWsProducers * 32);
+    mbar_fence_init();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zeros above are ordered before the bulk copies
   __syncthreads();
-  const double p0 = icpt ? P.p[0] : 0.0;
+  const int64_t nchunks = (rows + krows - 1) / krows;
+  double* tile_partials = partials;
+  double* extra_partials = partials + (size_t)nworkers * reps * npatches * kPatchDoubles;
 
-  // this warp's patch: the patch-th (pa <= pb) pair in row-major order over PT x PT
-  const int patch = blockIdx.x * kBigWarps + warp;
-  int pa = 0, pb = 0;
-  const bool active = patch < npatches;
-  if (active) { int rem = patch; while (rem >= PT - pa) { rem -= PT - pa; ++pa; } pb = pa + rem; }
-  const int offa = 8 * kPatch * pa + csel, offb = 8 * kPatch * pb + csel;
-
-  double acc[kPatch][kPatch][2];
+  if (warp < kWsProducers) {
+    // ------------------------------------------------------------------ producers
+    const int pw = warp;
+    const double p0 = icpt ? P.p[0] : 0.0;
+    const int rw = (krows + kWsProducers - 1) / kWsProducers;      // rows of a chunk per producer warp
+    auto load_stage = [&](int64_t chunk, int stage) {
+      if (chunk >= nchunks) return;
+      double* st = stage0 + (size_t)stage * krows * PW;
+      const int64_t row0 = chunk * krows;
+      const int nvalid = (int)min((int64_t)krows, rows - row0);
+      if (bulk) {
+        if (pw != 0) return;
+        if (lane == 0) mbar_arrive_expect_tx(&s_full[stage], (uint32_t)nvalid * (uint32_t)f * 8u);
+        __syncwarp();
+        for (int r = lane; r < nvalid; r += 32) bulk_g2s(st + r * PW, X + (row0 + r) * (int64_t)f, (uint32_t)f * 8u, &s_full[stage]);
+        for (int r = nvalid; r < krows; ++r)                 // ragged last chunk: rows past the end read as zero
+          for (int c = lane; c < f; c += 32) st[r * PW + c] = 0.0;
+      } else {
+        for (int r = pw; r < krows; r += kWsProducers) {
+          const bool valid = r < nvalid;
+          const double* src = X + (valid ? row0 + r : 0) * (int64_t)f + lane;
+          double* dst = st + r * PW + lane;
+          for (int c0 = 0; c0 < f; c0 += 128) {
 #pragma unroll
-  for (int i = 0; i < kPatch; ++i)
-#pragma unroll
-    for (int j = 0; j < kPatch; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-
-  const int64_t nchunks = (rows + kRows - 1) / kRows;
-  auto load_stage = [&](int64_t chunk, int stage) {      // this warp's rows of the chunk; always commits a group
-    if (chunk < nchunks) {
-      double* st = stage0 + (size_t)stage * kRows * PW;
-#pragma unroll
-      for (int k = 0; k < RPW; ++k) {
-        const int r = warp + k * kBigWarps;
-        const int64_t row = chunk * kRows + r;
-        const bool valid = row < rows;
-        const double* src = X + (valid ? row : 0) * (int64_t)f;
-        for (int c = lane; c < f; c += 32) cp_async8(st + r * PW + c, src + c, valid);
+            for (int u = 0; u < 4; ++u)
+              if (c0 + 32 * u + lane < f) cp_async8(dst + c0 + 32 * u, src + c0 + 32 * u, valid);
+          }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&s_full[stage])) : "memory");
       }
-    }
-    cp_async_commit();
-  };
-
-  int64_t chunk = blockIdx.y;
-  load_stage(chunk, 0);
-  load_stage(chunk + gridDim.y, 1);
-  int it = 0;
-  for (; chunk < nchunks; chunk += gridDim.y, ++it) {
-    const int stage = it % kBigStages;
-    cp_async_wait<1>();                                  // this warp's copies of `chunk` have landed
-    __syncwarp();
-    double* st = stage0 + (size_t)stage * kRows * PW;
+    };
+    double sr = 0.0, rr = 0.0;                               // this lane's rows (lane % 4 == 0 only)
+    // residuals of this warp's rows of `chunk` (in stage `it % kWsStages`) -> res_s[it & 1]
+    auto residuals = [&](int64_t chunk, int it) {
+      if (chunk >= nchunks) return;
+      const double* st = stage0 + (size_t)(it % kWsStages) * krows * PW;
+      double* rs = res_s + (it & 1) * kWsMaxRows;
+      const int64_t row0 = chunk * krows;
+      const int rlo = pw * rw, rhi = min(krows, rlo + rw);
+      const int mine = lane >> 2;                            // after the reduction lane holds row rb + mine
+      double yv[2];                                          // rw <= 16: at most two batches of 8 rows
 #pragma unroll
-    for (int k = 0; k < RPW; ++k) {                      // residual and intercept columns of this warp's rows
-      const int r = warp + k * kBigWarps;
-      const int64_t row = chunk * kRows + r;
-      const bool valid = row < rows;
-      double dot = 0.0;
-      for (int c = lane; c < f; c += 32) dot = fma(ps[c], st[r * PW + c], dot);
-      dot = warp_sum(dot);
-      if (lane == 0) {
+      for (int b = 0; b < 2; ++b) {
+        const int r = rlo + 8 * b + mine;
+        yv[b] = (r < rhi && row0 + r < rows) ? ld_stream(y + row0 + r) : 0.0;
+      }
+      mbar_wait(&s_full[it % kWsStages], (uint32_t)(it / kWsStages) & 1u);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int rb = rlo + 8 * b;
+        if (rb >= rhi) break;
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.0;
+        for (int c = lane; c < f; c += 32) {
+          const double pc = ps[c];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (rb + i < rhi) v[i] = fma(pc, st[(rb + i) * PW + c], v[i]);
+        }
+        // transposing reduction: 8 rows x 32 lanes -> lane holds the full sum of row rb + lane/4
+        const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0;
+        double w4[4], w2[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
+          w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double send = h3 ? w4[i] : w4[i + 2], keep = h3 ? w4[i + 2] : w4[i];
+          w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        double dot;
+        {
+          const double send = h2 ? w2[0] : w2[1], keep = h2 ? w2[1] : w2[0];
+          dot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        const int r = rb + mine;
         const double z = dot + p0;
-        const double yv = valid ? ld_stream(y + row) : 0.0;
         double res;
         if (FAM == kLinear) {
-          res = yv - z;
+          res = yv[b] - z;
         } else {
           const double e = so_exp(-fabs(z));
           const double inv = 1.0 / (1.0 + e);
-          res = ((z >= 0.0) ? inv : e * inv) - yv;
+          res = ((z >= 0.0) ? inv : e * inv) - yv[b];
         }
-        if (col_one >= 0) st[r * PW + col_one] = valid ? 1.0 : 0.0;
-        st[r * PW + col_res] = valid ? res : 0.0;
+        if (r >= rhi || row0 + r >= rows) res = 0.0;
+        if ((lane & 3) == 0 && r < rhi) { rs[r] = res; sr += res; rr = fma(res, res, rr); }
+      }
+    };
+
+    int64_t chunk = worker;
+    load_stage(chunk, 0);
+    load_stage(chunk + nworkers, 1);
+    residuals(chunk, 0);
+    bar_block();                                             // the residuals of the first chunk are visible
+    for (int it = 0; chunk < nchunks; chunk += nworkers, ++it) {
+      load_stage(chunk + 2 * (int64_t)nworkers, (it + 2) % kWsStages);   // the stage released by the last barrier
+      residuals(chunk + nworkers, it + 1);                   // one chunk ahead of the consumers
+      bar_block();                                           // everyone is done with this chunk
+    }
+    if (!bulk) asm volatile("cp.async.wait_all;" ::: "memory");
+    if (group == 0) {
+      sr = warp_sum(sr); rr = warp_sum(rr);
+      if (lane == 0) { s_sc[pw][0] = sr; s_sc[pw][1] = rr; }
+      asm volatile("bar.sync 1, %0;" :: "n"(kWsProducers * 32) : "memory");
+      if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kWsProducers; ++w) { a += s_sc[w][0]; b += s_sc[w][1]; }
+        int64_t cnt = 0;                                     // rows this worker streamed
+        for (int64_t c = worker; c < nchunks; c += nworkers) cnt += min((int64_t)krows, rows - c * krows);
+        double* ex = extra_partials + (size_t)worker * L.QE;
+        ex[0] = (double)cnt; ex[1] = a; ex[2] = b;
       }
     }
-    __syncthreads();     // stage complete for everyone; everyone has also finished computing on the previous chunk
-    load_stage(chunk + 2 * (int64_t)gridDim.y, (it + 2) % kBigStages);
-    if (active) {
-#pragma unroll 2
-      for (int slab = 0; slab < kRows / 4; ++slab) {
-        const double* base = st + (slab * 4 + rsel) * PW;
-        double fa[kPatch], fb[kPatch];
+  } else {
+    // ------------------------------------------------------------------ consumers
+    const int rsel = lane & 3, csel = lane >> 2;
+    const int cw = warp - kWsProducers;
+    int patch, rep = 0;
+    bool active;
+    if (L.groups == 1) { patch = cw % npatches; rep = cw / npatches; active = rep < reps; }
+    else { patch = group * kWsConsumers + cw; active = patch < npatches; }
+    int pa = 0, pb = 0;
+    if (active) { int rem = patch; while (rem >= PT - pa) { rem -= PT - pa; ++pa; } pb = pa + rem; }
+    const int na = min(kPatch, T - kPatch * pa), nb = min(kPatch, T - kPatch * pb);   // real tiles of the patch
+    const int offa = 8 * kPatch * pa + csel, offb = 8 * kPatch * pb + csel;
+    const int mode = !active ? 0 : (pa == pb ? (na == kPatch ? 1 : 3) : ((na == kPatch && nb == kPatch) ? 2 : 3));
+
+    double acc[kPatch][kPatch][2];
 #pragma unroll
-        for (int i = 0; i < kPatch; ++i) { fa[i] = base[offa + 8 * i]; fb[i] = base[offb + 8 * i]; }
-        if (pa != pb) {
+    for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+      for (int j = 0; j < kPatch; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    const int nslabs = krows >> 2;
+    int64_t chunk = worker;
+    bar_block();
+    for (int it = 0; chunk < nchunks; chunk += nworkers, ++it) {
+      const double* st = stage0 + (size_t)(it % kWsStages) * krows * PW + rsel * PW;
+      const double* rs = res_s + (it & 1) * kWsMaxRows + rsel;
+      mbar_wait(&s_full[it % kWsStages], (uint32_t)(it / kWsStages) & 1u);
+      if (mode == 2) {                                     // full off-diagonal patch: 8 fragments, 16 DMMAs per slab
+#pragma unroll 2
+        for (int slab = rep; slab < nslabs; slab += reps) {
+          const double* base = st + slab * 4 * PW;
+          double fa[kPatch], fb[kPatch];
+#pragma unroll
+          for (int i = 0; i < kPatch; ++i) { fa[i] = base[offa + 8 * i]; fb[i] = base[offb + 8 * i]; }
 #pragma unroll
           for (int i = 0; i < kPatch; ++i)
 #pragma unroll
             for (int j = 0; j < kPatch; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-        } else {            // diagonal patch: only tiles on or above the diagonal are ever read back
+        }
+      } else if (mode == 1) {                              // full diagonal patch: 4 fragments, 10 + 4 DMMAs per slab
+#pragma unroll 2
+        for (int slab = rep; slab < nslabs; slab += reps) {
+          const double* base = st + slab * 4 * PW;
+          double fa[kPatch];
+#pragma unroll
+          for (int i = 0; i < kPatch; ++i) fa[i] = base[offa + 8 * i];
+          const double bx = (csel == 0) ? 1.0 : (csel == 1 ? rs[slab * 4] : 0.0);     // [1 res 0 0 0 0 0 0]
 #pragma unroll
           for (int i = 0; i < kPatch; ++i)
 #pragma unroll
-            for (int j = i; j < kPatch; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            for (int j = i; j < kPatch; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fa[j]);
+#pragma unroll
+          for (int i = 0; i < kPatch; ++i) {
+            constexpr int kSlot[4] = {ws_extra_slot(0), ws_extra_slot(1), ws_extra_slot(2), ws_extra_slot(3)};
+            dmma(acc[kSlot[i] / kPatch][kSlot[i] % kPatch][0], acc[kSlot[i] / kPatch][kSlot[i] % kPatch][1], fa[i], bx);
+          }
+        }
+      } else if (mode == 3) {                              // ragged patch at the right / bottom edge
+        for (int slab = rep; slab < nslabs; slab += reps) {
+          const double* base = st + slab * 4 * PW;
+          double fa[kPatch], fb[kPatch];
+#pragma unroll
+          for (int i = 0; i < kPatch; ++i) {
+            fa[i] = (i < na) ? base[offa + 8 * i] : 0.0;
+            fb[i] = (i < nb) ? base[offb + 8 * i] : 0.0;
+          }
+#pragma unroll
+          for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+            for (int j = 0; j < kPatch; ++j)
+              if (i < na && j < nb && (pa != pb || j >= i)) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+          if (pa == pb) {
+            const double bx = (csel == 0) ? 1.0 : (csel == 1 ? rs[slab * 4] : 0.0);
+#pragma unroll
+            for (int i = 0; i < kPatch; ++i) {
+              constexpr int kSlot[4] = {ws_extra_slot(0), ws_extra_slot(1), ws_extra_slot(2), ws_extra_slot(3)};
+              if (i < na) dmma(acc[kSlot[i] / kPatch][kSlot[i] % kPatch][0], acc[kSlot[i] / kPatch][kSlot[i] % kPatch][1], fa[i], bx);
+            }
+          }
         }
       }
+      bar_block();
     }
-  }
-  cp_async_wait<0>();
-
-  // per-(row worker, patch) partials, lane-major tiles: [worker][patch][i][j][lane*2 + reg]
-  constexpr int kPatchDoubles = kPatch * kPatch * 64;
-  if (active) {
-    double* dst = partials + ((size_t)blockIdx.y * npatches + patch) * kPatchDoubles;
+    // per-(row worker, rep, patch) partials, lane-major tiles: [worker*reps + rep][patch][i][j][lane*2 + reg]
+    if (active) {
+      double* dst = tile_partials + (((size_t)worker * reps + rep) * npatches + patch) * kPatchDoubles;
 #pragma unroll
-    for (int i = 0; i < kPatch; ++i)
+      for (int i = 0; i < kPatch; ++i)
 #pragma unroll
-      for (int j = 0; j < kPatch; ++j) {
-        dst[(i * kPatch + j) * 64 + lane * 2] = acc[i][j][0];
-        dst[(i * kPatch + j) * 64 + lane * 2 + 1] = acc[i][j][1];
-      }
+        for (int j = 0; j < kPatch; ++j) {
+          dst[(i * kPatch + j) * 64 + lane * 2] = acc[i][j][0];
+          dst[(i * kPatch + j) * 64 + lane * 2 + 1] = acc[i][j][1];
+        }
+    }
   }
   __threadfence();
   __syncthreads();
@@ -491,8 +629,11 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t r
   __syncthreads();
   if (s_last) {
     __threadfence();
+    // emit the API layout: packed upper triangle over parameters (a <= b), then Jtr, then rtr.
+    constexpr int ONE = -1, RES = -2;
     const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
-    for (int q = tid; q < Qo; q += kBigThreads) {
+    const int nsets = nworkers * reps;
+    for (int q = tid; q < Qo; q += kWsThreads) {
       int ca, cb;
       double sgn = 1.0;
       if (q < Tn) {
@@ -501,86 +642,96 @@ k_gram_big(const double* __restrict__ X, const double* __restrict__ y, int64_t r
         while (a > 0 && a * n - a * (a - 1) / 2 > q) --a;
         while ((a + 1) * n - (a + 1) * a / 2 <= q) ++a;
         const int b = a + (q - (a * n - a * (a - 1) / 2));
-        ca = icpt ? (a == 0 ? f : a - 1) : a;
-        cb = icpt ? (b == 0 ? f : b - 1) : b;
+        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
+        cb = icpt ? (b == 0 ? ONE : b - 1) : b;
       } else if (q < Tn + n) {
         const int a = q - Tn;
-        ca = icpt ? (a == 0 ? f : a - 1) : a;
-        cb = col_res;
-        if (FAM == kLinear) sgn = -1.0;
+        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
+        cb = RES;
+        if (FAM == kLinear) sgn = -1.0;                    // J r = -x~ rho for least squares
       } else {
-        ca = col_res; cb = col_res;
+        ca = RES; cb = RES;
       }
-      if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }   // tile row <= tile col (hence patch row <= patch col)
-      const int qa = ca / (8 * kPatch), qb = cb / (8 * kPatch);
-      const int pidx = qa * PT - qa * (qa - 1) / 2 + (qb - qa);
-      const int ti = (ca >> 3) - qa * kPatch, tj = (cb >> 3) - qb * kPatch, i = ca & 7, j = cb & 7;
-      const size_t off = (size_t)pidx * kPatchDoubles + (ti * kPatch + tj) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
       double s2 = 0.0;
-      for (unsigned w = 0; w < gridDim.y; ++w) s2 += __ldcg(&partials[(size_t)w * npatches * kPatchDoubles + off]);
+      if (ca < 0 && cb < 0) {                              // row count, sum res, sum res^2: the producers' scalars
+        const int off = (ca == ONE && cb == ONE) ? 0 : ((ca == RES && cb == RES) ? 2 : 1);
+        for (int w = 0; w < nworkers; ++w) s2 += __ldcg(&extra_partials[(size_t)w * L.QE + off]);
+      } else {
+        size_t off;
+        if (ca >= 0 && cb >= 0) {
+          if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }   // tile row <= tile col
+          const int qa = ca / (8 * kPatch), qb = cb / (8 * kPatch);
+          const int pidx = qa * PT - qa * (qa - 1) / 2 + (qb - qa);
+          const int ti = (ca >> 3) - qa * kPatch, tj = (cb >> 3) - qb * kPatch, i = ca & 7, j = cb & 7;
+          off = (size_t)pidx * kPatchDoubles + (ti * kPatch + tj) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
+        } else {                                           // sum x_c (j = 0) or sum x_c res (j = 1): the diagonal patch of c
+          const int c = ca >= 0 ? ca : cb, j = (ca == ONE || cb == ONE) ? 0 : 1;
+          const int qa = c / (8 * kPatch), pidx = qa * PT - qa * (qa - 1) / 2;
+          const int ti = (c >> 3) - qa * kPatch, i = c & 7;
+          off = (size_t)pidx * kPatchDoubles + ws_extra_slot(ti) * 64 + (i * 4) * 2 + j;
+        }
+        for (int w = 0; w < nsets; ++w) s2 += __ldcg(&tile_partials[(size_t)w * npatches * kPatchDoubles + off]);
+      }
       out[q] = s2 * sgn;
     }
     if (tid == 0) *ticket = 0u;
   }
 }
 
-struct BigPlan { int PT, npatches, groups, workers, rpw; size_t smem; };
-inline BigPlan big_plan(int n, int sm_count) {
-  BigPlan b;
-  const int T = (n + 1 + 7) / 8;
-  b.PT = (T + kPatch - 1) / kPatch;
+inline WsPlan ws_plan(int f, int sm_count) {
+  WsPlan b;
+  b.T = (f + 7) / 8;
+  b.PT = (b.T + kPatch - 1) / kPatch;
   b.npatches = b.PT * (b.PT + 1) / 2;
-  b.groups = (b.npatches + kBigWarps - 1) / kBigWarps;
+  b.groups = (b.npatches + kWsConsumers - 1) / kWsConsumers;
+  b.reps = b.groups == 1 ? std::max(1, kWsConsumers / b.npatches) : 1;
   b.workers = std::max(1, sm_count / b.groups);
-  const size_t W = (size_t)8 * kPatch * b.PT;
-  auto bytes = [&](int rpw) { return sizeof(double) * (W + (size_t)kBigStages * kBigWarps * rpw * (W + 4)); };
-  b.rpw = (bytes(2) <= 229000) ? 2 : 1;   // 227 KB per block minus ~3 KB of static shared memory
-  b.smem = bytes(b.rpw);
+  const size_t W = (size_t)8 * b.T, PW = W + 4;
+  const size_t fixed = sizeof(double) * (W + 2 * kWsMaxRows), budget = 227 * 1024 - 4096;   // static shared: exp table, flags
+  int krows = (int)((budget - fixed) / (sizeof(double) * kWsStages * PW));
+  krows = std::min(kWsMaxRows, krows) & ~3;
+  b.krows = krows;
+  b.QE = 4;
+  b.smem = fixed + sizeof(double) * kWsStages * (size_t)std::max(krows, 0) * PW;
   return b;
 }
 
-template <int FAM, int RPW>
-int launch_big_rpw(const Shard& s, const Params& P, const BigPlan& b) {
-  auto kern = k_gram_big<FAM, RPW>;
+template <int FAM>
+int launch_ws(const Shard& s, const Params& P) {
+  if (P.f > SO_MAX_FEATURES) return SO_EUNSUPPORTED;
+  WsPlan b = ws_plan(P.f, s.sm_count);
+  if (b.krows < 4) return SO_EUNSUPPORTED;
+  auto kern = k_gram_ws<FAM>;
   static bool attr[64] = {false};
   int dev = 0; cudaGetDevice(&dev); dev &= 63;
   if (!attr[dev]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 229000) != cudaSuccess) return SO_ECUDA;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096) != cudaSuccess) return SO_ECUDA;
     attr[dev] = true;
   }
-  constexpr int kRows = kBigWarps * RPW;
-  const int64_t nchunks = (s.rows + kRows - 1) / kRows;
-  const int workers = (int)std::min<int64_t>(b.workers, std::max<int64_t>(1, nchunks));
-  const size_t need = (size_t)workers * b.npatches * kPatch * kPatch * 64;
+  const int64_t nchunks = (s.rows + b.krows - 1) / b.krows;
+  b.workers = (int)std::min<int64_t>(b.workers, std::max<int64_t>(1, nchunks));
+  const size_t need = (size_t)b.workers * b.reps * b.npatches * kPatchDoubles + (size_t)b.workers * b.QE;
   const int Qo = P.n * (P.n + 1) / 2 + P.n + 1;
   if (need > s.partials_doubles || (size_t)Qo > s.out_doubles) return SO_ENOMEM;
-  dim3 grid(b.groups, workers);
-  kern<<<grid, kBigThreads, b.smem, s.stream>>>(s.X, s.y, s.rows, P, b.PT, b.npatches, s.partials, s.out, s.ticket);
+  dim3 grid(b.groups, b.workers);
+  kern<<<grid, kWsThreads, b.smem, s.stream>>>(s.X, s.y, s.rows, P, b, s.partials, s.out, s.ticket);
   return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
-}
-
-template <int FAM>
-int launch_big(const Shard& s, const Params& P) {
-  const BigPlan b = big_plan(P.n, s.sm_count);
-  if (b.smem > 229000) return SO_EUNSUPPORTED;
-  return b.rpw == 2 ? launch_big_rpw<FAM, 2>(s, P, b) : launch_big_rpw<FAM, 1>(s, P, b);
 }
 
 }  // namespace
 
 size_t gram_partials_needed(int n, int f, int sm_count) {
-  (void)f;
   if (n <= 8) return (size_t)sm_count * 8 * (size_t)(n * (n + 1) / 2 + n + 1);
   const int T = (n + 1 + 7) / 8;
   if (n + 1 <= 48) return (size_t)sm_count * 4 * ((size_t)(T * (T + 1) / 2) * 64 + 16 * T + 4);
-  const BigPlan b = big_plan(n, sm_count);
-  return (size_t)b.workers * b.npatches * kPatch * kPatch * 64;
+  const WsPlan b = ws_plan(f, sm_count);
+  return (size_t)b.workers * b.reps * b.npatches * kPatchDoubles + (size_t)b.workers * b.QE;
 }
 
 int launch_gram(const Shard& s, int fam, const Params& P) {
   if (P.n <= 8) return fam == kLinear ? dispatch_small<kLinear>(s, P) : dispatch_small<kLogistic>(s, P);
   if (P.n + 1 <= 48) return fam == kLinear ? dispatch_tri<kLinear>(s, P) : dispatch_tri<kLogistic>(s, P);
-  return fam == kLinear ? launch_big<kLinear>(s, P) : launch_big<kLogistic>(s, P);
+  return fam == kLinear ? launch_ws<kLinear>(s, P) : launch_ws<kLogistic>(s, P);
 }
 
 }  // namespace wide

@@ -54,9 +54,11 @@ def test_loss_gradient_line_hessvec_match_oracle(native, oracle, gpu_ctx, name, 
 GRAM_CASES = [("LINEAR", 1), ("LINEAR", 3), ("LINEAR", 7), ("LINEAR_NOINT", 8), ("LINEAR", 8), ("LINEAR", 10),
               ("LINEAR", 31), ("LINEAR", 32), ("LINEAR_NOINT", 33), ("LINEAR_NOINT", 47), ("LINEAR", 46),
               ("LOGISTIC", 2), ("LOGISTIC", 7), ("LOGISTIC", 32),
-              # n + 1 > 48: shared-memory staged DMMA SYRK
+              # n + 1 > 48: warp-specialised shared-memory staged DMMA SYRK
               ("LINEAR_NOINT", 48), ("LINEAR_NOINT", 64), ("LINEAR", 127), ("LINEAR_NOINT", 128), ("LINEAR", 256),
-              ("LINEAR_NOINT", 256), ("LOGISTIC", 64), ("LINEAR_NOINT", 511), ("LINEAR", 512)]
+              ("LINEAR_NOINT", 256), ("LOGISTIC", 64), ("LINEAR_NOINT", 511), ("LINEAR", 512),
+              # ragged edge patches (T % 4 != 0), odd f (8-byte copies), one patch shared by several warps
+              ("LINEAR", 100), ("LOGISTIC", 255), ("LINEAR_NOINT", 72), ("LINEAR", 50), ("LOGISTIC", 47)]
 
 
 @pytest.mark.parametrize("name,f", GRAM_CASES)
