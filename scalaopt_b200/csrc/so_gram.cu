@@ -15,6 +15,7 @@
 //               (profiles/r1_fp64_peak.json), and one DMMA replaces 8 DFMA issue slots + their operand traffic.
 //   larger n    warp-specialised shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_ws below), f <= 512
 #include <algorithm>
+#include <cstdlib>
 
 #include "so_wide.cuh"
 
@@ -350,10 +351,11 @@ int dispatch_tri(const Shard& s, const Params& P) {
 //     unused below-diagonal accumulators), which brings those warps from 10 to 14 DMMAs per slab next to the 16 of
 //     an off-diagonal patch.  n = 257: 560 DMMAs per 4-row slab instead of 666.
 //   * The residuals themselves need the linear predictor, a matrix-vector product that DMMA would do at 1/8
-//     efficiency; the producer warps compute it with DFMAs, ONE CHUNK AHEAD of the consumers.  FP64 instructions
-//     of other warps are starved by a saturated DMMA stream (measured: a lone DFMA waits for the whole DMMA
-//     phase), so that work effectively runs in the gap at the chunk barrier; it is kept short: 8 rows at a time
-//     per warp, f/32 DFMAs per row and lane, a transposing shuffle reduction (9 DADDs for 8 rows).
+//     efficiency, so it is DFMA work.  A DFMA of another warp does not get through a saturated DMMA stream
+//     (measured: a producer warp's DFMA waited for the whole DMMA phase of its block, 1 300 cycles per
+//     instruction), so it cannot be hidden behind the DMMAs; instead all 16 warps compute the residuals of the
+//     NEXT chunk together as a short phase before the chunk barrier (warp w takes rows w, w+16, ...; a
+//     transposing shuffle reduction), and chunks are made as long as shared memory allows (2-slot ring).
 //   * Rows are streamed into a 3-stage ring, row pitch 8T+4 doubles so that the 4 rows x 8 columns of an MMA
 //     fragment hit distinct banks.  f even: one TMA bulk copy per row (cp.async.bulk, 8f bytes), issued by a
 //     single producer warp and completed on the stage's mbarrier (complete_tx).  f odd (rows only 8-byte
@@ -365,7 +367,7 @@ int dispatch_tri(const Shard& s, const Params& P) {
 //     slabs of a chunk between them ("reps").
 // ---------------------------------------------------------------------------------------------------
 constexpr int kWsConsumers = 12, kWsProducers = 4, kWsThreads = 32 * (kWsConsumers + kWsProducers);
-constexpr int kPatch = 4, kWsStages = 3, kWsMaxRows = 64;
+constexpr int kPatch = 4, kWsMaxStages = 3, kWsMaxRows = 128;
 constexpr int kPatchDoubles = kPatch * kPatch * 64;
 // below-diagonal accumulator slots of a diagonal patch that hold X^T [1 res] of its tile rows 0..3
 __host__ __device__ constexpr int ws_extra_slot(int ti) { return ti == 0 ? 1 * kPatch + 0 : ti == 1 ? 2 * kPatch + 0 : ti == 2 ? 3 * kPatch + 0 : 2 * kPatch + 1; }
@@ -376,29 +378,30 @@ __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src, bool 
 }
 __device__ __forceinline__ void bar_block() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-struct WsPlan { int T, PT, npatches, groups, reps, workers, krows, QE; size_t smem; };
+struct WsPlan { int T, PT, npatches, groups, reps, workers, krows, stages, QE; size_t smem; };
 
 template <int FAM>
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
           const __grid_constant__ WsPlan L, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   extern __shared__ __align__(16) double sm[];
-  __shared__ double s_sc[kWsProducers][2];
-  __shared__ __align__(8) uint64_t s_full[kWsStages];
+  __shared__ double s_sc[kWsThreads / 32][2];
+  __shared__ __align__(8) uint64_t s_full[kWsMaxStages];
   const int f = P.f, icpt = P.icpt, n = P.n;
   const bool bulk = (f & 1) == 0;                        // rows 16-byte aligned: TMA bulk copies
-  const int T = L.T, PT = L.PT, npatches = L.npatches, reps = L.reps, krows = L.krows;
+  const int T = L.T, PT = L.PT, npatches = L.npatches, reps = L.reps, krows = L.krows, stages = L.stages;
   const int W = 8 * T, PW = W + 4;                       // row pitch in doubles
   double* ps = sm;                                       // [W] parameters of the input columns (0 beyond f)
   double* res_s = sm + W;                                // [2][kWsMaxRows] residuals of the chunk consumed / the next one
-  double* stage0 = res_s + 2 * kWsMaxRows;               // kWsStages stages of krows x PW
+  double* y_s = res_s + 2 * kWsMaxRows;                  // [kWsMaxStages][kWsMaxRows] y of the chunks in the ring
+  double* stage0 = y_s + kWsMaxStages * kWsMaxRows;      // L.stages ring slots of krows x PW
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int worker = blockIdx.y, nworkers = gridDim.y, group = blockIdx.x;
   if (FAM == kLogistic) exp_table_init();
   for (int c = tid; c < W; c += kWsThreads) ps[c] = (c < f) ? P.p[icpt + c] : 0.0;
-  for (int i = tid; i < kWsStages * krows * PW; i += kWsThreads) stage0[i] = 0.0;     // padding columns stay zero
+  for (int i = tid; i < stages * krows * PW; i += kWsThreads) stage0[i] = 0.0;     // padding columns stay zero
   if (tid == 0) {
-    for (int st = 0; st < kWsStages; ++st) mbar_init(&s_full[st], bulk ? 1 : kWsProducers * 32);
+    for (int st = 0; st < stages; ++st) mbar_init(&s_full[st], (bulk ? 1 : kWsProducers * 32) + 1);   // + warp 1: y
     mbar_fence_init();
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zeros above are ordered before the bulk copies
@@ -407,152 +410,159 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
   double* tile_partials = partials;
   double* extra_partials = partials + (size_t)nworkers * reps * npatches * kPatchDoubles;
 
-  if (warp < kWsProducers) {
-    // ------------------------------------------------------------------ producers
-    const int pw = warp;
-    const double p0 = icpt ? P.p[0] : 0.0;
-    const int rw = (krows + kWsProducers - 1) / kWsProducers;      // rows of a chunk per producer warp
-    auto load_stage = [&](int64_t chunk, int stage) {
-      if (chunk >= nchunks) return;
-      double* st = stage0 + (size_t)stage * krows * PW;
-      const int64_t row0 = chunk * krows;
-      const int nvalid = (int)min((int64_t)krows, rows - row0);
-      if (bulk) {
-        if (pw != 0) return;
-        if (lane == 0) mbar_arrive_expect_tx(&s_full[stage], (uint32_t)nvalid * (uint32_t)f * 8u);
-        __syncwarp();
-        for (int r = lane; r < nvalid; r += 32) bulk_g2s(st + r * PW, X + (row0 + r) * (int64_t)f, (uint32_t)f * 8u, &s_full[stage]);
-        for (int r = nvalid; r < krows; ++r)                 // ragged last chunk: rows past the end read as zero
-          for (int c = lane; c < f; c += 32) st[r * PW + c] = 0.0;
-      } else {
-        for (int r = pw; r < krows; r += kWsProducers) {
-          const bool valid = r < nvalid;
-          const double* src = X + (valid ? row0 + r : 0) * (int64_t)f + lane;
-          double* dst = st + r * PW + lane;
-          for (int c0 = 0; c0 < f; c0 += 128) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (c0 + 32 * u + lane < f) cp_async8(dst + c0 + 32 * u, src + c0 + 32 * u, valid);
-          }
-        }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&s_full[stage])) : "memory");
-      }
-    };
-    double sr = 0.0, rr = 0.0;                               // this lane's rows (lane % 4 == 0 only)
-    // residuals of this warp's rows of `chunk` (in stage `it % kWsStages`) -> res_s[it & 1]
-    auto residuals = [&](int64_t chunk, int it) {
-      if (chunk >= nchunks) return;
-      const double* st = stage0 + (size_t)(it % kWsStages) * krows * PW;
-      double* rs = res_s + (it & 1) * kWsMaxRows;
-      const int64_t row0 = chunk * krows;
-      const int rlo = pw * rw, rhi = min(krows, rlo + rw);
-      const int mine = lane >> 2;                            // after the reduction lane holds row rb + mine
-      double yv[2];                                          // rw <= 16: at most two batches of 8 rows
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int r = rlo + 8 * b + mine;
-        yv[b] = (r < rhi && row0 + r < rows) ? ld_stream(y + row0 + r) : 0.0;
-      }
-      mbar_wait(&s_full[it % kWsStages], (uint32_t)(it / kWsStages) & 1u);
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int rb = rlo + 8 * b;
-        if (rb >= rhi) break;
-        double v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.0;
-        for (int c = lane; c < f; c += 32) {
-          const double pc = ps[c];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (rb + i < rhi) v[i] = fma(pc, st[(rb + i) * PW + c], v[i]);
-        }
-        // transposing reduction: 8 rows x 32 lanes -> lane holds the full sum of row rb + lane/4
-        const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0;
-        double w4[4], w2[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
-          w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const double send = h3 ? w4[i] : w4[i + 2], keep = h3 ? w4[i + 2] : w4[i];
-          w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-        double dot;
-        {
-          const double send = h2 ? w2[0] : w2[1], keep = h2 ? w2[1] : w2[0];
-          dot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        const int r = rb + mine;
-        const double z = dot + p0;
-        double res;
-        if (FAM == kLinear) {
-          res = yv[b] - z;
-        } else {
-          const double e = so_exp(-fabs(z));
-          const double inv = 1.0 / (1.0 + e);
-          res = ((z >= 0.0) ? inv : e * inv) - yv[b];
-        }
-        if (r >= rhi || row0 + r >= rows) res = 0.0;
-        if ((lane & 3) == 0 && r < rhi) { rs[r] = res; sr += res; rr = fma(res, res, rr); }
-      }
-    };
+  const bool producer = warp < kWsProducers;
+  const double p0 = icpt ? P.p[0] : 0.0;
 
-    int64_t chunk = worker;
-    load_stage(chunk, 0);
-    load_stage(chunk + nworkers, 1);
-    residuals(chunk, 0);
-    bar_block();                                             // the residuals of the first chunk are visible
-    for (int it = 0; chunk < nchunks; chunk += nworkers, ++it) {
-      load_stage(chunk + 2 * (int64_t)nworkers, (it + 2) % kWsStages);   // the stage released by the last barrier
-      residuals(chunk + nworkers, it + 1);                   // one chunk ahead of the consumers
-      bar_block();                                           // everyone is done with this chunk
+  // ---- producers: stream chunk `chunk` (rows and y) into ring slot `stage`
+  auto load_stage = [&](int64_t chunk, int stage) {
+    if (chunk >= nchunks) return;
+    double* st = stage0 + (size_t)stage * krows * PW;
+    const int64_t row0 = chunk * krows;
+    const int nvalid = (int)min((int64_t)krows, rows - row0);
+    if (warp == 1) {                                       // y of the chunk: plain stores, released by an arrival
+      for (int r = lane; r < krows; r += 32) y_s[stage * kWsMaxRows + r] = (r < nvalid) ? ld_stream(y + row0 + r) : 0.0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[stage]);
     }
-    if (!bulk) asm volatile("cp.async.wait_all;" ::: "memory");
-    if (group == 0) {
-      sr = warp_sum(sr); rr = warp_sum(rr);
-      if (lane == 0) { s_sc[pw][0] = sr; s_sc[pw][1] = rr; }
-      asm volatile("bar.sync 1, %0;" :: "n"(kWsProducers * 32) : "memory");
-      if (tid == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < kWsProducers; ++w) { a += s_sc[w][0]; b += s_sc[w][1]; }
-        int64_t cnt = 0;                                     // rows this worker streamed
-        for (int64_t c = worker; c < nchunks; c += nworkers) cnt += min((int64_t)krows, rows - c * krows);
-        double* ex = extra_partials + (size_t)worker * L.QE;
-        ex[0] = (double)cnt; ex[1] = a; ex[2] = b;
+    if (bulk) {
+      if (warp != 0) return;
+      for (int r = nvalid; r < krows; ++r)                 // ragged last chunk: rows past the end read as zero
+        for (int c = lane; c < f; c += 32) st[r * PW + c] = 0.0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&s_full[stage], (uint32_t)nvalid * (uint32_t)f * 8u);   // releases the zeros too
+      __syncwarp();
+      for (int r = lane; r < nvalid; r += 32) bulk_g2s(st + r * PW, X + (row0 + r) * (int64_t)f, (uint32_t)f * 8u, &s_full[stage]);
+    } else {
+      for (int r = warp; r < krows; r += kWsProducers) {
+        const bool valid = r < nvalid;
+        const double* src = X + (valid ? row0 + r : 0) * (int64_t)f + lane;
+        double* dst = st + r * PW + lane;
+        for (int c0 = 0; c0 < f; c0 += 128) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c0 + 32 * u + lane < f) cp_async8(dst + c0 + 32 * u, src + c0 + 32 * u, valid);
+        }
       }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&s_full[stage])) : "memory");
     }
-  } else {
-    // ------------------------------------------------------------------ consumers
-    const int rsel = lane & 3, csel = lane >> 2;
-    const int cw = warp - kWsProducers;
-    int patch, rep = 0;
-    bool active;
+  };
+
+  // ---- all 16 warps: residuals of chunk `chunk` (ring slot it % stages) -> res_s[it & 1]; warp w takes rows
+  //      w, w+16, w+32, w+48 of the chunk.  This is the only FP64-pipe (non-DMMA) work of the kernel and it runs as
+  //      its own short phase between two DMMA phases: a DFMA of another warp does not get through a saturated
+  //      DMMA stream.
+  double sr = 0.0, rr = 0.0;                               // lanes 0..NR-1: the rows this warp finished
+  const int nr = (krows - warp + 15) >> 4;                 // rows of a chunk this warp finishes (0..8)
+  auto residual_rows = [&]<int NR>(int64_t chunk, int it, int slot) {
+    const double* st = stage0 + (size_t)slot * krows * PW + warp * PW;
+    double v[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) v[i] = 0.0;
+#pragma unroll 2
+    for (int c = lane; c < f; c += 32) {
+      const double pc = ps[c];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) v[i] = fma(pc, st[16 * i * PW + c], v[i]);
+    }
+    // transposing reduction (NR a power of two): every step halves the number of values a lane carries; at the
+    // end lane l holds the full sum of row slot `slot_of(l)`; then slot i is fetched by lane i.
+    double dot;
+    if constexpr (NR == 8 || NR == 4 || NR == 2) {
+      int width = 16;
+      int myslot = 0;
+#pragma unroll
+      for (int n = NR; n > 1; n >>= 1) {
+        const bool hi = (lane & width) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+          const double send = hi ? v[i] : v[i + n / 2], keep = hi ? v[i + n / 2] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+        }
+        myslot += hi ? n / 2 : 0;
+        width >>= 1;
+      }
+      dot = v[0];
+#pragma unroll
+      for (int o = 16 / NR; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      // slot i lives in the lanes whose top log2(NR) bits spell i (bit 4 = NR/2, bit 3 = NR/4, ...)
+      int src = 0;
+#pragma unroll
+      for (int n = NR, bit = 16; n > 1; n >>= 1, bit >>= 1) src |= (lane & (n / 2)) ? bit : 0;
+      dot = __shfl_sync(0xffffffffu, dot, src);
+      (void)myslot;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NR; ++i) v[i] = warp_sum(v[i]);
+      dot = v[0];
+#pragma unroll
+      for (int i = 1; i < NR; ++i) if (lane == i) dot = v[i];
+    }
+    const int r = warp + 16 * lane;                        // lanes 0..NR-1 finish one row each
+    if (lane < NR) {
+      const double z = dot + p0, yv = y_s[slot * kWsMaxRows + r];
+      double res;
+      if (FAM == kLinear) {
+        res = yv - z;
+      } else {
+        const double e = so_exp(-fabs(z));
+        const double inv = 1.0 / (1.0 + e);
+        res = ((z >= 0.0) ? inv : e * inv) - yv;
+      }
+      if (chunk * krows + r >= rows) res = 0.0;
+      res_s[(it & 1) * kWsMaxRows + r] = res;
+      sr += res;
+      rr = fma(res, res, rr);
+    }
+  };
+  auto residual_phase = [&](int64_t chunk, int it) {
+    if (chunk >= nchunks) return;
+    const int slot = it % stages;
+    mbar_wait(&s_full[slot], (uint32_t)(it / stages) & 1u);
+    switch (nr) {
+      case 1: residual_rows.template operator()<1>(chunk, it, slot); break;
+      case 2: residual_rows.template operator()<2>(chunk, it, slot); break;
+      case 3: residual_rows.template operator()<3>(chunk, it, slot); break;
+      case 4: residual_rows.template operator()<4>(chunk, it, slot); break;
+      case 5: residual_rows.template operator()<5>(chunk, it, slot); break;
+      case 6: residual_rows.template operator()<6>(chunk, it, slot); break;
+      case 7: residual_rows.template operator()<7>(chunk, it, slot); break;
+      case 8: residual_rows.template operator()<8>(chunk, it, slot); break;
+      default: break;
+    }
+  };
+
+  // ---- consumers: this warp's patch
+  const int rsel = lane & 3, csel = lane >> 2;
+  const int cw = warp - kWsProducers;
+  int patch = 0, rep = 0;
+  bool active = false;
+  if (!producer) {
     if (L.groups == 1) { patch = cw % npatches; rep = cw / npatches; active = rep < reps; }
     else { patch = group * kWsConsumers + cw; active = patch < npatches; }
-    int pa = 0, pb = 0;
-    if (active) { int rem = patch; while (rem >= PT - pa) { rem -= PT - pa; ++pa; } pb = pa + rem; }
-    const int na = min(kPatch, T - kPatch * pa), nb = min(kPatch, T - kPatch * pb);   // real tiles of the patch
-    const int offa = 8 * kPatch * pa + csel, offb = 8 * kPatch * pb + csel;
-    const int mode = !active ? 0 : (pa == pb ? (na == kPatch ? 1 : 3) : ((na == kPatch && nb == kPatch) ? 2 : 3));
-
-    double acc[kPatch][kPatch][2];
+  }
+  int pa = 0, pb = 0;
+  if (active) { int rem = patch; while (rem >= PT - pa) { rem -= PT - pa; ++pa; } pb = pa + rem; }
+  const int na = min(kPatch, T - kPatch * pa), nb = min(kPatch, T - kPatch * pb);   // real tiles of the patch
+  const int offa = 8 * kPatch * pa + csel, offb = 8 * kPatch * pb + csel;
+  const int mode = !active ? 0 : (pa == pb ? (na == kPatch ? 1 : 3) : ((na == kPatch && nb == kPatch) ? 2 : 3));
+  double acc[kPatch][kPatch][2];
 #pragma unroll
-    for (int i = 0; i < kPatch; ++i)
+  for (int i = 0; i < kPatch; ++i)
 #pragma unroll
-      for (int j = 0; j < kPatch; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int j = 0; j < kPatch; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  const int nslabs = krows >> 2;
 
-    const int nslabs = krows >> 2;
-    int64_t chunk = worker;
-    bar_block();
-    for (int it = 0; chunk < nchunks; chunk += nworkers, ++it) {
-      const double* st = stage0 + (size_t)(it % kWsStages) * krows * PW + rsel * PW;
+  int64_t chunk = worker;
+  if (producer) for (int a = 0; a < stages - 1; ++a) load_stage(chunk + a * (int64_t)nworkers, a);
+  residual_phase(chunk, 0);
+  bar_block();
+  for (int it = 0; chunk < nchunks; chunk += nworkers, ++it) {
+    if (producer) {
+      load_stage(chunk + (stages - 1) * (int64_t)nworkers, (it + stages - 1) % stages);   // the slot released by the last barrier
+    } else if (mode != 0) {
+      const double* st = stage0 + (size_t)(it % stages) * krows * PW + rsel * PW;
       const double* rs = res_s + (it & 1) * kWsMaxRows + rsel;
-      mbar_wait(&s_full[it % kWsStages], (uint32_t)(it / kWsStages) & 1u);
+      mbar_wait(&s_full[it % stages], (uint32_t)(it / stages) & 1u);
       if (mode == 2) {                                     // full off-diagonal patch: 8 fragments, 16 DMMAs per slab
 #pragma unroll 2
         for (int slab = rep; slab < nslabs; slab += reps) {
@@ -583,7 +593,7 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
             dmma(acc[kSlot[i] / kPatch][kSlot[i] % kPatch][0], acc[kSlot[i] / kPatch][kSlot[i] % kPatch][1], fa[i], bx);
           }
         }
-      } else if (mode == 3) {                              // ragged patch at the right / bottom edge
+      } else {                                             // ragged patch at the right / bottom edge
         for (int slab = rep; slab < nslabs; slab += reps) {
           const double* base = st + slab * 4 * PW;
           double fa[kPatch], fb[kPatch];
@@ -607,18 +617,34 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
           }
         }
       }
-      bar_block();
     }
-    // per-(row worker, rep, patch) partials, lane-major tiles: [worker*reps + rep][patch][i][j][lane*2 + reg]
-    if (active) {
-      double* dst = tile_partials + (((size_t)worker * reps + rep) * npatches + patch) * kPatchDoubles;
+    residual_phase(chunk + nworkers, it + 1);              // one chunk ahead of the DMMAs
+    bar_block();                                           // everyone is done with this chunk
+  }
+  if (!bulk) asm volatile("cp.async.wait_all;" ::: "memory");
+
+  // per-(row worker, rep, patch) partials, lane-major tiles: [worker*reps + rep][patch][i][j][lane*2 + reg]
+  if (active) {
+    double* dst = tile_partials + (((size_t)worker * reps + rep) * npatches + patch) * kPatchDoubles;
 #pragma unroll
-      for (int i = 0; i < kPatch; ++i)
+    for (int i = 0; i < kPatch; ++i)
 #pragma unroll
-        for (int j = 0; j < kPatch; ++j) {
-          dst[(i * kPatch + j) * 64 + lane * 2] = acc[i][j][0];
-          dst[(i * kPatch + j) * 64 + lane * 2 + 1] = acc[i][j][1];
-        }
+      for (int j = 0; j < kPatch; ++j) {
+        dst[(i * kPatch + j) * 64 + lane * 2] = acc[i][j][0];
+        dst[(i * kPatch + j) * 64 + lane * 2 + 1] = acc[i][j][1];
+      }
+  }
+  if (group == 0) {                                        // row count, sum res, sum res^2 of this worker
+    sr = warp_sum(sr); rr = warp_sum(rr);
+    if (lane == 0) { s_sc[warp][0] = sr; s_sc[warp][1] = rr; }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < kWsThreads / 32; ++w) { a += s_sc[w][0]; b += s_sc[w][1]; }
+      int64_t cnt = 0;
+      for (int64_t c = worker; c < nchunks; c += nworkers) cnt += min((int64_t)krows, rows - c * krows);
+      double* ex = extra_partials + (size_t)worker * L.QE;
+      ex[0] = (double)cnt; ex[1] = a; ex[2] = b;
     }
   }
   __threadfence();
@@ -687,12 +713,15 @@ inline WsPlan ws_plan(int f, int sm_count) {
   b.reps = b.groups == 1 ? std::max(1, kWsConsumers / b.npatches) : 1;
   b.workers = std::max(1, sm_count / b.groups);
   const size_t W = (size_t)8 * b.T, PW = W + 4;
-  const size_t fixed = sizeof(double) * (W + 2 * kWsMaxRows), budget = 227 * 1024 - 4096;   // static shared: exp table, flags
-  int krows = (int)((budget - fixed) / (sizeof(double) * kWsStages * PW));
+  const size_t fixed = sizeof(double) * (W + (2 + kWsMaxStages) * kWsMaxRows), budget = 227 * 1024 - 4096;   // static shared: exp table, flags
+  b.stages = 2;
+  if (const char* e = getenv("SO_WS_STAGES")) b.stages = atoi(e);
+  int krows = (int)((budget - fixed) / (sizeof(double) * b.stages * PW));
   krows = std::min(kWsMaxRows, krows) & ~3;
+  if (const char* e = getenv("SO_WS_KROWS")) krows = std::min(krows, atoi(e));
   b.krows = krows;
   b.QE = 4;
-  b.smem = fixed + sizeof(double) * kWsStages * (size_t)std::max(krows, 0) * PW;
+  b.smem = fixed + sizeof(double) * b.stages * (size_t)std::max(krows, 0) * PW;
   return b;
 }
 

@@ -11,6 +11,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // MODE 0: fragments from LDS each slab; 1: fragments loaded once (registers); BAR: __syncthreads per chunk of 8 slabs
+// MODE 2/3/4: as 0 + barrier, plus a small per-chunk phase before the barrier: 2 = 8 dependent DFMAs + shuffle sum,
+// 3 = the same length of integer work, 4 = 8 dependent DFMAs only
 template <int MODE, bool BAR>
 __global__ void __launch_bounds__(512, 1) k(const double* __restrict__ src, double* out, int chunks, int PW, int krows) {
   extern __shared__ double sm[];
@@ -20,11 +22,12 @@ __global__ void __launch_bounds__(512, 1) k(const double* __restrict__ src, doub
   const int offa = 32 * (warp % 4) + csel, offb = 32 * ((warp / 4) % 4 + 4) + csel;
   double acc[4][4][2] = {};
   double fa[4], fb[4];
+  double extra = 0.0;
   for (int i = 0; i < 4; ++i) { fa[i] = sm[rsel * PW + offa + 8 * i]; fb[i] = sm[rsel * PW + offb + 8 * i]; }
   for (int c = 0; c < chunks; ++c) {
 #pragma unroll 2
     for (int slab = 0; slab < krows / 4; ++slab) {
-      if (MODE == 0) {
+      if (MODE != 1) {
         const double* base = sm + (slab * 4 + rsel) * PW;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { fa[i] = base[offa + 8 * i]; fb[i] = base[offb + 8 * i]; }
@@ -34,8 +37,23 @@ __global__ void __launch_bounds__(512, 1) k(const double* __restrict__ src, doub
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
     }
+    if (MODE == 2 || MODE == 4) {
+      double d = fa[0];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d = fma(d, fb[q & 3], sm[(c & 7) * PW + lane + 32 * q]);
+      if (MODE == 2) for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      extra += d;
+    }
+    if (MODE == 3) {
+      int d = lane + c;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d = d * 3 + ((const int*)sm)[(c & 7) * PW + lane + 32 * q];
+      for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      extra += d;
+    }
     if (BAR) __syncthreads();
   }
+  if (extra == 1.2345) out[1] = extra;
   double s = 0;
   for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
   if (s == 123.456) out[0] = s;
@@ -70,6 +88,8 @@ int main() {
       run<1, false>("regs", warps, src, out, sms, random);
       run<0, false>("lds", warps, src, out, sms, random);
       run<0, true>("lds+bar", warps, src, out, sms, random);
+      if (random) { run<2, true>("lds+bar+dfma_phase", warps, src, out, sms, random); run<4, true>("lds+bar+dfma_only", warps, src, out, sms, random);
+                    run<3, true>("lds+bar+int_phase", warps, src, out, sms, random); }
     }
   }
   return 0;
