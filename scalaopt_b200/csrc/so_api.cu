@@ -142,8 +142,8 @@ int setup_device(so_ctx* ctx, Device& d) {
   SO_CUDA(ctx, cudaEventCreate(&d.ev0));
   SO_CUDA(ctx, cudaEventCreate(&d.ev1));
   SO_CUDA(ctx, cudaEventCreate(&d.ev2));
-  SO_CUDA(ctx, cudaMalloc(&d.ticket, sizeof(unsigned int)));
-  SO_CUDA(ctx, cudaMemset(d.ticket, 0, sizeof(unsigned int)));
+  SO_CUDA(ctx, cudaMalloc(&d.ticket, 4 * sizeof(unsigned int)));      // [0] last-block ticket, [1..2] grid barrier of k_gram_ws
+  SO_CUDA(ctx, cudaMemset(d.ticket, 0, 4 * sizeof(unsigned int)));
   return SO_OK;
 }
 

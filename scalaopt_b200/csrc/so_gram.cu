@@ -15,6 +15,7 @@
 //               (profiles/r1_fp64_peak.json), and one DMMA replaces 8 DFMA issue slots + their operand traffic.
 //   larger n    warp-specialised shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_ws below), f <= 512
 #include <algorithm>
+#include <vector>
 #include <cstdlib>
 
 #include "so_wide.cuh"
@@ -363,8 +364,8 @@ int dispatch_tri(const Shard& s, const Params& P) {
 //     cp.async.mbarrier.arrive.noinc.  One block barrier per chunk releases the stage.
 //   * grid = (tile groups) x (row workers); tile group is the fastest block index so that the blocks streaming
 //     the same rows run together and share them through L2 (the kernel is FP64-bound: n = 257 needs 66 306 flop
-//     per 2 056-byte row).  When all patches fit one group several consumer warps share a patch and split the
-//     slabs of a chunk between them ("reps").
+//     per 2 056-byte row).  Spare consumer warps share a patch with another warp and split the slabs of a chunk
+//     between them ("reps"); ws_plan() balances the DMMA count over the four SM sub-partitions.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kWsConsumers = 12, kWsProducers = 4, kWsThreads = 32 * (kWsConsumers + kWsProducers);
 constexpr int kPatch = 4, kWsMaxStages = 3, kWsMaxRows = 128;
@@ -378,7 +379,14 @@ __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src, bool 
 }
 __device__ __forceinline__ void bar_block() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-struct WsPlan { int T, PT, npatches, groups, reps, workers, krows, stages, QE; size_t smem; };
+constexpr int kWsMaxGroups = 12, kWsMaxPatches = 136;      // f <= 512: PT <= 16
+struct WsSlot { unsigned char patch, rep, reps, pad; };     // patch 255: idle warp
+struct WsPlan {
+  int T, PT, npatches, groups, reps, workers, krows, stages, QE;     // reps = max over patches
+  size_t smem;
+  WsSlot slot[kWsMaxGroups][kWsConsumers];                   // consumer warp -> (patch, slab residue class)
+  unsigned char preps[kWsMaxPatches];                        // warps sharing a patch
+};
 
 template <int FAM>
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -534,11 +542,11 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
   // ---- consumers: this warp's patch
   const int rsel = lane & 3, csel = lane >> 2;
   const int cw = warp - kWsProducers;
-  int patch = 0, rep = 0;
+  int patch = 0, rep = 0, nrep = 1;
   bool active = false;
   if (!producer) {
-    if (L.groups == 1) { patch = cw % npatches; rep = cw / npatches; active = rep < reps; }
-    else { patch = group * kWsConsumers + cw; active = patch < npatches; }
+    const WsSlot sl = L.slot[group][cw];
+    patch = sl.patch; rep = sl.rep; nrep = sl.reps; active = sl.patch != 255;
   }
   int pa = 0, pb = 0;
   if (active) { int rem = patch; while (rem >= PT - pa) { rem -= PT - pa; ++pa; } pb = pa + rem; }
@@ -565,7 +573,7 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
       mbar_wait(&s_full[it % stages], (uint32_t)(it / stages) & 1u);
       if (mode == 2) {                                     // full off-diagonal patch: 8 fragments, 16 DMMAs per slab
 #pragma unroll 2
-        for (int slab = rep; slab < nslabs; slab += reps) {
+        for (int slab = rep; slab < nslabs; slab += nrep) {
           const double* base = st + slab * 4 * PW;
           double fa[kPatch], fb[kPatch];
 #pragma unroll
@@ -577,7 +585,7 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
         }
       } else if (mode == 1) {                              // full diagonal patch: 4 fragments, 10 + 4 DMMAs per slab
 #pragma unroll 2
-        for (int slab = rep; slab < nslabs; slab += reps) {
+        for (int slab = rep; slab < nslabs; slab += nrep) {
           const double* base = st + slab * 4 * PW;
           double fa[kPatch];
 #pragma unroll
@@ -594,7 +602,7 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
           }
         }
       } else {                                             // ragged patch at the right / bottom edge
-        for (int slab = rep; slab < nslabs; slab += reps) {
+        for (int slab = rep; slab < nslabs; slab += nrep) {
           const double* base = st + slab * 4 * PW;
           double fa[kPatch], fb[kPatch];
 #pragma unroll
@@ -647,19 +655,22 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
       ex[0] = (double)cnt; ex[1] = a; ex[2] = b;
     }
   }
+  // ---- grid barrier (cooperative launch: every block is resident), then ALL blocks fold the partials: block b emits
+  //      outputs b*512 + tid, + nblocks*512, ...  The order of the sum over (worker, rep) is fixed: deterministic.
+  const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
   __threadfence();
   __syncthreads();
-  __shared__ unsigned int s_last;
-  const unsigned int nblocks = gridDim.x * gridDim.y;
-  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == nblocks - 1) ? 1u : 0u;
+  if (tid == 0) {
+    atomicAdd(&ticket[1], 1u);
+    unsigned int seen;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&ticket[1]) : "memory"); } while (seen < nblocks);
+  }
   __syncthreads();
-  if (s_last) {
-    __threadfence();
+  {
     // emit the API layout: packed upper triangle over parameters (a <= b), then Jtr, then rtr.
     constexpr int ONE = -1, RES = -2;
     const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
-    const int nsets = nworkers * reps;
-    for (int q = tid; q < Qo; q += kWsThreads) {
+    for (int q = bid * kWsThreads + tid; q < Qo; q += nblocks * kWsThreads) {
       int ca, cb;
       double sgn = 1.0;
       if (q < Tn) {
@@ -696,21 +707,31 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
           const int ti = (c >> 3) - qa * kPatch, i = c & 7;
           off = (size_t)pidx * kPatchDoubles + ws_extra_slot(ti) * 64 + (i * 4) * 2 + j;
         }
-        for (int w = 0; w < nsets; ++w) s2 += __ldcg(&tile_partials[(size_t)w * npatches * kPatchDoubles + off]);
+        const int pr = L.preps[off / kPatchDoubles];
+#pragma unroll 4
+        for (int w = 0; w < nworkers; ++w)
+          for (int e = 0; e < pr; ++e) s2 += __ldcg(&tile_partials[((size_t)w * reps + e) * npatches * kPatchDoubles + off]);
       }
       out[q] = s2 * sgn;
     }
-    if (tid == 0) *ticket = 0u;
+  }
+  __syncthreads();
+  if (tid == 0 && atomicAdd(&ticket[2], 1u) == nblocks - 1) {    // last block out: everyone is past the barrier
+    ticket[1] = 0u; ticket[2] = 0u;
+    __threadfence();
   }
 }
 
+// Which warp works on what.  Patches are dealt to the tile groups by weight (DMMAs per slab: 16 for a full
+// off-diagonal patch, 10 + 4 for a diagonal one, less at the ragged edge); inside a group spare warps take over slab
+// residue classes of the heaviest patches, and the 12 consumer warps are placed so that the four SM sub-partitions
+// (warp id mod 4: each has its own FP64/DMMA pipe) carry the same number of DMMAs.
 inline WsPlan ws_plan(int f, int sm_count) {
-  WsPlan b;
+  WsPlan b{};
   b.T = (f + 7) / 8;
   b.PT = (b.T + kPatch - 1) / kPatch;
   b.npatches = b.PT * (b.PT + 1) / 2;
   b.groups = (b.npatches + kWsConsumers - 1) / kWsConsumers;
-  b.reps = b.groups == 1 ? std::max(1, kWsConsumers / b.npatches) : 1;
   b.workers = std::max(1, sm_count / b.groups);
   const size_t W = (size_t)8 * b.T, PW = W + 4;
   const size_t fixed = sizeof(double) * (W + (2 + kWsMaxStages) * kWsMaxRows), budget = 227 * 1024 - 4096;   // static shared: exp table, flags
@@ -722,6 +743,63 @@ inline WsPlan ws_plan(int f, int sm_count) {
   b.krows = krows;
   b.QE = 4;
   b.smem = fixed + sizeof(double) * b.stages * (size_t)std::max(krows, 0) * PW;
+
+  // patch weights
+  std::vector<int> weight(b.npatches);
+  {
+    int p = 0;
+    for (int pa = 0; pa < b.PT; ++pa)
+      for (int pb = pa; pb < b.PT; ++pb, ++p) {
+        const int na = std::min(kPatch, b.T - kPatch * pa), nb = std::min(kPatch, b.T - kPatch * pb);
+        weight[p] = pa == pb ? na * (na + 1) / 2 + na : na * nb;
+      }
+  }
+  // patches -> groups: heaviest first into the lightest group that still has a free warp
+  std::vector<int> order(b.npatches);
+  for (int p = 0; p < b.npatches; ++p) order[p] = p;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return weight[x] > weight[y2]; });
+  std::vector<std::vector<int>> members(b.groups);
+  std::vector<int> gload(b.groups, 0);
+  for (int p : order) {
+    int best = -1;
+    for (int g = 0; g < b.groups; ++g)
+      if ((int)members[g].size() < kWsConsumers && (best < 0 || gload[g] < gload[best])) best = g;
+    members[best].push_back(p);
+    gload[best] += weight[p];
+  }
+  const int nslabs = std::max(1, krows / 4);
+  b.reps = 1;
+  for (int g = 0; g < b.groups; ++g) {
+    for (int cw = 0; cw < kWsConsumers; ++cw) b.slot[g][cw] = WsSlot{255, 0, 1, 0};
+    std::vector<int> reps(members[g].size(), 1);
+    int warps = (int)members[g].size();
+    while (warps < kWsConsumers) {                       // spare warps split the heaviest share
+      int best = -1;
+      for (size_t i = 0; i < members[g].size(); ++i)
+        if (reps[i] < nslabs && (best < 0 || weight[members[g][i]] * reps[best] > weight[members[g][best]] * reps[i])) best = (int)i;
+      if (best < 0) break;
+      ++reps[best]; ++warps;
+    }
+    struct Item { int patch, rep, reps; double w; };
+    std::vector<Item> items;
+    for (size_t i = 0; i < members[g].size(); ++i) {
+      b.preps[members[g][i]] = (unsigned char)reps[i];
+      b.reps = std::max(b.reps, reps[i]);
+      for (int e = 0; e < reps[i]; ++e) items.push_back(Item{members[g][i], e, reps[i], (double)weight[members[g][i]] / reps[i]});
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y2) { return x.w > y2.w; });
+    double load[4] = {0, 0, 0, 0};
+    int used[4] = {0, 0, 0, 0};
+    for (const Item& it : items) {                       // heaviest first into the lightest sub-partition with a free warp
+      int best = -1;
+      for (int k = 0; k < 4; ++k)
+        if (used[k] < kWsConsumers / 4 && (best < 0 || load[k] < load[best])) best = k;
+      const int cw = best + 4 * used[best];              // consumer warp cw runs on sub-partition cw % 4 (4 producer warps first)
+      b.slot[g][cw] = WsSlot{(unsigned char)it.patch, (unsigned char)it.rep, (unsigned char)it.reps, 0};
+      load[best] += it.w;
+      ++used[best];
+    }
+  }
   return b;
 }
 
@@ -742,9 +820,12 @@ int launch_ws(const Shard& s, const Params& P) {
   const size_t need = (size_t)b.workers * b.reps * b.npatches * kPatchDoubles + (size_t)b.workers * b.QE;
   const int Qo = P.n * (P.n + 1) / 2 + P.n + 1;
   if (need > s.partials_doubles || (size_t)Qo > s.out_doubles) return SO_ENOMEM;
-  dim3 grid(b.groups, b.workers);
-  kern<<<grid, kWsThreads, b.smem, s.stream>>>(s.X, s.y, s.rows, P, b, s.partials, s.out, s.ticket);
-  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+  dim3 grid(b.groups, b.workers);                        // <= sm_count blocks, one per SM: co-resident (grid barrier)
+  const double* Xp = s.X; const double* yp = s.y; int64_t rows = s.rows;
+  double* partials = s.partials; double* outp = s.out; unsigned int* ticket = s.ticket;
+  void* args[] = {&Xp, &yp, &rows, const_cast<Params*>(&P), &b, &partials, &outp, &ticket};
+  if (cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(kWsThreads), args, b.smem, s.stream) != cudaSuccess) return SO_ECUDA;
+  return 1;
 }
 
 }  // namespace
