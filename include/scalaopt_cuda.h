@@ -171,6 +171,16 @@ int so_eval_loss_grad(so_dataset* ds, int family, const double* p, int n, double
 int so_eval_normal_eq(so_dataset* ds, int family, const double* p, int n,
                       double* JtJ /* n*n row-major, full symmetric */, double* Jtr /* n */, double* rtr);
 
+/* K2 without the normal equations: the R factor of the m x (n+1) matrix [J | r] that
+ * QR.apply (linalg/QR.scala:131-250) factors with 2n+1 passes over the data set — here one pass, Householder TSQR on
+ * the rows themselves (per-thread triangles merged up a fixed tree, then across GPUs), so the condition number of J
+ * is NOT squared.  R is (n+1) x (n+1) row-major upper triangular with
+ *   R^T R = [ JtJ  Jtr ; Jtr^T  rtr ]   (same conventions and scaling as so_eval_normal_eq),
+ * i.e. rows i < n are (R_J[i,:] | (Q^T r)_i) and R[n][n] = +-||r - J J^+ r||: exactly the (n+1)-row system
+ * MSEFunction.jacobianAndResidualsMatrix hands to QR.apply in the drop-in (row signs are arbitrary, as with any QR).
+ * Single-input families only (SO_EUNSUPPORTED otherwise). */
+int so_eval_qr(so_dataset* ds, int family, const double* p, int n, double* R /* (n+1)*(n+1) */);
+
 /* K3. k step sizes scored in one pass:  phi[j] = loss(p + alpha[j] d),  dphi[j] = grad(p + alpha[j] d) . d
  * (LineSearchPoint.fx / dfx, variable/Point.scala:54-57, as requested by linesearch/StrongWolfe.scala:96-118,214-217). */
 int so_eval_line(so_dataset* ds, int family, const double* p, const double* d, int n,

@@ -79,6 +79,11 @@ soh_objective* soh_objective_from_callbacks(int n, soh_apply_fn apply, soh_gradi
  * FFNeuralNetworkTrainer's logistic case.  The data set must outlive the objective. */
 soh_objective* soh_objective_gpu(so_ctx* ctx, so_dataset* ds, int f, int family, int n);
 
+/* GpuMSEFunction.jacobianAndResidualsMatrix from so_eval_qr (on-device Householder TSQR of [J | r])
+ * instead of so_eval_normal_eq + Cholesky: one pass either way, about 2.5x the kernel time at n = 5, and the condition
+ * number of J is not squared.  Single-input families. */
+int soh_objective_use_tsqr(soh_objective* objective, int on);
+
 /* negLogLikelihood(pdf, GpuDataSet(ds)) _ (std-apps/.../stats/package.scala:97-103) with finite-difference derivatives
  * (what the reference's implicit `toFunctionWoGradient` gives a plain closure, core/.../package.scala:74-77). */
 soh_objective* soh_objective_gpu_nll(so_ctx* ctx, so_dataset* ds, int pdf, int n, const double* consts, int nconsts);

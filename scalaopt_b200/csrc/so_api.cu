@@ -251,6 +251,12 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
       sh.partials = dv.partials; sh.partials_doubles = dv.partials_cap;
       sh.out = dv.out; sh.out_doubles = dv.out_cap; sh.ticket = dv.ticket;
       sh.stream = dv.stream; sh.sm_count = dv.sm_count;
+      if (kind == kQr) {      // every device writes its triangle into its own slot of a zeroed buffer: the sum is a gather
+        const int slot = ctx->rank_mode ? ctx->rank : g, per = (n + 1) * (n + 1);
+        SO_CUDA(ctx, cudaMemsetAsync(dv.out, 0, sizeof(double) * (size_t)Q, dv.stream));
+        sh.out = dv.out + (size_t)slot * per;
+        sh.out_doubles = (size_t)per;
+      }
       rc = nll ? launch_nll(sh, nll->pdf, p, n, nll->consts, nll->nconsts)
                : scalar ? launch_scalar(kind, sh, family, p, d, n, alpha, k, want_grad)
                         : launch_wide(kind, sh, family, p, d, n, alpha, k, want_grad);
@@ -735,6 +741,49 @@ extern "C" int so_eval_normal_eq(so_dataset* ds, int family, const double* p, in
     for (int b = a; b < n; ++b) { JtJ[a * n + b] = res[q]; JtJ[b * n + a] = res[q]; ++q; }
   for (int a = 0; a < n; ++a) Jtr[a] = res[T + a];
   *rtr = res[T + n];
+  return SO_OK;
+}
+
+// R factor of [R_0; R_1; ...]: Householder on the stacked triangles, rank order (host, O(G n^3))
+static void merge_triangles(const double* tri, int count, int C, double* R) {
+  std::vector<double> A((size_t)count * C * C);
+  std::copy(tri, tri + (size_t)count * C * C, A.begin());
+  const int M = count * C;
+  for (int j = 0; j < C; ++j) {
+    double sigma = 0.0;
+    for (int i = j + 1; i < M; ++i) sigma += A[(size_t)i * C + j] * A[(size_t)i * C + j];
+    const double ajj = A[(size_t)j * C + j];
+    const double nrm = std::sqrt(ajj * ajj + sigma);
+    if (nrm == 0.0) continue;
+    const double alpha = ajj > 0.0 ? -nrm : nrm, vp = ajj - alpha, beta = -1.0 / (alpha * vp);
+    A[(size_t)j * C + j] = alpha;
+    for (int k = j + 1; k < C; ++k) {
+      double sdot = vp * A[(size_t)j * C + k];
+      for (int i = j + 1; i < M; ++i) sdot += A[(size_t)i * C + j] * A[(size_t)i * C + k];
+      sdot *= beta;
+      A[(size_t)j * C + k] -= sdot * vp;
+      for (int i = j + 1; i < M; ++i) A[(size_t)i * C + k] -= sdot * A[(size_t)i * C + j];
+    }
+    for (int i = j + 1; i < M; ++i) A[(size_t)i * C + j] = 0.0;
+  }
+  for (int j = 0; j < C; ++j)
+    for (int k = 0; k < C; ++k) R[j * C + k] = k >= j ? A[(size_t)j * C + k] : 0.0;
+}
+
+extern "C" int so_eval_qr(so_dataset* ds, int family, const double* p, int n, double* R) {
+  if (!ds || !p || !R) return SO_EINVAL;
+  so_ctx* ctx = ds->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = check_family(ctx, family, ds->f, n);
+  if (rc) return rc;
+  if (!family_is_scalar_t(family)) return fail(ctx, SO_EUNSUPPORTED, "so_eval_qr: family %d is outside the TSQR catalogue (single-input families)", family);
+  const int C = n + 1, per = C * C;
+  const int slots = ctx->rank_mode ? ctx->world : (int)ctx->devs.size();
+  std::vector<double> res;
+  rc = run_eval(ds, kQr, family, p, nullptr, n, nullptr, 0, 0, slots * per, res);
+  if (rc) return rc;
+  if (slots == 1) std::copy(res.begin(), res.begin() + per, R);
+  else merge_triangles(res.data(), slots, C, R);
   return SO_OK;
 }
 

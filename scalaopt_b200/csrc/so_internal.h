@@ -23,7 +23,7 @@ struct Shard {
   int sm_count = 148;
 };
 
-enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4, kNll = 5 };
+enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4, kNll = 5, kQr = 6 };
 
 // number of doubles each evaluation leaves in Shard::out (before the 1/m normalisation, which the
 // API layer applies after the cross-GPU sum):
@@ -31,6 +31,7 @@ enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4, kNll = 5 };
 //   kNormalEq : [ JtJ upper triangle packed row-major (a<=b), Jtr_0..Jtr_{n-1}, rtr ]
 //   kLine     : [ phi_sum_0..phi_sum_{k-1}, dphi_sum_0..dphi_sum_{k-1} ]
 //   kHessVec  : [ Hd_sum_0 .. Hd_sum_{n-1} ]
+//   kQr       : [ R, (n+1) x (n+1) row-major, upper triangular: the R factor of this shard's rows of [J | r] ]
 inline int out_doubles(Kind kind, int n, int k) {
   switch (kind) {
     case kLossGrad: return 1 + n;
@@ -38,6 +39,7 @@ inline int out_doubles(Kind kind, int n, int k) {
     case kLine: return 2 * k;
     case kHessVec: return n;
     case kNll: return 1;
+    case kQr: return (n + 1) * (n + 1);
   }
   return 0;
 }

@@ -18,6 +18,7 @@
 // Derivatives are therefore expressed as df/dp_a = D_a * u_a with D_a constant over the data set: the
 // kernels accumulate sums of u_a u_b, u_a rho, rho^2 and the last block applies D on the way out.
 #include <algorithm>
+#include <utility>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -335,13 +336,177 @@ struct OpNll {
 };
 
 // G rows: all exp arguments first, ONE range check, then branch-free exponentials, then the accumulation.
+// ---------------------------------------------------------------------------------------------------
+// TSQR of the m x (n+1) matrix [J | r]: what QR.apply (linalg/QR.scala:131-250) computes with 2n+1
+// passes over the data set, in ONE pass and without forming J^T J.  Every thread keeps a private upper-triangular
+// R (C = n+1 columns, C(C+1)/2 registers) and folds B rows at a time into it with C Householder reflections of the
+// stacked matrix [R; rows] — the reflector of column j is (R_jj - alpha; a_1j .. a_Bj) because everything else in
+// that column is already zero.  No communication until the end; then triangles are merged pairwise (the QR of two
+// stacked triangles) up a fixed tree: lanes, warps, blocks.  Householder on the rows themselves is backward stable
+// whatever the conditioning of J; the normal-equations route (K2 + Cholesky) squares the condition number.
+// Rows are the derivative BASIS rows (u_0 .. u_{n-1}, rho): [J | r] = +-[u | rho] diag(-D, 1), so R_A = R_U diag(-D, 1).
+// ---------------------------------------------------------------------------------------------------
+template <int C> __host__ __device__ constexpr int tri_idx(int j, int k) { return j * C - j * (j - 1) / 2 + (k - j); }
+
+// 1/x and sqrt(x) for normal, positive x: MUFU seed + Newton steps, branch-free (the IEEE sequences the compiler emits
+// for `/` and sqrt() carry slow-path calls; at 2 per column and 8 rows per fold they were a third of the kernel's code).
+// Both are accurate to ~1 ulp, which is all a Householder reflector needs (its error enters as O(eps) orthogonality).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double fast_sqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = r * fma(-0.5 * x * r, r, 1.5);            // Newton on 1/sqrt
+  r = r * fma(-0.5 * x * r, r, 1.5);
+  r = r * fma(-0.5 * x * r, r, 1.5);
+  const double sq = x * r;
+  return fma(0.5 * r, fma(-sq, sq, x), sq);     // one correction step on sqrt itself
+}
+
+// compile-time loops: every index of R[] and a[][] below is a constant expression whatever the unroller decides
+// (with plain `#pragma unroll` loops the 8-row fold of C >= 5 columns was left partly rolled and a[][] went to
+// local memory: 10x slower).
+template <int... I, class F> __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F&& f) { (f(std::integral_constant<int, I>()), ...); }
+template <int N, class F> __device__ __forceinline__ void static_for(F&& f) { static_for_impl(std::make_integer_sequence<int, N>(), f); }
+
+template <int C, int B>
+__device__ __forceinline__ void qr_fold(double (&R)[C * (C + 1) / 2], double (&a)[B][C]) {
+  static_for<C>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    double sigma = 0.0;
+    static_for<B>([&](auto I) { constexpr int i = decltype(I)::value; sigma = fma(a[i][j], a[i][j], sigma); });
+    const double rjj = R[tri_idx<C>(j, j)];
+    const double t2 = fma(rjj, rjj, sigma);
+    const double nrm = t2 > 0.0 ? fast_sqrt(t2) : 0.0;
+    const double alpha = rjj > 0.0 ? -nrm : nrm;           // -sign(R_jj) ||(R_jj; a_:j)||: no cancellation in vp
+    const double vp = rjj - alpha;
+    const double beta = nrm > 0.0 ? fast_rcp(nrm * fabs(vp)) : 0.0;   // 2 / v.v,  v.v = -2 alpha vp = 2 nrm |vp|
+    R[tri_idx<C>(j, j)] = alpha;
+    static_for<C - 1 - j>([&](auto K) {
+      constexpr int k = j + 1 + decltype(K)::value;
+      double s = vp * R[tri_idx<C>(j, k)];
+      static_for<B>([&](auto I) { constexpr int i = decltype(I)::value; s = fma(a[i][j], a[i][k], s); });
+      s *= beta;
+      R[tri_idx<C>(j, k)] = fma(-s, vp, R[tri_idx<C>(j, k)]);
+      static_for<B>([&](auto I) { constexpr int i = decltype(I)::value; a[i][k] = fma(-s, a[i][j], a[i][k]); });
+    });
+  });
+}
+
+// R <- R factor of [R; S], S a packed upper triangle
+template <int C>
+__device__ __forceinline__ void qr_merge(double (&R)[C * (C + 1) / 2], const double (&S)[C * (C + 1) / 2]) {
+  double a[C][C];
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+#pragma unroll
+    for (int k = 0; k < C; ++k) a[i][k] = k >= i ? S[tri_idx<C>(i, k)] : 0.0;
+  qr_fold<C, C>(R, a);
+}
+
+// lanes 0 of every warp -> warp 0 -> (thread 0 of the block): fixed binary tree
+template <int C>
+__device__ __forceinline__ void qr_block_tree(double (&R)[C * (C + 1) / 2], double* smem) {
+  constexpr int Q = C * (C + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  auto warp_tree = [&]() {
+    for (int o = 16; o >= 1; o >>= 1) {
+      double S[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) S[q] = __shfl_down_sync(0xffffffffu, R[q], o);
+      qr_merge<C>(R, S);
+    }
+  };
+  warp_tree();
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) smem[warp * Q + q] = R[q];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) R[q] = lane < nwarps ? smem[lane * Q + q] : 0.0;
+    warp_tree();
+  }
+  __syncthreads();
+}
+
+template <int C>
+__device__ __forceinline__ void qr_grid_reduce(double (&R)[C * (C + 1) / 2], double* smem, double* __restrict__ partials,
+                                               double* __restrict__ out, const double* __restrict__ colscale,
+                                               unsigned int* ticket) {
+  constexpr int Q = C * (C + 1) / 2;
+  qr_block_tree<C>(R, smem);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) partials[(size_t)blockIdx.x * Q + q] = R[q];
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last_qr;
+  if (threadIdx.x == 0) s_last_qr = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last_qr) {
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < Q; ++q) R[q] = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {      // block order within a thread, then the tree
+      double S[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) S[q] = __ldcg(&partials[(size_t)b * Q + q]);
+      qr_merge<C>(R, S);
+    }
+    qr_block_tree<C>(R, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+#pragma unroll
+        for (int k = 0; k < C; ++k) out[j * C + k] = k >= j ? R[tri_idx<C>(j, k)] * colscale[k] : 0.0;
+      *ticket = 0u;
+    }
+  }
+}
+
+template <class Fam>
+struct OpQr {
+  static constexpr int N = Fam::N, C = N + 1, Q = C * (C + 1) / 2, NEXP = Fam::NE, G = C <= 6 ? 8 : 4;   // rows per fold
+  struct Args { typename Fam::Pre pre; double scale[C]; };
+  static constexpr bool kHasSrc = false, kNeedsY = true, kGroupFold = true;
+  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void row(const Args& a, double t, double y, const double* ex, double (&r)[C]) {
+    double f, u[N];
+    Fam::finish(a.pre, t, ex, f, u);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = u[i];
+    r[N] = Fam::residual(a.pre, y, ex, f);
+  }
+  template <int B>
+  __device__ static __forceinline__ void accum_group(const Args& a, const double (&t)[B], const double (&y)[B],
+                                                     const double* ex, double (&acc)[Q]) {   // ex: [B][NEXP]
+    double rows[B][C];
+#pragma unroll
+    for (int i = 0; i < B; ++i) row(a, t[i], y[i], ex + i * NEXP, rows[i]);
+    qr_fold<C, B>(acc, rows);
+  }
+  __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
+    const double tt[1] = {t}, yy[1] = {y};
+    accum_group<1>(a, tt, yy, ex, acc);
+  }
+};
+
 template <class Op, int G, bool BIG, bool CHECK = true>
 __device__ __forceinline__ void process_rows(const typename Op::Args& args, const double (&t)[G], const double (&y)[G],
                                              double (&acc)[Op::Q], const double* __restrict__ big_tab) {
   constexpr int NE = Op::NEXP;
   if constexpr (NE == 0) {
+    if constexpr (requires { Op::kGroupFold; }) Op::template accum_group<G>(args, t, y, nullptr, acc);
+    else {
 #pragma unroll
-    for (int r = 0; r < G; ++r) Op::accum(args, t[r], y[r], nullptr, acc);
+      for (int r = 0; r < G; ++r) Op::accum(args, t[r], y[r], nullptr, acc);
+    }
   } else {
     double ea[G][NE];
     int mx = 0;
@@ -364,8 +529,11 @@ __device__ __forceinline__ void process_rows(const typename Op::Args& args, cons
 #pragma unroll
         for (int e = 0; e < NE; ++e) ea[r][e] = exp_slow(ea[r][e]);
     }
+    if constexpr (requires { Op::kGroupFold; }) Op::template accum_group<G>(args, t, y, &ea[0][0], acc);
+    else {
 #pragma unroll
-    for (int r = 0; r < G; ++r) Op::accum(args, t[r], y[r], ea[r], acc);
+      for (int r = 0; r < G; ++r) Op::accum(args, t[r], y[r], ea[r], acc);
+    }
   }
 }
 
@@ -388,6 +556,12 @@ __device__ __forceinline__ void process1(const typename Op::Args& args, double t
                                          const double* __restrict__ big_tab) {
   const double tg[1] = {t}, yg[1] = {y};
   process_rows<Op, 1, BIG>(args, tg, yg, acc, big_tab);
+}
+
+template <class Op, bool BIG>
+__device__ __noinline__ void process1_cold(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q],
+                                           const double* __restrict__ big_tab) {
+  process1<Op, BIG>(args, t, y, acc, big_tab);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -490,6 +664,17 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
         }
       }
     }
+    if constexpr (Op::G == 8 && RPT == 8) {
+      if (tid + 3 * TPB < npairs) {                             // all 8 rows of this thread are there: one fold of 8
+        const double t8[8] = {tv[0].x, tv[0].y, tv[1].x, tv[1].y, tv[2].x, tv[2].y, tv[3].x, tv[3].y};
+        const double y8[8] = {yv[0].x, yv[0].y, yv[1].x, yv[1].y, yv[2].x, yv[2].y, yv[3].x, yv[3].y};
+        process_rows<Op, 8, BIG, CHECK>(args, t8, y8, acc, big_tab);
+      } else {                                                  // ragged last chunk: one row at a time, out of line
+#pragma unroll
+        for (int j = 0; j < RPT / 2; ++j)
+          if (tid + j * TPB < npairs) { process1_cold<Op, BIG>(args, tv[j].x, yv[j].x, acc, big_tab); process1_cold<Op, BIG>(args, tv[j].y, yv[j].y, acc, big_tab); }
+      }
+    } else
 #pragma unroll
     for (int j = 0; j < RPT / 2; j += 2) {
       if (tid + (j + 1) * TPB < npairs) {
@@ -500,11 +685,17 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
     }
     if constexpr (requires { Op::renorm(acc); }) Op::renorm(acc);
   }
-  if (blockIdx.x == 0 && tid == 0 && head) process1<Op, BIG>(args, t[0], Op::kNeedsY ? y[0] : 0.0, acc, big_tab);
-  if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op, BIG>(args, t[rows - 1], Op::kNeedsY ? y[rows - 1] : 0.0, acc, big_tab);
+  if constexpr (requires { Op::kGroupFold; }) {
+    if (blockIdx.x == 0 && tid == 0 && head) process1_cold<Op, BIG>(args, t[0], y[0], acc, big_tab);
+    if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1_cold<Op, BIG>(args, t[rows - 1], y[rows - 1], acc, big_tab);
+  } else {
+    if (blockIdx.x == 0 && tid == 0 && head) process1<Op, BIG>(args, t[0], Op::kNeedsY ? y[0] : 0.0, acc, big_tab);
+    if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op, BIG>(args, t[rows - 1], Op::kNeedsY ? y[rows - 1] : 0.0, acc, big_tab);
+  }
   if constexpr (requires { Op::finalize(acc); }) { Op::renorm(acc); Op::finalize(acc); }
 
-  if constexpr (Op::kHasSrc) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, args.src);
+  if constexpr (requires { Op::kGroupFold; }) qr_grid_reduce<Op::C>(acc, s_red, partials, out, args.scale, ticket);
+  else if constexpr (Op::kHasSrc) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, args.src);
   else if constexpr (requires { args.scale2; }) grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket, nullptr, Q / 2, args.scale2);
   else grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket);
 }
@@ -604,6 +795,13 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       typename Op::Args a; a.pre = pre; a.h = Fam::hprepare(p, d);
       for (int i = 0; i < N; ++i) { a.dd[i] = pre.D[i] * d[i]; a.scale[i] = pre.D[i]; a.scale2[i] = -1.0; }
       return launch_op<Op, 3>(s, a);
+    }
+    case kQr: {
+      using Op = OpQr<Fam>;
+      typename Op::Args a; a.pre = pre;
+      for (int i = 0; i < N; ++i) a.scale[i] = -pre.D[i];          // J = -sign(rho) df/dp, r = |rho|: rows +-(-D u | rho)
+      a.scale[N] = 1.0;
+      return launch_op_cfg<Op, 256, 1, 0, 8>(s, a);
     }
     case kNll: break;      // served by launch_nll
   }

@@ -99,6 +99,7 @@ class GpuMSEFunction : public MSEFunction {
  public:
   std::shared_ptr<GpuDataSet> data; int family; int n;
   int line_batch = 3;               // step sizes scored per K3 pass once a line search needs a second trial point
+  bool use_tsqr = false;            // jacobianAndResidualsMatrix from so_eval_qr (Householder on the rows) instead of K2 + Cholesky
   mutable GpuCounters counters;
   GpuMSEFunction(std::shared_ptr<GpuDataSet> d, int family_, int n_) : data(std::move(d)), family(family_), n(n_) {}
 
@@ -144,6 +145,19 @@ class GpuMSEFunction : public MSEFunction {
   std::shared_ptr<DataSet<AugmentedRow>> jacobianAndResidualsMatrix(const Vec& p) const override {
     counters.jacobian_calls++;
     loss_only_mode = true;          // Levenberg-Marquardt only ever asks for the loss between Jacobians
+    if (use_tsqr) {
+      // the rows of the R factor of [J | r] ARE the (n+1)-row system; no Gram matrix, no Cholesky
+      std::vector<double> Rf((size_t)(n + 1) * (n + 1));
+      check(so_eval_qr(data->ds, family, p.data(), n, Rf.data()));
+      counters.k2_passes++;
+      double rtr = 0.0;
+      for (int i = 0; i <= n; ++i) rtr += Rf[(size_t)i * (n + 1) + n] * Rf[(size_t)i * (n + 1) + n];
+      { int64_t m = data->size(); remember(p, rtr / (2.0 * (double)m), nullptr); }
+      std::vector<AugmentedRow> rows;
+      for (int i = 0; i <= n; ++i)
+        rows.emplace_back(Vec(Rf.begin() + (size_t)i * (n + 1), Rf.begin() + (size_t)i * (n + 1) + n), Rf[(size_t)i * (n + 1) + n], (int64_t)i);
+      return std::make_shared<SeqDataSet<AugmentedRow>>(std::move(rows));
+    }
     std::vector<double> JtJ((size_t)n * n), Jtr(n);
     double rtr = 0.0;
     check(so_eval_normal_eq(data->ds, family, p.data(), n, JtJ.data(), Jtr.data(), &rtr));

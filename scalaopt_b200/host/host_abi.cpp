@@ -107,6 +107,13 @@ extern "C" soh_objective* soh_objective_gpu(so_ctx* ctx, so_dataset* ds, int f, 
   return o;
 }
 
+extern "C" int soh_objective_use_tsqr(soh_objective* o, int on) {
+  auto* g = o ? dynamic_cast<GpuMSEFunction*>(o->fn.get()) : nullptr;
+  if (!g) { g_err = "soh_objective_use_tsqr: not a GPU least-squares objective"; return SOH_ILLEGAL_ARG; }
+  g->use_tsqr = on != 0;
+  return SOH_OK;
+}
+
 extern "C" soh_objective* soh_objective_gpu_nll(so_ctx* ctx, so_dataset* ds, int pdf, int n, const double* consts, int nconsts) {
   if (!ctx || !ds || n < 1 || (nconsts > 0 && !consts)) { g_err = "soh_objective_gpu_nll: bad arguments"; return nullptr; }
   auto data = std::make_shared<GpuDataSet>(ctx, ds, 1, false);

@@ -27,7 +27,7 @@ EXPORTS = [
     "so_host_alloc", "so_host_free",
     "so_dataset_create", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
     "so_dataset_size", "so_dataset_head", "so_dataset_slice", "so_dataset_free",
-    "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_line", "so_eval_hess_vec", "so_eval_nll", "so_stats",
+    "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_qr", "so_eval_line", "so_eval_hess_vec", "so_eval_nll", "so_stats",
 ]
 
 
@@ -91,6 +91,7 @@ def load():
     L.so_dataset_free.restype = None
     L.so_eval_loss_grad.argtypes = [vp, i32, _dp, i32, _dp, _dp]
     L.so_eval_normal_eq.argtypes = [vp, i32, _dp, i32, _dp, _dp, _dp]
+    L.so_eval_qr.argtypes = [vp, i32, _dp, i32, _dp]
     L.so_eval_line.argtypes = [vp, i32, _dp, _dp, i32, _dp, i32, _dp, _dp]
     L.so_eval_hess_vec.argtypes = [vp, i32, _dp, _dp, i32, _dp]
     L.so_eval_nll.argtypes = [vp, i32, _dp, i32, _dp, i32, _dp]
@@ -262,6 +263,13 @@ class Dataset:
         rtr = C.c_double()
         self.ctx.check(load().so_eval_normal_eq(self._h, family, _ptr(p), n, _ptr(JtJ), _ptr(Jtr), C.byref(rtr)))
         return JtJ, Jtr, rtr.value
+
+    def qr(self, family, p):
+        """R factor ((n+1) x (n+1), upper triangular) of [J | r] by on-device Householder TSQR."""
+        p = _vec(p)
+        R = np.empty((p.size + 1, p.size + 1))
+        self.ctx.check(load().so_eval_qr(self._h, family, _ptr(p), p.size, _ptr(R)))
+        return R
 
     def line(self, family, p, d, alphas):
         p, d, al = _vec(p), _vec(d), _vec(alphas)

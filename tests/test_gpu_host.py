@@ -16,10 +16,10 @@ def host():
     return h
 
 
-def _gpu(native, host, ctx, fam, X, y, n):
+def _gpu(native, host, ctx, fam, X, y, n, tsqr=False):
     X = np.asarray(X, float).reshape(len(y), -1)
     ds = native.Dataset(ctx, len(y), X.shape[1]).append(X, y)
-    return ds, host.Objective.gpu(ctx, ds, fam, n)
+    return ds, host.Objective.gpu(ctx, ds, fam, n, tsqr=tsqr)
 
 
 def test_gpu_objective_answers_the_objective_function_interface(native, oracle, host, gpu_ctx):
@@ -50,8 +50,12 @@ def test_gpu_objective_answers_the_objective_function_interface(native, oracle, 
 CASES = ["gauss_expbkg", "lm_spec_linear", "lm_spec_exponential", "expdecay_large", "poly"]
 
 
+@pytest.mark.parametrize("tsqr", [False, True])
 @pytest.mark.parametrize("case", CASES)
-def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu_ctx, case):
+def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu_ctx, case, tsqr):
+    """tsqr=False: K2 + Cholesky; tsqr=True: the (n+1)-row system is the R factor from so_eval_qr."""
+    if tsqr and case == "lm_spec_linear":
+        pytest.skip("TSQR covers the single-input families")
     if case == "gauss_expbkg":         # BASELINE config 3 at oracle-sized m
         fam, n = oracle.GAUSS_EXPBKG, 5
         truth = np.array([2.0, 0.5, 0.05, 1.0, 3.0])
@@ -71,7 +75,7 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
         fam, n = oracle.POLY, 4
         X, y = oracle.generate(fam, 50_000, 1, [1.0, -2.0, 0.5, 3.0], noise_sigma=0.1)
         start = np.array([0.0, 0.0, 0.0, 0.0])
-    ds, f_gpu = _gpu(native, host, gpu_ctx, fam, X, y, n)
+    ds, f_gpu = _gpu(native, host, gpu_ctx, fam, X, y, n, tsqr=tsqr)
     f_ref = oracle_objective(host, oracle, fam, X, y, n)
     x_gpu, r_gpu = host.minimize(host.LEVENBERG_MARQUARDT, f_gpu, start)
     x_ref, r_ref = host.minimize(host.LEVENBERG_MARQUARDT, f_ref, start)

@@ -38,6 +38,11 @@ def test_sharded_evaluation_matches_oracle(native, oracle, G, m):
         phi_o, dphi_o = oracle.line(fam, X, y, p, d, [0.0, 1.0, 2.0])
         assert_vec(phi, phi_o, what="phi"); assert_vec(dphi, dphi_o, rtol=1e-11, what="dphi")
         assert_vec(ds.hess_vec(fam, p, d), oracle.hess_vec(fam, X, y, p, d), rtol=1e-11, what="Hd")
+        # TSQR: per-GPU triangles gathered through the all-reduce and merged on the host in rank order
+        R = ds.qr(fam, p)
+        Gm = np.block([[JtJ_o, Jtr_o[:, None]], [Jtr_o[None, :], np.array([[rtr_o]])]])
+        assert np.all(np.tril(R, -1) == 0.0)
+        assert np.max(np.abs(R.T @ R - Gm) / np.sqrt(np.outer(np.diag(Gm), np.diag(Gm)))) < 1e-11
         # device-side generation across shards continues the global row counter
         ds2 = native.Dataset(ctx, m, 1).generate(fam, truth, noise_sigma=0.05)
         X2, _ = ds2.read(0, m)
