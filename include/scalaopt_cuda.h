@@ -62,7 +62,17 @@ typedef enum so_family {
   SO_FAMILY_GAUSS_EXPBKG = 5,
   /* y ~ sum_k p[k] t^k; f = 1, 1 <= n <= SO_MAX_POLY_N */
   SO_FAMILY_POLY = 6,
-  SO_FAMILY_COUNT = 7
+  /* FFNeuralNetwork(Vector(f, h, 1)) with logistic inner neurons trained by FFNeuralNetworkTrainer (SURVEY.md 8f.3;
+   * std-apps/.../nnet/FFNeuralNetwork.scala:114-189, Neuron.scala:40-73, FFNeuralNetworkTrainer.scala:59-131):
+   * n = h (f + 1) + h + 1 weights in the reference's order (hidden neurons, then the output neuron; bias first), so h
+   * follows from n and f.  MLP_MSE: LossType.MeanSquaredError with a LinearFunction output (loss = residual^2 — the
+   * reference does not halve it here); MLP_CE: LossType.CrossEntropy with a LogisticFunction output, y in [0, 1].
+   * Catalogue: f <= 4, h <= 4; so_eval_normal_eq additionally needs n <= 9 (Vector(2, 2, 1), the shape of the
+   * reference's own spec).  so_eval_line / so_eval_hess_vec are composed from loss+gradient passes the way the
+   * reference composes them (dirHessian = forward difference of gradients, eps = 1e-8, Trainer.scala:76-80). */
+  SO_FAMILY_MLP_MSE = 7,
+  SO_FAMILY_MLP_CE = 8,
+  SO_FAMILY_COUNT = 9
 } so_family;
 
 #define SO_MAX_POLY_N   8      /* polynomial family: at most 8 coefficients */

@@ -75,7 +75,15 @@ static double inner(const double* a, const double* b, int len) {
   return acc;
 }
 
+static void mlp_backprop(int family, const double* p, int n, const double* x, int f, double y,
+                         double* grad, double* residual, double* loss, double* output);
+
 double orc_model(int family, const double* p, int n, const double* x, int f) {
+  if (family == ORC_MLP_MSE || family == ORC_MLP_CE) {
+    double out;
+    mlp_backprop(family, p, n, x, f, 0.0, NULL, NULL, NULL, &out);
+    return out;
+  }
   switch (family) {
     case ORC_LINEAR:        /* p(0) + p.tail.inner(x): LevenbergMarquardtSpec.scala:38-40 */
       return p[0] + inner(p + 1, x, f);
@@ -247,6 +255,51 @@ static void fold_rows(row_fn fn, const void* ctx, const double* X, const double*
   free(accs);
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * FFNeuralNetwork(Vector(f, h, 1)).forward(x).backward(y), one row.
+ * forward: Neuron.activate, excitation = weights(0) + (inputs dot weights.tail) (Neuron.scala:40-49);
+ *   inner neurons LogisticFunction, output neuron LinearFunction (MSE) or LogisticFunction (cross-entropy).
+ * backward, outer layer (FFNeuralNetwork.scala:159-181): MSE: Neuron.propagateError(target, f): lossDerivative =
+ *   output - target, error = lossDerivative * f.derivative(output), residual = lossDerivative (Neuron.scala:51-56);
+ *   cross-entropy, one output: residual = output - target, error = residual.
+ * inner layer (Neuron.scala:58-63): lossDerivative = sum over next layer of error * weights(index + 1),
+ *   error = lossDerivative * output (1 - output), residual = next.head.residual.
+ * gradient = (1 +: inputs) * error per neuron, layer by layer (Neuron.scala:65, FFNeuralNetwork.scala:62-64);
+ * loss = residual^2 (MSE: norm2 of the output residuals, :70-72) or the cross-entropy of :73-81.
+ * ------------------------------------------------------------------------------------------- */
+static int mlp_hidden(int n, int f) { return (n - 1) / (f + 2); }
+
+static void mlp_backprop(int family, const double* p, int n, const double* x, int f, double y,
+                         double* grad, double* residual, double* loss, double* output) {
+  int h = mlp_hidden(n, f);
+  double o[ORC_MAXN];
+  for (int j = 0; j < h; ++j) {
+    const double* w = p + (size_t)j * (f + 1);
+    double excitation = w[0] + inner(x, w + 1, f);
+    o[j] = 1.0 / (1.0 + exp(-excitation));
+  }
+  const double* v = p + (size_t)h * (f + 1);
+  double excitation = v[0] + inner(o, v + 1, h);
+  double out = (family == ORC_MLP_CE) ? 1.0 / (1.0 + exp(-excitation)) : excitation;
+  double res = out - y;
+  double error = (family == ORC_MLP_CE) ? res : res * 1.0;
+  if (grad) {
+    for (int j = 0; j < h; ++j) {
+      double loss_derivative = error * v[j + 1];
+      double ej = loss_derivative * (o[j] * (1.0 - o[j]));
+      double* g = grad + (size_t)j * (f + 1);
+      g[0] = 1.0 * ej;
+      for (int i = 0; i < f; ++i) g[1 + i] = x[i] * ej;
+    }
+    double* g = grad + (size_t)h * (f + 1);
+    g[0] = 1.0 * error;
+    for (int j = 0; j < h; ++j) g[1 + j] = o[j] * error;
+  }
+  if (residual) *residual = res;
+  if (output) *output = out;
+  if (loss) *loss = (family == ORC_MLP_CE) ? logistic_ce(out, y) : res * res;
+}
+
 typedef struct eval_ctx { int family; const double* p; int n; int f; const double* d; double eps; } eval_ctx;
 
 /* ---------------------------------------------------------------------------------------------
@@ -257,6 +310,10 @@ static void loss_row(const void* vctx, const double* x, double y, int64_t i, dou
   if (c->family == ORC_LOGISTIC) {
     /* FFNeuralNetworkTrainer.loss: zero + network.forward(x).backward(y).loss, Trainer.scala:133-135 */
     acc[0] = acc[0] + logistic_ce(orc_model(ORC_LOGISTIC, c->p, c->n, x, c->f), y);
+  } else if (c->family == ORC_MLP_MSE || c->family == ORC_MLP_CE) {
+    double l;
+    mlp_backprop(c->family, c->p, c->n, x, c->f, y, NULL, NULL, &l, NULL);
+    acc[0] = acc[0] + l;
   } else {
     /* lossSum(sum, xy) = sum + loss(p, xy); loss = res*res/2, MSEFunction.scala:34,45-48 */
     double res = mse_residual(c->family, c->p, c->n, x, c->f, y);
@@ -276,6 +333,14 @@ double orc_apply(int family, const double* X, const double* y, int64_t m, int f,
  * ------------------------------------------------------------------------------------------- */
 double orc_jacobian_row(int family, const double* p, int n, const double* x, int f, double y, double* Jrow) {
   double df[ORC_MAXN];
+  if (family == ORC_MLP_MSE || family == ORC_MLP_CE) {
+    /* Neuron.jacobian = gradient / residual, or the gradient itself when residual is NaN or 0 (Neuron.scala:67-73);
+     * FFNeuralNetworkTrainer.backpropagateRow: AugmentedRow(jacobian, residual), Trainer.scala:127-131 */
+    double residual;
+    mlp_backprop(family, p, n, x, f, y, df, &residual, NULL, NULL);
+    for (int j = 0; j < n; ++j) Jrow[j] = (isnan(residual) || residual == 0.0) ? df[j] : df[j] / residual;
+    return residual;
+  }
   model_grad(family, p, n, x, f, df);
   if (family == ORC_LOGISTIC) {
     /* Neuron.propagateError / FFNeuralNetwork.propagateErrorsOuterLayer (CrossEntropy, one output):
@@ -326,7 +391,12 @@ static void grad_row(const void* vctx, const double* x, double y, int64_t i, dou
    * acc[0..n) = gradient sum, acc[n] = residual sum */
   const eval_ctx* c = (const eval_ctx*)vctx; (void)i;
   double J[ORC_MAXN];
-  if (c->family == ORC_LOGISTIC) {
+  if (c->family == ORC_MLP_MSE || c->family == ORC_MLP_CE) {
+    double residual;
+    mlp_backprop(c->family, c->p, c->n, x, c->f, y, J, &residual, NULL, NULL);
+    for (int j = 0; j < c->n; ++j) acc[j] = acc[j] + J[j];
+    acc[c->n] = acc[c->n] + residual;
+  } else if (c->family == ORC_LOGISTIC) {
     /* Neuron.gradient = (1 +: inputs) * error, error = output - target */
     double error = orc_model(ORC_LOGISTIC, c->p, c->n, x, c->f) - y;
     model_grad(ORC_LOGISTIC, c->p, c->n, x, c->f, J);

@@ -23,7 +23,11 @@ extern "C" {
 /* same numbering as include/scalaopt_cuda.h (kept separate on purpose: the oracle shares no code
  * with the product) */
 enum { ORC_LINEAR = 0, ORC_LINEAR_NOINT = 1, ORC_LOGISTIC = 2, ORC_EXPDECAY = 3, ORC_GAUSS = 4,
-       ORC_GAUSS_EXPBKG = 5, ORC_POLY = 6 };
+       ORC_GAUSS_EXPBKG = 5, ORC_POLY = 6,
+       /* FFNeuralNetwork(Vector(f, h, 1)) with logistic inner neurons (FFNeuralNetwork.scala:114-189, Neuron.scala:40-73):
+        * MSE loss + linear output / cross-entropy loss + logistic output; n = h (f + 1) + h + 1 weights in the
+        * reference's order (hidden neurons, then the output neuron; bias first) */
+       ORC_MLP_MSE = 7, ORC_MLP_CE = 8 };
 
 /* fold order: parts <= 1 -> strict left fold (SeqDataSet.aggregate, core/.../SeqDataSetConverter.scala:32-35);
  * parts = N > 1 -> N contiguous partitions [i*m/N, (i+1)*m/N) folded independently from the zero element and

@@ -191,6 +191,8 @@ int check_family(so_ctx* ctx, int family, int f, int n) {
   }
   if (f > SO_MAX_FEATURES) return fail(ctx, SO_EUNSUPPORTED, "f=%d exceeds SO_MAX_FEATURES=%d", f, SO_MAX_FEATURES);
   const int want = family_nparams(family, f, n);
+  if (family_is_mlp(family) && want < 0)
+    return fail(ctx, SO_EINVAL, "MLP family on f=%d inputs takes n = h (f + 2) + 1 weights for h >= 1 hidden neurons, got %d", f, n);
   if (n != want) return fail(ctx, SO_EINVAL, "family %d on f=%d inputs takes n=%d parameters, got %d", family, f, want, n);
   return SO_OK;
 }
@@ -239,8 +241,9 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
   for (int g = 0; g < G; ++g) {
     Device& dv = ctx->devs[g];
     const ShardMem& sm = ds->shards[g];
-    const size_t need_partials = scalar ? scalar_partials_needed(kind, n, k, dv.sm_count)
-                                        : wide_partials_needed(kind, family, n, ds->f, k, dv.sm_count);
+    const size_t need_partials = family_is_mlp(family) && !nll ? mlp_partials_needed(kind, n, dv.sm_count)
+                                 : scalar ? scalar_partials_needed(kind, n, k, dv.sm_count)
+                                          : wide_partials_needed(kind, family, n, ds->f, k, dv.sm_count);
     int rc = ensure_workspace(ctx, dv, need_partials, (size_t)Q + 2);
     if (rc) return rc;
     SO_CUDA(ctx, cudaSetDevice(dv.id));
@@ -258,6 +261,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
         sh.out_doubles = (size_t)per;
       }
       rc = nll ? launch_nll(sh, nll->pdf, p, n, nll->consts, nll->nconsts)
+               : family_is_mlp(family) ? launch_mlp(kind, sh, family, p, n, want_grad)
                : scalar ? launch_scalar(kind, sh, family, p, d, n, alpha, k, want_grad)
                         : launch_wide(kind, sh, family, p, d, n, alpha, k, want_grad);
       if (rc < 0) {
@@ -710,6 +714,23 @@ extern "C" int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_d
 // =================================================================================================
 // Evaluation
 // =================================================================================================
+// loss and gradient at x with the context mutex already held (used by the composed MLP evaluations below)
+static int loss_grad_unlocked(so_dataset* ds, int family, const double* x, int n, double* loss, double* grad, so_call_stats* acc) {
+  so_ctx* ctx = ds->ctx;
+  const int Q = grad ? 1 + n : 1;
+  std::vector<double> res;
+  int rc = run_eval(ds, kLossGrad, family, x, nullptr, n, nullptr, 0, grad ? 1 : 0, Q, res);
+  if (rc) return rc;
+  const double m = res[Q];
+  *loss = res[0] / m;
+  if (grad) for (int i = 0; i < n; ++i) grad[i] = res[1 + i] / m;
+  if (acc) {
+    acc->kernel_ms += ctx->stats.kernel_ms; acc->device_ms += ctx->stats.device_ms; acc->launches += ctx->stats.launches;
+    acc->rows += ctx->stats.rows; acc->bytes += ctx->stats.bytes;
+  }
+  return SO_OK;
+}
+
 extern "C" int so_eval_loss_grad(so_dataset* ds, int family, const double* p, int n, double* loss, double* grad) {
   if (!ds || !p || !loss) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
@@ -795,6 +816,23 @@ extern "C" int so_eval_line(so_dataset* ds, int family, const double* p, const d
   int rc = check_family(ctx, family, ds->f, n);
   if (rc) return rc;
   if (k < 1 || k > SO_MAX_ALPHAS) return fail(ctx, SO_EINVAL, "so_eval_line: k=%d outside [1, %d]", k, SO_MAX_ALPHAS);
+  if (family_is_mlp(family)) {
+    // LineSearchPoint.fx / dfx as the reference evaluates them: f(x + a d) and gradient(x + a d) . d (Point.scala:54-57),
+    // one fused loss+gradient launch per step size
+    so_call_stats acc{};
+    std::vector<double> x(n), g(n);
+    for (int j = 0; j < k; ++j) {
+      for (int i = 0; i < n; ++i) x[i] = p[i] + d[i] * alpha[j];
+      rc = loss_grad_unlocked(ds, family, x.data(), n, &phi[j], g.data(), &acc);
+      if (rc) return rc;
+      double s2 = 0.0;
+      for (int i = 0; i < n; ++i) s2 += g[i] * d[i];
+      dphi[j] = s2;
+    }
+    ctx->stats.kernel_ms = acc.kernel_ms; ctx->stats.device_ms = acc.device_ms; ctx->stats.launches = acc.launches;
+    ctx->stats.rows = acc.rows; ctx->stats.bytes = acc.bytes;
+    return SO_OK;
+  }
   const bool scalar = family_is_scalar_t(family);
   // one pass scores up to `chunk` step sizes; longer schedules take ceil(k/chunk) passes
   const int chunk = 8;
@@ -835,6 +873,22 @@ extern "C" int so_eval_hess_vec(so_dataset* ds, int family, const double* p, con
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_family(ctx, family, ds->f, n);
   if (rc) return rc;
+  if (family_is_mlp(family)) {
+    // FFNeuralNetworkTrainer.dirHessian: (gradient(w + d * eps) - gradient(w)) / eps, eps = 1e-8 (Trainer.scala:46,76-80)
+    const double eps = 1.0e-8;
+    so_call_stats acc{};
+    std::vector<double> x(n), g0(n), g1(n);
+    double l0 = 0.0, l1 = 0.0;
+    rc = loss_grad_unlocked(ds, family, p, n, &l0, g0.data(), &acc);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) x[i] = p[i] + d[i] * eps;
+    rc = loss_grad_unlocked(ds, family, x.data(), n, &l1, g1.data(), &acc);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) Hd[i] = (g1[i] - g0[i]) / eps;
+    ctx->stats.kernel_ms = acc.kernel_ms; ctx->stats.device_ms = acc.device_ms; ctx->stats.launches = acc.launches;
+    ctx->stats.rows = acc.rows; ctx->stats.bytes = acc.bytes;
+    return SO_OK;
+  }
   std::vector<double> res;
   rc = run_eval(ds, kHessVec, family, p, d, n, nullptr, 0, 0, n, res);
   if (rc) return rc;

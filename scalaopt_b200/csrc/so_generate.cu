@@ -75,6 +75,7 @@ __global__ void k_gen_outputs(const double* __restrict__ X, double* __restrict__
 int launch_generate(const Shard& s, double* X, double* y, int family, const double* p_true, int n, uint64_t seed,
                     double noise_sigma, int64_t row_offset, int64_t total_rows) {
   if (s.rows == 0) return 0;
+  if (family_is_mlp(family)) return SO_EUNSUPPORTED;      // no synthetic generator for the MLP families
   if (n < 1 || n > SO_MAX_FEATURES + 1) return SO_EINVAL;
   GenParams prm;
   for (int i = 0; i < n; ++i) prm.p[i] = p_true[i];

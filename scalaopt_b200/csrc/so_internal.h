@@ -55,6 +55,11 @@ int launch_scalar(Kind kind, const Shard& s, int family, const double* p, const 
 int launch_wide(Kind kind, const Shard& s, int family, const double* p, const double* d, int n,
                 const double* alpha, int k, int want_grad);
 
+// FFNeuralNetwork(Vector(f, h, 1)) families (so_mlp.cu): kLossGrad and kNormalEq
+int launch_mlp(Kind kind, const Shard& s, int family, const double* p, int n, int want_grad);
+int mlp_hidden_units(int f, int n);      // h from n = h (f + 2) + 1, or -1
+size_t mlp_partials_needed(Kind kind, int n, int sm_count);
+
 // sum_i -2 log pdf(p, x_i) -> out[0]; reads the X stream only
 int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* consts, int nconsts);
 
@@ -77,8 +82,10 @@ inline int family_nparams(int family, int f, int n_hint) {
     case SO_FAMILY_GAUSS: return 3;
     case SO_FAMILY_GAUSS_EXPBKG: return 5;
     case SO_FAMILY_POLY: return n_hint;
+    case SO_FAMILY_MLP_MSE: case SO_FAMILY_MLP_CE: return (n_hint >= f + 3 && (n_hint - 1) % (f + 2) == 0) ? n_hint : -1;
   }
   return -1;
 }
+inline bool family_is_mlp(int family) { return family == SO_FAMILY_MLP_MSE || family == SO_FAMILY_MLP_CE; }
 
 }  // namespace so

@@ -162,7 +162,10 @@ class GpuMSEFunction : public MSEFunction {
     double rtr = 0.0;
     check(so_eval_normal_eq(data->ds, family, p.data(), n, JtJ.data(), Jtr.data(), &rtr));
     counters.k2_passes++;
-    if (family != SO_FAMILY_LOGISTIC) { int64_t m = data->size(); remember(p, rtr / (2.0 * (double)m), nullptr); }
+    // the loss at p comes for free: sum r^2 / (2m) for the MSE families; FFNeuralNetwork's MSE loss is not halved
+    // (FFNeuralNetwork.scala:70-72); the cross-entropy families' loss is not a function of r^T r
+    if (family == SO_FAMILY_MLP_MSE) { int64_t m = data->size(); remember(p, rtr / (double)m, nullptr); }
+    else if (family != SO_FAMILY_LOGISTIC && family != SO_FAMILY_MLP_CE) { int64_t m = data->size(); remember(p, rtr / (2.0 * (double)m), nullptr); }
     // Cholesky JtJ = R^T R (upper R), q = R^-T Jtr, rho = sqrt(max(0, rtr - q.q)); O(n^3) on the host
     std::vector<Vec> R(n, Vec(n, 0.0));
     Vec q(n, 0.0);

@@ -14,9 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscalaopt_cuda.so")
 
-LINEAR, LINEAR_NOINT, LOGISTIC, EXPDECAY, GAUSS, GAUSS_EXPBKG, POLY = range(7)
+LINEAR, LINEAR_NOINT, LOGISTIC, EXPDECAY, GAUSS, GAUSS_EXPBKG, POLY, MLP_MSE, MLP_CE = range(9)
 FAMILY_NAMES = {LINEAR: "linear", LINEAR_NOINT: "linear_noint", LOGISTIC: "logistic", EXPDECAY: "expdecay",
-                GAUSS: "gauss", GAUSS_EXPBKG: "gauss_expbkg", POLY: "poly"}
+                GAUSS: "gauss", GAUSS_EXPBKG: "gauss_expbkg", POLY: "poly", MLP_MSE: "mlp_mse", MLP_CE: "mlp_ce"}
 PDF_GAUSS_EXPBKG = 0
 MAX_ALPHAS = 32
 NCCL_UID_BYTES = 128

@@ -137,3 +137,27 @@ def test_faithful_lm_pass_model_runs(oracle):
     _, _, rtr = oracle.normal_eq(fam, X, y, truth * 1.1)
     assert b1 == pytest.approx(np.sqrt(rtr), rel=1e-12)
     assert b4 == pytest.approx(b1, rel=1e-12)
+
+
+def test_mlp_restatement_reproduces_the_trainer_spec_properties(oracle):
+    """FFNeuralNetworkTrainerSpec.scala:38-117: on Vector(2, 2, 1) the back-propagated gradient equals the finite
+    difference gradient of a SimpleMSEFunction (loss r^2/2) for the MSE loss, and of the trainer's own apply for the
+    cross-entropy loss, to 1e-5; the Jacobian rows times the residual give the gradient rows back (Neuron.scala:65-73)."""
+    rng = np.random.default_rng(1)
+    m, f, h = 400, 2, 2
+    X = rng.standard_normal((m, f))
+    w = rng.uniform(-1.0, 1.0, h * (f + 1) + h + 1)
+    y = rng.standard_normal(m)
+    g = oracle.gradient(oracle.MLP_MSE, X, y, w)
+    fd = oracle.gradient_fd(oracle.MLP_MSE, X, y, w)          # FD of the trainer's apply = sum r^2 / m (not halved)
+    np.testing.assert_allclose(g, 0.5 * fd, atol=1e-5)
+    yc = (rng.random(m) < 0.5).astype(float)
+    gc = oracle.gradient(oracle.MLP_CE, X, yc, w)
+    np.testing.assert_allclose(gc, oracle.gradient_fd(oracle.MLP_CE, X, yc, w), atol=1e-5)
+    for fam, yy in ((oracle.MLP_MSE, y), (oracle.MLP_CE, yc)):
+        J = oracle.jacobian_matrix(fam, X, yy, w)
+        np.testing.assert_allclose((J[:, :-1] * J[:, -1:]).sum(axis=0) / m, oracle.gradient(fam, X, yy, w), rtol=1e-12)
+    # the network function itself: logistic inner neurons, linear output
+    e = w[:6].reshape(2, 3)
+    o = 1.0 / (1.0 + np.exp(-(e[:, 0] + X[0] @ e[:, 1:].T)))
+    assert oracle.model(oracle.MLP_MSE, w, X[0]) == pytest.approx(w[6] + o @ w[7:], rel=1e-14)
