@@ -315,6 +315,30 @@ def run_own(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6650 GB/s)"
         alg_bytes = 16.0 * m                                   # per launch: one GPU's shard, 16 B per observation
         ach = alg_bytes / (kernel_ms_max / args.steps * 1e-3) / 1e9
+        # DRAM bytes of one launch from the committed `ncu --set full` capture (only if it was taken at this launch size)
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
+            if int(tr["rows_per_launch"]) == int(m):
+                traffic = float(tr["dram_read_bytes"]) + float(tr["dram_write_bytes"])
+                traffic_src = tr["source"]
+        except Exception:
+            pass
+        # north_star's roofline is the SLOWER of bytes at HBM bandwidth and flops at FP64 peak; this kernel executes 47 FP64
+        # instructions per observation (SASS of k_scalar<OpNormalEq<FamGaussExpBkg>>), which at the DFMA
+        # rate measured on this pool (profiles/r1_fp64_peak.json) takes longer than its 16 bytes at the HBM rate
+        fp64 = None
+        try:
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_peak.json")))
+            dfma_per_s = float(pk["dfma_tflops_burst"]) * 1e12 / 2.0
+            instr = 47.0 * m
+            bound_ms = instr / dfma_per_s * 1e3
+            fp64 = {"fp64_instr_per_observation": 47, "dfma_peak_instr_per_s": dfma_per_s, "bound_ms_per_launch": bound_ms,
+                    "hbm_bound_ms_per_launch": alg_bytes / (hbm_peak * 1e9) * 1e3,
+                    "frac_of_fp64_bound": bound_ms / (kernel_ms_max / args.steps),
+                    "note": "explanatory only; roofline.frac above is against HBM"}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True,
@@ -322,8 +346,9 @@ def run_own(args):
             "config": workload_config(args, world),
             "device_ms_per_step": device_ms / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_scalar<OpNormalEq<FamGaussExpBkg>>", "algorithmic_bytes_per_launch": alg_bytes},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "k_scalar<OpNormalEq<FamGaussExpBkg>>", "algorithmic_bytes_per_launch": alg_bytes,
+                         "fp64": fp64},
             "clocks": clocks, "gpu_launches": int(launches),
         }
         if e2e is not None:
