@@ -95,5 +95,33 @@ JNIEXPORT jint JNICALL JFN(datasetGenerate)(JNIEnv* e, jobject o, jlong ds, jint
   (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
   return rc;
 }
+JNIEXPORT jint JNICALL JFN(evalQr)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray out) {
+  jsize n = (*e)->GetArrayLength(e, p);                  /* out: (n+1)*(n+1) doubles, the R factor of [J | r] */
+  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  int rc = so_eval_qr((so_dataset*)(intptr_t)ds, fam, pp, n, po);
+  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jint JNICALL JFN(evalNll)(JNIEnv* e, jobject o, jlong ds, jint pdf, jdoubleArray p, jdoubleArray consts, jdoubleArray out) {
+  jsize n = (*e)->GetArrayLength(e, p), nc = (*e)->GetArrayLength(e, consts);
+  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  double* pc = (*e)->GetPrimitiveArrayCritical(e, consts, 0);
+  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  int rc = so_eval_nll((so_dataset*)(intptr_t)ds, pdf, pp, n, pc, nc, po);
+  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
+  (*e)->ReleasePrimitiveArrayCritical(e, consts, pc, JNI_ABORT);
+  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jint JNICALL JFN(datasetLoadRaw)(JNIEnv* e, jobject o, jlong ds, jstring xPath, jstring yPath, jlong rows, jlong fileRowOffset) {
+  const char* xp = (*e)->GetStringUTFChars(e, xPath, 0);
+  const char* yp = (*e)->GetStringUTFChars(e, yPath, 0);
+  int rc = so_dataset_load_raw((so_dataset*)(intptr_t)ds, xp, yp, rows, fileRowOffset);
+  (*e)->ReleaseStringUTFChars(e, yPath, yp);
+  (*e)->ReleaseStringUTFChars(e, xPath, xp);
+  return rc;
+}
 #endif
 #endif

@@ -24,7 +24,13 @@ object NativeLib {
   /** out = (phi_0..phi_{k-1}, dphi_0..dphi_{k-1}) */
   @native def evalLine(ds: Long, family: Int, p: Array[Double], d: Array[Double], alpha: Array[Double], out: Array[Double]): Int
   @native def evalHessVec(ds: Long, family: Int, p: Array[Double], d: Array[Double], out: Array[Double]): Int
+  /** out: (n+1)*(n+1) doubles, row-major upper triangular R factor of [J | r] (so_eval_qr: on-device Householder TSQR) */
+  @native def evalQr(ds: Long, family: Int, p: Array[Double], out: Array[Double]): Int
+  /** out(0) = sum -2 log pdf(p, x_i) (stats/package.scala:97-103) */
+  @native def evalNll(ds: Long, pdf: Int, p: Array[Double], consts: Array[Double], out: Array[Double]): Int
+  @native def datasetLoadRaw(ds: Long, xPath: String, yPath: String, rows: Long, fileRowOffset: Long): Int
 
   val Linear = 0; val LinearNoIntercept = 1; val Logistic = 2; val ExpDecay = 3
-  val Gauss = 4; val GaussExpBkg = 5; val Poly = 6
+  val Gauss = 4; val GaussExpBkg = 5; val Poly = 6; val MlpMse = 7; val MlpCe = 8
+  val PdfGaussExpBkg = 0
 }
