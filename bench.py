@@ -278,6 +278,9 @@ def run_own(args):
         try:
             from scalaopt_b200 import host as sohost
             lm = sohost.bench_lm(ctx, ds, fam, TRUTH * 1.1, barrier, max_over_ranks)
+            # the same fit with one K1 loss pass per trial point + one K2 pass per outer iteration (no speculation)
+            plain = sohost.bench_lm(ctx, ds, fam, TRUTH * 1.1, barrier, max_over_ranks, speculate=False)
+            lm["without_speculation"] = {k: plain[k] for k in ("seconds", "iterations", "iterations_per_s", "k2_passes", "k1_passes")}
         except Exception as e:  # the evaluation numbers stand on their own
             lm = {"unavailable": f"{type(e).__name__}: {e}"}
 

@@ -58,6 +58,7 @@ typedef struct soh_counters {
   int64_t loss_calls, gradient_calls, dirder_calls, hessvec_calls, jacobian_calls;
   int64_t k1_passes, k2_passes, k3_passes, k4_passes;
   int64_t cache_hits, line_hits;
+  int64_t spec_passes, spec_hits;   /* speculative K2 passes at LM trial points, Jacobians served from them */
 } soh_counters;
 
 typedef struct soh_objective soh_objective;
@@ -83,6 +84,10 @@ soh_objective* soh_objective_gpu(so_ctx* ctx, so_dataset* ds, int f, int family,
  * instead of so_eval_normal_eq + Cholesky: one pass either way, about 2.5x the kernel time at n = 5, and the condition
  * number of J is not squared.  Single-input families. */
 int soh_objective_use_tsqr(soh_objective* objective, int on);
+
+/* Levenberg-Marquardt trial-point losses from a K2 pass whose sums are kept for the Jacobian request that follows an
+ * accepted step (default on; off = one K1 loss pass per trial point + one K2 pass per outer iteration). */
+int soh_objective_speculate(soh_objective* objective, int on);
 
 /* negLogLikelihood(pdf, GpuDataSet(ds)) _ (std-apps/.../stats/package.scala:97-103) with finite-difference derivatives
  * (what the reference's implicit `toFunctionWoGradient` gives a plain closure, core/.../package.scala:74-77). */

@@ -149,6 +149,10 @@ int setup_device(so_ctx* ctx, Device& d) {
 
 int ensure_workspace(so_ctx* ctx, Device& d, size_t partials, size_t out) {
   SO_CUDA(ctx, cudaSetDevice(d.id));
+  // some kernels reduce more accumulators than they emit (K4: two sets of n, folded on the way out): never size
+  // the result buffer below what any catalogue kernel's block reduction needs
+  out = std::max<size_t>(out, 2048);
+  partials = std::max<size_t>(partials, (size_t)d.sm_count * 8 * 64);
   if (partials > d.partials_cap) {
     if (d.partials) cudaFree(d.partials);
     d.partials = nullptr; d.partials_cap = 0;

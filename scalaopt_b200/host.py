@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libscalaopt_host.so")
 LEVENBERG_MARQUARDT, BFGS, CONJUGATE_GRADIENT, NEWTON_CG, STEIHAUG_CG, NELDER_MEAD = range(6)
 OK, MAX_ITER, ILLEGAL_ARG, GPU_ERROR, ERROR = range(5)
 
-EXPORTS = ["soh_default_config", "soh_objective_from_callbacks", "soh_objective_gpu", "soh_objective_use_tsqr", "soh_objective_gpu_nll", "soh_objective_free",
+EXPORTS = ["soh_default_config", "soh_objective_from_callbacks", "soh_objective_gpu", "soh_objective_use_tsqr", "soh_objective_speculate", "soh_objective_gpu_nll", "soh_objective_free",
            "soh_objective_counters", "soh_objective_apply", "soh_objective_gradient", "soh_objective_dirder",
            "soh_objective_dir_hessian", "soh_objective_jacobian_rows", "soh_minimize", "soh_zoom_step_length",
            "soh_qr", "soh_last_error"]
@@ -55,7 +55,7 @@ class Result(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("loss_calls", "gradient_calls", "dirder_calls", "hessvec_calls",
                                          "jacobian_calls", "k1_passes", "k2_passes", "k3_passes", "k4_passes",
-                                         "cache_hits", "line_hits")]
+                                         "cache_hits", "line_hits", "spec_passes", "spec_hits")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -85,6 +85,7 @@ def load():
     L.soh_objective_gpu.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.soh_objective_gpu.restype = vp
     L.soh_objective_use_tsqr.argtypes = [vp, C.c_int]
+    L.soh_objective_speculate.argtypes = [vp, C.c_int]
     L.soh_objective_gpu_nll.argtypes = [vp, vp, C.c_int, C.c_int, _dp, C.c_int]
     L.soh_objective_gpu_nll.restype = vp
     L.soh_objective_free.argtypes = [vp]
@@ -162,9 +163,12 @@ class Objective:
         return cls(h, n, keepalive=cbs)
 
     @classmethod
-    def gpu(cls, ctx: native.Context, ds: native.Dataset, family: int, n: int, tsqr: bool = False):
-        """GpuMSEFunction(family, GpuDataSet(ds)); tsqr=True: Jacobian system from so_eval_qr instead of K2 + Cholesky"""
+    def gpu(cls, ctx: native.Context, ds: native.Dataset, family: int, n: int, tsqr: bool = False, speculate: bool = True):
+        """GpuMSEFunction(family, GpuDataSet(ds)); tsqr=True: Jacobian system from so_eval_qr instead of K2 + Cholesky;
+        speculate=False: LM trial-point losses from K1 loss passes instead of speculative K2 passes"""
         h = load().soh_objective_gpu(ctx._h, ds._h, ds.f, family, n)
+        if not speculate:
+            load().soh_objective_speculate(h, 0)
         if tsqr and load().soh_objective_use_tsqr(h, 1) != 0:
             raise RuntimeError(load().soh_last_error().decode())
         return cls(h, n, keepalive=(ctx, ds))
@@ -264,13 +268,13 @@ def qr(ab, n, pivoting=True):
     return {"R": R, "qtb": qtb, "ipvt": ipvt, "acNorms": acn, "bNorm": bn.value, "solution": sol}
 
 
-def bench_lm(ctx, ds, family, x0, barrier=lambda: None, max_over_ranks=lambda v: v, repeats=3):
+def bench_lm(ctx, ds, family, x0, barrier=lambda: None, max_over_ranks=lambda v: v, repeats=3, speculate=True):
     """LevenbergMarquardt.minimize over the resident data set: iterations/s (one iteration = one pass through
     `iterate`, LevenbergMarquardt.scala:118-150 = one normal-equation evaluation + >= 1 loss evaluation + lmPar)."""
     x0 = _vec(x0)
     best = None
     for _ in range(repeats):
-        f = Objective.gpu(ctx, ds, family, x0.size)
+        f = Objective.gpu(ctx, ds, family, x0.size, speculate=speculate)
         barrier()
         t0 = time.perf_counter()
         x, res = minimize(LEVENBERG_MARQUARDT, f, x0)
@@ -281,5 +285,6 @@ def bench_lm(ctx, ds, family, x0, barrier=lambda: None, max_over_ranks=lambda v:
         if best is None or dt < best["seconds"]:
             best = {"seconds": dt, "iterations": int(res.iterations), "inner_iterations": int(res.inner_iterations),
                     "iterations_per_s": res.iterations / dt, "minimiser": [float(v) for v in x],
-                    "k2_passes": cnt["k2_passes"], "k1_passes": cnt["k1_passes"]}
+                    "k2_passes": cnt["k2_passes"], "k1_passes": cnt["k1_passes"], "spec_hits": cnt["spec_hits"],
+                    "speculate": bool(speculate)}
     return best

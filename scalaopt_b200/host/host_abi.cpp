@@ -114,6 +114,13 @@ extern "C" int soh_objective_use_tsqr(soh_objective* o, int on) {
   return SOH_OK;
 }
 
+extern "C" int soh_objective_speculate(soh_objective* o, int on) {
+  auto* g = o ? dynamic_cast<GpuMSEFunction*>(o->fn.get()) : nullptr;
+  if (!g) { g_err = "soh_objective_speculate: not a GPU least-squares objective"; return SOH_ILLEGAL_ARG; }
+  g->speculate = on != 0;
+  return SOH_OK;
+}
+
 extern "C" soh_objective* soh_objective_gpu_nll(so_ctx* ctx, so_dataset* ds, int pdf, int n, const double* consts, int nconsts) {
   if (!ctx || !ds || n < 1 || (nconsts > 0 && !consts)) { g_err = "soh_objective_gpu_nll: bad arguments"; return nullptr; }
   auto data = std::make_shared<GpuDataSet>(ctx, ds, 1, false);
@@ -130,7 +137,8 @@ extern "C" int soh_objective_counters(soh_objective* f, soh_counters* out) {
   if (!f || !out) return SOH_ILLEGAL_ARG;
   const GpuCounters& c = *f->counters;
   *out = soh_counters{c.loss_calls, c.gradient_calls, c.dirder_calls, c.hessvec_calls, c.jacobian_calls,
-                      c.k1_passes, c.k2_passes, c.k3_passes, c.k4_passes, c.cache_hits, c.line_hits};
+                      c.k1_passes, c.k2_passes, c.k3_passes, c.k4_passes, c.cache_hits, c.line_hits,
+                      c.spec_passes, c.spec_hits};
   return SOH_OK;
 }
 

@@ -16,10 +16,10 @@ def host():
     return h
 
 
-def _gpu(native, host, ctx, fam, X, y, n, tsqr=False):
+def _gpu(native, host, ctx, fam, X, y, n, tsqr=False, speculate=True):
     X = np.asarray(X, float).reshape(len(y), -1)
     ds = native.Dataset(ctx, len(y), X.shape[1]).append(X, y)
-    return ds, host.Objective.gpu(ctx, ds, fam, n, tsqr=tsqr)
+    return ds, host.Objective.gpu(ctx, ds, fam, n, tsqr=tsqr, speculate=speculate)
 
 
 def test_gpu_objective_answers_the_objective_function_interface(native, oracle, host, gpu_ctx):
@@ -50,10 +50,12 @@ def test_gpu_objective_answers_the_objective_function_interface(native, oracle, 
 CASES = ["gauss_expbkg", "lm_spec_linear", "lm_spec_exponential", "expdecay_large", "poly"]
 
 
-@pytest.mark.parametrize("tsqr", [False, True])
+@pytest.mark.parametrize("mode", ["k2", "k2-speculative", "tsqr"])
 @pytest.mark.parametrize("case", CASES)
-def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu_ctx, case, tsqr):
-    """tsqr=False: K2 + Cholesky; tsqr=True: the (n+1)-row system is the R factor from so_eval_qr."""
+def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu_ctx, case, mode):
+    """k2: K2 + Cholesky, trial-point losses from K1; k2-speculative (the default): trial-point losses from K2 passes whose
+    sums serve the next Jacobian request; tsqr: the (n+1)-row system is the R factor from so_eval_qr."""
+    tsqr, speculate = mode == "tsqr", mode == "k2-speculative"
     if tsqr and case == "lm_spec_linear":
         pytest.skip("TSQR covers the single-input families")
     if case == "gauss_expbkg":         # BASELINE config 3 at oracle-sized m
@@ -75,7 +77,7 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
         fam, n = oracle.POLY, 4
         X, y = oracle.generate(fam, 50_000, 1, [1.0, -2.0, 0.5, 3.0], noise_sigma=0.1)
         start = np.array([0.0, 0.0, 0.0, 0.0])
-    ds, f_gpu = _gpu(native, host, gpu_ctx, fam, X, y, n, tsqr=tsqr)
+    ds, f_gpu = _gpu(native, host, gpu_ctx, fam, X, y, n, tsqr=tsqr, speculate=speculate)
     f_ref = oracle_objective(host, oracle, fam, X, y, n)
     x_gpu, r_gpu = host.minimize(host.LEVENBERG_MARQUARDT, f_gpu, start)
     x_ref, r_ref = host.minimize(host.LEVENBERG_MARQUARDT, f_ref, start)
@@ -83,8 +85,14 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
     assert r_gpu.inner_iterations == r_ref.inner_iterations
     np.testing.assert_allclose(x_gpu, x_ref, rtol=1e-8, atol=1e-8)
     c = f_gpu.counters()
-    assert c["k2_passes"] == r_gpu.iterations            # one normal-equation pass per outer iteration
-    assert c["k1_passes"] == r_gpu.inner_iterations      # one loss pass per trial point
+    if speculate:
+        # every trial point is a K2 pass; an accepted step's Jacobian request is served from it: no K1 pass at all
+        assert c["k1_passes"] == 0 and c["spec_passes"] == r_gpu.inner_iterations
+        assert c["k2_passes"] + c["spec_hits"] == r_gpu.iterations + r_gpu.inner_iterations
+        assert c["spec_hits"] >= min(1, r_gpu.iterations - 1)
+    else:
+        assert c["k2_passes"] == r_gpu.iterations            # one normal-equation pass per outer iteration
+        assert c["k1_passes"] == r_gpu.inner_iterations      # one loss pass per trial point
     f_gpu.free(); ds.free()
 
 
