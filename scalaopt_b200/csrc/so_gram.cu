@@ -16,7 +16,6 @@
 //   larger n    warp-specialised shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_ws below), f <= 512
 #include <algorithm>
 #include <vector>
-#include <cstdlib>
 
 #include "so_wide.cuh"
 
@@ -736,10 +735,8 @@ inline WsPlan ws_plan(int f, int sm_count) {
   const size_t W = (size_t)8 * b.T, PW = W + 4;
   const size_t fixed = sizeof(double) * (W + (2 + kWsMaxStages) * kWsMaxRows), budget = 227 * 1024 - 4096;   // static shared: exp table, flags
   b.stages = 2;
-  if (const char* e = getenv("SO_WS_STAGES")) b.stages = atoi(e);
   int krows = (int)((budget - fixed) / (sizeof(double) * b.stages * PW));
   krows = std::min(kWsMaxRows, krows) & ~3;
-  if (const char* e = getenv("SO_WS_KROWS")) krows = std::min(krows, atoi(e));
   b.krows = krows;
   b.QE = 4;
   b.smem = fixed + sizeof(double) * b.stages * (size_t)std::max(krows, 0) * PW;

@@ -105,7 +105,10 @@ class GpuMSEFunction : public MSEFunction {
   // Jacobian system at that same point next (LevenbergMarquardt.scala:124,164).  With `speculate` the trial-point loss
   // is taken from a K2 pass (loss = r^T r / 2m) whose J^T J, J^T r are kept: an accepted step costs one pass over the
   // data instead of two (K1 loss 2.6 ms + K2 3.9 ms -> K2 3.9 ms at 1e9 rows); a rejected one costs K2 instead of K1.
+  // Only the FIRST trial point after a Jacobian is speculated on (later ones follow a rejection and are mostly
+  // rejected again), and only where a K2 pass costs about what a K1 pass costs (n <= 16: the Gram is HBM-bound).
   bool speculate = true;
+  static constexpr int kSpeculateMaxN = 16;
   mutable GpuCounters counters;
   GpuMSEFunction(std::shared_ptr<GpuDataSet> d, int family_, int n_) : data(std::move(d)), family(family_), n(n_) {}
 
@@ -115,7 +118,7 @@ class GpuMSEFunction : public MSEFunction {
     if (const Entry* e = find(x)) { counters.cache_hits++; return e->loss; }
     if (const LineEntry* le = find_on_ray(x)) { counters.line_hits++; return le->phi; }
     if (on_ray_beta(x)) return score_ray(x).phi;
-    if (loss_only_mode && speculate && !use_tsqr && loss_scale() > 0.0) {
+    if (loss_only_mode && speculate && !use_tsqr && loss_scale() > 0.0 && n <= kSpeculateMaxN && trials_since_jacobian++ == 0) {
       spec.JtJ.assign((size_t)n * n, 0.0); spec.Jtr.assign(n, 0.0);
       check(so_eval_normal_eq(data->ds, family, x.data(), n, spec.JtJ.data(), spec.Jtr.data(), &spec.rtr));
       spec.x = x; spec.valid = true;
@@ -160,6 +163,7 @@ class GpuMSEFunction : public MSEFunction {
   std::shared_ptr<DataSet<AugmentedRow>> jacobianAndResidualsMatrix(const Vec& p) const override {
     counters.jacobian_calls++;
     loss_only_mode = true;          // Levenberg-Marquardt only ever asks for the loss between Jacobians
+    trials_since_jacobian = 0;
     if (use_tsqr) {
       // the rows of the R factor of [J | r] ARE the (n+1)-row system; no Gram matrix, no Cholesky
       std::vector<double> Rf((size_t)(n + 1) * (n + 1));
@@ -215,6 +219,7 @@ class GpuMSEFunction : public MSEFunction {
   struct Entry { Vec x; double loss; bool has_grad; Vec grad; };
   struct Spec { bool valid = false; Vec x; std::vector<double> JtJ, Jtr; double rtr = 0.0; };
   mutable Spec spec;
+  mutable int trials_since_jacobian = 0;
   // loss = loss_scale * r^T r / m where the loss is a function of r^T r (0: it is not)
   double loss_scale() const {
     if (family == SO_FAMILY_MLP_MSE) return 1.0;                  // FFNeuralNetwork.scala:70-72, not halved

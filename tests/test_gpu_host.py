@@ -86,10 +86,11 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
     np.testing.assert_allclose(x_gpu, x_ref, rtol=1e-8, atol=1e-8)
     c = f_gpu.counters()
     if speculate:
-        # every trial point is a K2 pass; an accepted step's Jacobian request is served from it: no K1 pass at all
-        assert c["k1_passes"] == 0 and c["spec_passes"] == r_gpu.inner_iterations
-        assert c["k2_passes"] + c["spec_hits"] == r_gpu.iterations + r_gpu.inner_iterations
-        assert c["spec_hits"] >= min(1, r_gpu.iterations - 1)
+        # the first trial point after each Jacobian is a K2 pass (n <= 16); an accepted step's Jacobian request is served
+        # from it; later trial points of the same outer iteration are plain K1 loss passes
+        assert c["k1_passes"] + c["spec_passes"] == r_gpu.inner_iterations
+        assert c["k2_passes"] + c["spec_hits"] == r_gpu.iterations + c["spec_passes"]
+        assert c["spec_passes"] == r_gpu.iterations and c["spec_hits"] >= min(1, r_gpu.iterations - 1)
     else:
         assert c["k2_passes"] == r_gpu.iterations            # one normal-equation pass per outer iteration
         assert c["k1_passes"] == r_gpu.inner_iterations      # one loss pass per trial point

@@ -49,6 +49,8 @@ def run_family(ctx, name, fam, m, f, truth, sigma, kinds, flops_gram=None):
             fn = lambda: ds.loss_grad(fam, p, want_grad=False)
         elif kind == "K2":
             fn = lambda: ds.normal_eq(fam, p)
+        elif kind == "TSQR":
+            fn = lambda: ds.qr(fam, p)
         elif kind.startswith("K3"):
             k = int(kind.split("k=")[1])
             al = [0.0, 1.0, 2.0, 4.0, 8.0, 0.5, 0.25, 0.125][:k]
@@ -71,7 +73,10 @@ def main():
         if "cfg3" in which:
             truth = [2.0, 0.5, 0.05, 1.0, 3.0]
             ds = run_family(ctx, "cfg3 gauss_expbkg 1e9", native.GAUSS_EXPBKG, 1_000_000_000, 1, truth, 0.05,
-                            ["K2", "K1", "K1loss", "K3 k=1", "K3 k=2", "K3 k=4", "K4"])
+                            ["K2", "TSQR", "K1", "K1loss", "K3 k=1", "K3 k=2", "K3 k=4", "K4"])
+            for spec in (True, False):
+                lm = host.bench_lm(ctx, ds, native.GAUSS_EXPBKG, np.array(truth) * 1.1, speculate=spec)
+                report(config="cfg3 LevenbergMarquardt gauss_expbkg 1e9", **lm)
             ds.free()
             ds = run_family(ctx, "cfg3b expdecay 1e9", native.EXPDECAY, 1_000_000_000, 1, [2.0, -1.3], 0.1, ["K2", "K1", "K4"])
             ds.free()
@@ -107,7 +112,10 @@ def main():
             report(config="cfg4 Newton-CG linear 1e7x256", iterations=int(res.iterations), seconds=dt,
                    iterations_per_s=res.iterations / dt, max_abs_err_vs_truth=float(np.abs(x - truth).max()),
                    counters=fobj.counters())
-            fobj.free(); ds.free()
+            fobj.free()
+            lm = host.bench_lm(ctx, ds, native.LINEAR_NOINT, np.zeros(f), repeats=1)
+            report(config="cfg4 LevenbergMarquardt linear 1e7x256 (compute-bound Gram)", **{k: v for k, v in lm.items() if k != "minimiser"})
+            ds.free()
         if "cfg5" in which:
             for n, m in ((4, 1_000_000_000), (4, 100_000_000), (4, 1_000_000), (32, 100_000_000), (32, 1_000_000),
                          (128, 100_000_000), (128, 1_000_000)):
