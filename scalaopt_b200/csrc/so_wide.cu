@@ -157,6 +157,80 @@ int launch_lcv(const Shard& s, const Params& P, int want_grad) {
   return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// n <= 8: one thread per observation (K1 and K4).  With 8-72 bytes per row the lanes-per-row mapping above
+// spends its time in shuffles (n = 4: 0.69 of the HBM roofline); a thread that keeps its whole row and n + 1
+// accumulators in registers streams at the rate of k_gram_small (>= 1.0).
+// ---------------------------------------------------------------------------------------------------
+template <int FAM, int NP, int ICPT, int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+k_small(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+        int want_grad, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+  constexpr int F = NP - ICPT, Q = (MODE == kModeLossGrad) ? NP + 1 : NP, base = (MODE == kModeLossGrad) ? 1 : 0;
+  __shared__ double s_red[kWarps * Q];
+  __shared__ double s_scale[Q];
+  if (FAM == kLogistic) exp_table_init();
+  for (int q = threadIdx.x; q < Q; q += kThreads) s_scale[q] = (MODE == kModeLossGrad && q == 0) ? P.scale0 : 1.0;
+  __syncthreads();
+  double acc[Q], p[NP], d[NP];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { p[i] = P.p[i]; d[i] = P.d[i]; }
+  for (int64_t row = (int64_t)blockIdx.x * kThreads + threadIdx.x; row < rows; row += (int64_t)gridDim.x * kThreads) {
+    double xt[NP];
+    if (ICPT) xt[0] = 1.0;
+#pragma unroll
+    for (int j = 0; j < F; ++j) xt[ICPT + j] = ld_stream(X + row * F + j);
+    double z = 0.0;
+#pragma unroll
+    for (int j = 0; j < F; ++j) z = fma(p[ICPT + j], xt[ICPT + j], z);
+    if (ICPT) z += p[0];
+    double w;
+    if (MODE == kModeLossGrad) {
+      const double yv = ld_stream(y + row);
+      double loss;
+      link<FAM>(z, yv, loss, w);
+      acc[0] += loss;
+      if (!want_grad) continue;
+    } else {
+      double dv = 0.0;
+#pragma unroll
+      for (int j = 0; j < F; ++j) dv = fma(d[ICPT + j], xt[ICPT + j], dv);
+      if (ICPT) dv += d[0];
+      w = curvature<FAM>(z) * dv;
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[base + i] = fma(w, xt[i], acc[base + i]);
+  }
+  grid_reduce<Q>(acc, s_red, partials, out, s_scale, ticket);
+}
+
+template <int FAM, int MODE, int NP, int ICPT>
+int launch_small_np(const Shard& s, const Params& P, int want_grad) {
+  auto kern = k_small<FAM, NP, ICPT, MODE>;
+  constexpr int Q = (MODE == kModeLossGrad) ? NP + 1 : NP;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0);
+  per_sm = std::max(1, std::min(per_sm, 8));
+  const int64_t want = std::max<int64_t>(1, (s.rows + kThreads - 1) / kThreads);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
+  if ((size_t)grid * Q > s.partials_doubles || (size_t)Q > s.out_doubles) return SO_ENOMEM;
+  kern<<<grid, kThreads, 0, s.stream>>>(s.X, s.y, s.rows, P, want_grad, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+template <int FAM, int MODE>
+int launch_small(const Shard& s, const Params& P, int want_grad) {
+#define SO_CASE(NPV) case NPV: return P.icpt ? launch_small_np<FAM, MODE, NPV, 1>(s, P, want_grad) : launch_small_np<FAM, MODE, NPV, 0>(s, P, want_grad);
+  switch (P.n) {
+    case 1: return P.icpt ? SO_EUNSUPPORTED : launch_small_np<FAM, MODE, 1, 0>(s, P, want_grad);
+    SO_CASE(2) SO_CASE(3) SO_CASE(4) SO_CASE(5) SO_CASE(6) SO_CASE(7) SO_CASE(8)
+  }
+#undef SO_CASE
+  return SO_EUNSUPPORTED;
+}
+
 template <int FAM, int MODE>
 int launch_mapped(const Shard& s, const Params& P, int want_grad) {
   const Mapping m = choose_mapping(P.f);
@@ -198,10 +272,14 @@ int launch_wide(Kind kind, const Shard& s, int family, const double* p, const do
   P.scale0 = (fam == kLinear) ? 0.5 : 1.0;
   switch (kind) {
     case kLossGrad:
+      if (n <= 8) return fam == kLinear ? launch_small<kLinear, kModeLossGrad>(s, P, want_grad)
+                                        : launch_small<kLogistic, kModeLossGrad>(s, P, want_grad);
       return fam == kLinear ? launch_mapped<kLinear, kModeLossGrad>(s, P, want_grad)
                             : launch_mapped<kLogistic, kModeLossGrad>(s, P, want_grad);
     case kHessVec:
       P.scale0 = 1.0;
+      if (n <= 8) return fam == kLinear ? launch_small<kLinear, kModeHessVec>(s, P, 1)
+                                        : launch_small<kLogistic, kModeHessVec>(s, P, 1);
       return fam == kLinear ? launch_mapped<kLinear, kModeHessVec>(s, P, 1)
                             : launch_mapped<kLogistic, kModeHessVec>(s, P, 1);
     case kLine:
