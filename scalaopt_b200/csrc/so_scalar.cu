@@ -368,6 +368,13 @@ __device__ __forceinline__ double fast_sqrt(double x) {
   return fma(0.5 * r, fma(-sq, sq, x), sq);     // one correction step on sqrt itself
 }
 
+// zero, subnormal or huge column norms: IEEE sqrt and division, out of line
+__device__ __noinline__ void householder_slow(double t2, double rjj, double& nrm, double& beta) {
+  nrm = t2 > 0.0 ? sqrt(t2) : 0.0;
+  const double den = nrm * (nrm + fabs(rjj));
+  beta = den > 0.0 ? 1.0 / den : 0.0;
+}
+
 // compile-time loops: every index of R[] and a[][] below is a constant expression whatever the unroller decides
 // (with plain `#pragma unroll` loops the 8-row fold of C >= 5 columns was left partly rolled and a[][] went to
 // local memory: 10x slower).
@@ -382,10 +389,15 @@ __device__ __forceinline__ void qr_fold(double (&R)[C * (C + 1) / 2], double (&a
     static_for<B>([&](auto I) { constexpr int i = decltype(I)::value; sigma = fma(a[i][j], a[i][j], sigma); });
     const double rjj = R[tri_idx<C>(j, j)];
     const double t2 = fma(rjj, rjj, sigma);
-    const double nrm = t2 > 0.0 ? fast_sqrt(t2) : 0.0;
+    double nrm, beta;
+    if (t2 > 1.0e-280 && t2 < 1.0e280) {                   // the MUFU seeds flush subnormals: normal range only
+      nrm = fast_sqrt(t2);
+      beta = fast_rcp(nrm * (nrm + fabs(rjj)));            // 2 / v.v,  v.v = -2 alpha vp = 2 nrm (nrm + |R_jj|)
+    } else {
+      householder_slow(t2, rjj, nrm, beta);
+    }
     const double alpha = rjj > 0.0 ? -nrm : nrm;           // -sign(R_jj) ||(R_jj; a_:j)||: no cancellation in vp
     const double vp = rjj - alpha;
-    const double beta = nrm > 0.0 ? fast_rcp(nrm * fabs(vp)) : 0.0;   // 2 / v.v,  v.v = -2 alpha vp = 2 nrm |vp|
     R[tri_idx<C>(j, j)] = alpha;
     static_for<C - 1 - j>([&](auto K) {
       constexpr int k = j + 1 + decltype(K)::value;

@@ -82,3 +82,20 @@ def test_tsqr_does_not_square_the_condition_number(native, oracle, gpu_ctx):
     except np.linalg.LinAlgError:
         pass                                                  # not positive definite in floating point
     ds.free()
+
+
+def test_tsqr_extreme_scales(native, oracle, gpu_ctx):
+    """column norms far outside the normal range of the fast reciprocal / square-root seeds take the IEEE path"""
+    m = 10_001
+    rng = np.random.default_rng(11)
+    t = rng.random(m)
+    for scale in (1e-160, 1e150):
+        y = scale * (2.0 - 1.3 * t + 0.01 * rng.standard_normal(m))
+        ds = native.Dataset(gpu_ctx, m, 1).append(t.reshape(-1, 1), y)
+        p = np.array([scale * 2.2, scale * -1.0])
+        R = ds.qr(native.POLY, p)
+        assert np.all(np.isfinite(R))
+        ab = oracle.jacobian_matrix(oracle.POLY, t.reshape(-1, 1), y, p)
+        Rl = _normalise(np.linalg.qr(ab, mode="r"))
+        np.testing.assert_allclose(_normalise(R), Rl, rtol=1e-9, atol=1e-9 * np.abs(Rl).max())
+        ds.free()
