@@ -96,6 +96,40 @@ __device__ __forceinline__ double so_exp(double x) {
   return so_exp_fast(x);
 }
 
+// ---- cross-entropy link helpers: log1p(e) for e = exp(-|z|) in [0, 1] and 1/(1 + e) ----------------------------
+// log(1 + e) with a 129-entry table of (1/c_j, log c_j), c_j = 1 + j/128: j = round(128 e), r = (e - j/128)/c_j,
+// |r| <= 2^-8, log1p(r) to degree 6 (truncation r^7/7 < 2e-18): 11 FP64-pipe instructions + 1 LDS.128 where libdevice
+// log1p takes ~40 with branches.  For e < 2^-8 (j = 0) it is the plain series in e: full relative accuracy near 0.
+constexpr int kLogTableSize = 129;
+__shared__ double2 s_log_tab[kLogTableSize];
+struct LogConsts { double shift, n128, c6, c5, c4, c3; };
+static __constant__ LogConsts kLog = { 6755399441055744.0, -1.0 / 128.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0 };
+__device__ __forceinline__ void log_table_init() {
+  for (int j = threadIdx.x; j < kLogTableSize; j += blockDim.x) {
+    const double c = 1.0 + (double)j * (1.0 / 128.0);
+    s_log_tab[j] = make_double2(1.0 / c, log(c));
+  }
+}
+__device__ __forceinline__ double so_log1p_unit(double e) {
+  double kd = fma(e, 128.0, kLog.shift);
+  const int j = __double2loint(kd);
+  kd -= kLog.shift;
+  const double2 t = s_log_tab[j];
+  const double r = fma(kd, kLog.n128, e) * t.x;
+  double q = fma(r, kLog.c6, kLog.c5);
+  q = fma(q, r, kLog.c4);
+  q = fma(q, r, kLog.c3);
+  q = fma(q, r, -0.5);
+  return fma(r * r, q, r) + t.y;
+}
+// 1/x for x in the normal range (here 1 + e in [1, 2]): MUFU seed (>= 23 bits) + two Newton steps, no branches
+__device__ __forceinline__ double so_rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  return fma(r, fma(-x, r, 1.0), r);
+}
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP): global -> shared without touching registers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

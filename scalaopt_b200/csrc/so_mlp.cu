@@ -33,6 +33,7 @@ k_mlp(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, 
   constexpr int Q = MODE == 0 ? 1 : (MODE == 1 ? 1 + N : T + N + 1);
   __shared__ double s_red[(kMlpThreads / 32) * Q];
   exp_table_init();
+  if (CE) log_table_init();
   __syncthreads();
   double acc[Q];
 #pragma unroll
@@ -50,7 +51,7 @@ k_mlp(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, 
       for (int i = 0; i < F; ++i) e = fma(x[i], W.w[j][1 + i], e);
       e += W.w[j][0];                               // weights(0) + (inputs dot weights.tail), Neuron.scala:42-43
       const double ex = so_exp(-fabs(e));
-      const double inv = 1.0 / (1.0 + ex);
+      const double inv = so_rcp_fast(1.0 + ex);
       o[j] = e >= 0.0 ? inv : ex * inv;
       E = fma(o[j], W.v[1 + j], E);
     }
@@ -58,10 +59,10 @@ k_mlp(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, 
     double res, loss;
     if (CE) {
       const double ex = so_exp(-fabs(E));
-      const double inv = 1.0 / (1.0 + ex);
+      const double inv = so_rcp_fast(1.0 + ex);
       res = (E >= 0.0 ? inv : ex * inv) - yv;
       // -y log(o/y) - (1-y) log((1-o)/(1-y)) = softplus(-E) + (1-y) E + [y log y + (1-y) log(1-y)]
-      loss = log1p(ex) + fmax(-E, 0.0) + (1.0 - yv) * E;
+      loss = ((ex >= 0.0 && ex <= 1.0) ? so_log1p_unit(ex) : log1p(ex)) + fmax(-E, 0.0) + (1.0 - yv) * E;
       if (yv > 0.0 && yv < 1.0) loss += yv * log(yv) + (1.0 - yv) * log(1.0 - yv);
     } else {
       res = E - yv;

@@ -24,7 +24,7 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
   const int q = lane & (L - 1), r = lane / L;
   const int f = P.f, icpt = P.icpt;
   const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
-  if (FAM == kLogistic) { exp_table_init(); __syncthreads(); }
+  if (FAM == kLogistic) { exp_table_init(); log_table_init(); __syncthreads(); }
 
   double pj[CV], dj[CV], g[CV];
 #pragma unroll
@@ -169,7 +169,7 @@ k_small(const double* __restrict__ X, const double* __restrict__ y, int64_t rows
   constexpr int F = NP - ICPT, Q = (MODE == kModeLossGrad) ? NP + 1 : NP, base = (MODE == kModeLossGrad) ? 1 : 0;
   __shared__ double s_red[kWarps * Q];
   __shared__ double s_scale[Q];
-  if (FAM == kLogistic) exp_table_init();
+  if (FAM == kLogistic) { exp_table_init(); log_table_init(); }
   for (int q = threadIdx.x; q < Q; q += kThreads) s_scale[q] = (MODE == kModeLossGrad && q == 0) ? P.scale0 : 1.0;
   __syncthreads();
   double acc[Q], p[NP], d[NP];

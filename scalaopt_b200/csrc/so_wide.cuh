@@ -38,12 +38,12 @@ __device__ __forceinline__ void link(double z, double y, double& loss, double& w
     w = z - y;
     loss = w * w;
   } else {
-    const double e = so_exp(-fabs(z));                  // in (0, 1]
-    const double inv = 1.0 / (1.0 + e);
+    const double e = so_exp(-fabs(z));                  // in [0, 1] (NaN for a NaN predictor: propagates)
+    const double inv = so_rcp_fast(1.0 + e);
     const double o = (z >= 0.0) ? inv : e * inv;
     w = o - y;
     // -y log(o/y) - (1-y) log((1-o)/(1-y)) = softplus(-z) + (1-y) z + [y log y + (1-y) log(1-y)]
-    double l = log1p(e) + fmax(-z, 0.0) + (1.0 - y) * z;
+    double l = ((e >= 0.0 && e <= 1.0) ? so_log1p_unit(e) : log1p(e)) + fmax(-z, 0.0) + (1.0 - y) * z;
     if (y > 0.0 && y < 1.0) l += y * log(y) + (1.0 - y) * log(1.0 - y);
     loss = l;
   }
@@ -54,7 +54,7 @@ template <int FAM>
 __device__ __forceinline__ double curvature(double z) {
   if (FAM == kLinear) return 1.0;
   const double e = so_exp(-fabs(z));
-  const double inv = 1.0 / (1.0 + e);
+  const double inv = so_rcp_fast(1.0 + e);
   return e * inv * inv;
 }
 

@@ -21,7 +21,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
   const int q = lane & (L - 1), r = lane / L;
   const int f = P.f, icpt = P.icpt, k = P.k;
   const int Q = 2 * k;
-  if (FAM == kLogistic) { exp_table_init(); __syncthreads(); }
+  if (FAM == kLogistic) { exp_table_init(); log_table_init(); __syncthreads(); }
 
   double pj[CV], dj[CV];
 #pragma unroll
