@@ -56,7 +56,7 @@ k_gram_small(const double* __restrict__ X, const double* __restrict__ y, int64_t
       res = yv - z;                     // rho; J r = -x~ rho
     } else {
       const double e = so_exp(-fabs(z));
-      const double inv = 1.0 / (1.0 + e);
+      const double inv = so_rcp_fast(1.0 + e);
       res = ((z >= 0.0) ? inv : e * inv) - yv;
     }
     int q = 0;
@@ -176,7 +176,7 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
       res = ycur - z;
     } else {
       const double e = so_exp(-fabs(z));
-      const double inv = 1.0 / (1.0 + e);
+      const double inv = so_rcp_fast(1.0 + e);
       res = ((z >= 0.0) ? inv : e * inv) - ycur;
     }
     if (!vcur) res = 0.0;
@@ -512,7 +512,7 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
         res = yv - z;
       } else {
         const double e = so_exp(-fabs(z));
-        const double inv = 1.0 / (1.0 + e);
+        const double inv = so_rcp_fast(1.0 + e);
         res = ((z >= 0.0) ? inv : e * inv) - yv;
       }
       if (chunk * krows + r >= rows) res = 0.0;
