@@ -118,6 +118,19 @@ class GpuMSEFunction : public MSEFunction {
     if (const Entry* e = find(x)) { counters.cache_hits++; return e->loss; }
     if (const LineEntry* le = find_on_ray(x)) { counters.line_hits++; return le->phi; }
     if (on_ray_beta(x)) return score_ray(x).phi;
+    if (loss_only_mode && speculate && use_tsqr && trials_since_jacobian == 0) {
+      // same idea on the TSQR route: r^T r is the squared norm of R's last column
+      ++trials_since_jacobian;
+      spec.R.assign((size_t)(n + 1) * (n + 1), 0.0);
+      check(so_eval_qr(data->ds, family, x.data(), n, spec.R.data()));
+      spec.x = x; spec.valid = true;
+      counters.k2_passes++; counters.spec_passes++;
+      double rtr = 0.0;
+      for (int i = 0; i <= n; ++i) rtr += spec.R[(size_t)i * (n + 1) + n] * spec.R[(size_t)i * (n + 1) + n];
+      const double loss = rtr / (2.0 * (double)data->size());
+      remember(x, loss, nullptr);
+      return loss;
+    }
     if (loss_only_mode && speculate && !use_tsqr && loss_scale() > 0.0 && n <= kSpeculateMaxN && trials_since_jacobian++ == 0) {
       spec.JtJ.assign((size_t)n * n, 0.0); spec.Jtr.assign(n, 0.0);
       check(so_eval_normal_eq(data->ds, family, x.data(), n, spec.JtJ.data(), spec.Jtr.data(), &spec.rtr));
@@ -167,8 +180,13 @@ class GpuMSEFunction : public MSEFunction {
     if (use_tsqr) {
       // the rows of the R factor of [J | r] ARE the (n+1)-row system; no Gram matrix, no Cholesky
       std::vector<double> Rf((size_t)(n + 1) * (n + 1));
-      check(so_eval_qr(data->ds, family, p.data(), n, Rf.data()));
-      counters.k2_passes++;
+      if (spec.valid && same_bits(spec.x, p) && spec.R.size() == Rf.size()) {
+        Rf = spec.R;
+        counters.spec_hits++;
+      } else {
+        check(so_eval_qr(data->ds, family, p.data(), n, Rf.data()));
+        counters.k2_passes++;
+      }
       double rtr = 0.0;
       for (int i = 0; i <= n; ++i) rtr += Rf[(size_t)i * (n + 1) + n] * Rf[(size_t)i * (n + 1) + n];
       { int64_t m = data->size(); remember(p, rtr / (2.0 * (double)m), nullptr); }
@@ -179,7 +197,7 @@ class GpuMSEFunction : public MSEFunction {
     }
     std::vector<double> JtJ((size_t)n * n), Jtr(n);
     double rtr = 0.0;
-    if (spec.valid && same_bits(spec.x, p)) {                      // the accepted trial point: its sums are already here
+    if (spec.valid && same_bits(spec.x, p) && spec.JtJ.size() == JtJ.size()) {   // the accepted trial point: its sums are already here
       JtJ = spec.JtJ; Jtr = spec.Jtr; rtr = spec.rtr;
       counters.spec_hits++;
     } else {
@@ -217,7 +235,7 @@ class GpuMSEFunction : public MSEFunction {
 
  private:
   struct Entry { Vec x; double loss; bool has_grad; Vec grad; };
-  struct Spec { bool valid = false; Vec x; std::vector<double> JtJ, Jtr; double rtr = 0.0; };
+  struct Spec { bool valid = false; Vec x; std::vector<double> JtJ, Jtr, R; double rtr = 0.0; };
   mutable Spec spec;
   mutable int trials_since_jacobian = 0;
   // loss = loss_scale * r^T r / m where the loss is a function of r^T r (0: it is not)

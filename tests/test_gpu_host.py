@@ -55,7 +55,7 @@ CASES = ["gauss_expbkg", "lm_spec_linear", "lm_spec_exponential", "expdecay_larg
 def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu_ctx, case, mode):
     """k2: K2 + Cholesky, trial-point losses from K1; k2-speculative (the default): trial-point losses from K2 passes whose
     sums serve the next Jacobian request; tsqr: the (n+1)-row system is the R factor from so_eval_qr."""
-    tsqr, speculate = mode == "tsqr", mode == "k2-speculative"
+    tsqr, speculate = mode == "tsqr", mode != "k2"
     if tsqr and case == "lm_spec_linear":
         pytest.skip("TSQR covers the single-input families")
     if case == "gauss_expbkg":         # BASELINE config 3 at oracle-sized m
@@ -91,6 +91,7 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
         assert c["k1_passes"] + c["spec_passes"] == r_gpu.inner_iterations
         assert c["k2_passes"] + c["spec_hits"] == r_gpu.iterations + c["spec_passes"]
         assert c["spec_passes"] == r_gpu.iterations and c["spec_hits"] >= min(1, r_gpu.iterations - 1)
+        assert tsqr or c["k1_passes"] == r_gpu.inner_iterations - r_gpu.iterations
     else:
         assert c["k2_passes"] == r_gpu.iterations            # one normal-equation pass per outer iteration
         assert c["k1_passes"] == r_gpu.inner_iterations      # one loss pass per trial point
