@@ -26,7 +26,7 @@ constexpr int kMlpThreads = 256;
 template <int F, int H> struct MlpW { double w[H][F + 1]; double v[H + 1]; };
 
 template <int F, int H, bool CE, int MODE>      // MODE 0: loss, 1: loss + gradient, 2: normal equations
-__global__ void __launch_bounds__(kMlpThreads, 2)
+__global__ void __launch_bounds__(kMlpThreads, (MODE == 2 || H * (F + 1) + H + 1 > 16) ? 2 : 4)
 k_mlp(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ MlpW<F, H> W,
       double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   constexpr int N = H * (F + 1) + H + 1, T = N * (N + 1) / 2;
