@@ -140,6 +140,83 @@ int launch_kpl(const Shard& s, const Params& P) {
   return SO_EINVAL;                        // the API layer sends at most 8 step sizes per pass
 }
 
+// n <= 8: one thread per observation, KB step sizes in registers (see k_small in so_wide.cu)
+template <int FAM, int NP, int ICPT, int KB>
+__global__ void __launch_bounds__(kThreads, 4)
+k_small_line(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
+             double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
+  constexpr int F = NP - ICPT, Q = 2 * KB;
+  __shared__ double s_red[kWarps * Q];
+  __shared__ double s_scale[Q];
+  __shared__ signed char s_src[Q];
+  const int k = P.k;
+  if (FAM == kLogistic) { exp_table_init(); log_table_init(); }
+  for (int q = threadIdx.x; q < Q; q += kThreads) {          // out: phi[0..k), dphi[0..k) from accumulators [0..KB), [KB..2KB)
+    s_scale[q] = (q < k) ? P.scale0 : 1.0;
+    s_src[q] = (signed char)((q < k) ? q : KB + (q - k));
+  }
+  __syncthreads();
+  double acc[Q], p[NP], d[NP], al[KB];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { p[i] = P.p[i]; d[i] = P.d[i]; }
+#pragma unroll
+  for (int a = 0; a < KB; ++a) al[a] = P.alpha[a < k ? a : k - 1];
+  for (int64_t row = (int64_t)blockIdx.x * kThreads + threadIdx.x; row < rows; row += (int64_t)gridDim.x * kThreads) {
+    double u = 0.0, dv = 0.0;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      const double x = ld_stream(X + row * F + j);
+      u = fma(p[ICPT + j], x, u);
+      dv = fma(d[ICPT + j], x, dv);
+    }
+    if (ICPT) { u += p[0]; dv += d[0]; }
+    const double yv = ld_stream(y + row);
+#pragma unroll
+    for (int a = 0; a < KB; ++a) {
+      double l, w;
+      link<FAM>(fma(al[a], dv, u), yv, l, w);
+      acc[a] += l;
+      acc[KB + a] = fma(w, dv, acc[KB + a]);
+    }
+  }
+  grid_reduce<Q>(acc, s_red, partials, out, s_scale, ticket, s_src, 2 * k);
+}
+
+template <int FAM, int NP, int ICPT, int KB>
+int launch_small_line_kb(const Shard& s, const Params& P) {
+  auto kern = k_small_line<FAM, NP, ICPT, KB>;
+  constexpr int Q = 2 * KB;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0);
+  per_sm = std::max(1, std::min(per_sm, 8));
+  const int64_t want = std::max<int64_t>(1, (s.rows + kThreads - 1) / kThreads);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
+  if ((size_t)grid * Q > s.partials_doubles || (size_t)Q > s.out_doubles) return SO_ENOMEM;
+  kern<<<grid, kThreads, 0, s.stream>>>(s.X, s.y, s.rows, P, s.partials, s.out, s.ticket);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+template <int FAM, int NP, int ICPT>
+int launch_small_line_np(const Shard& s, const Params& P) {
+  if (P.k <= 1) return launch_small_line_kb<FAM, NP, ICPT, 1>(s, P);
+  if (P.k <= 2) return launch_small_line_kb<FAM, NP, ICPT, 2>(s, P);
+  if (P.k <= 4) return launch_small_line_kb<FAM, NP, ICPT, 4>(s, P);
+  return launch_small_line_kb<FAM, NP, ICPT, 8>(s, P);
+}
+
+template <int FAM>
+int launch_small_line(const Shard& s, const Params& P) {
+#define SO_CASE(NPV) case NPV: return P.icpt ? launch_small_line_np<FAM, NPV, 1>(s, P) : launch_small_line_np<FAM, NPV, 0>(s, P);
+  switch (P.n) {
+    case 1: return P.icpt ? SO_EUNSUPPORTED : launch_small_line_np<FAM, 1, 0>(s, P);
+    SO_CASE(2) SO_CASE(3) SO_CASE(4) SO_CASE(5) SO_CASE(6) SO_CASE(7) SO_CASE(8)
+  }
+#undef SO_CASE
+  return SO_EUNSUPPORTED;
+}
+
 template <int FAM>
 int launch_mapped(const Shard& s, const Params& P) {
   const Mapping m = choose_mapping(P.f);
@@ -156,6 +233,7 @@ int launch_mapped(const Shard& s, const Params& P) {
 
 int launch_line(const Shard& s, int fam, const Params& P) {
   if (P.k < 1 || P.k > 8) return SO_EINVAL;
+  if (P.n <= 8) return fam == kLinear ? launch_small_line<kLinear>(s, P) : launch_small_line<kLogistic>(s, P);
   return fam == kLinear ? launch_mapped<kLinear>(s, P) : launch_mapped<kLogistic>(s, P);
 }
 
