@@ -1,9 +1,11 @@
 // so_device.cuh — device-side building blocks shared by the evaluation kernels (sm_100a).
 //
 //  * so_exp_fast: fp64 exp with a 256-entry 2^(j/256) table in shared memory and a degree-4 polynomial:
-//    9 FP64-pipe instructions instead of ~25 for libdevice exp.  The Gaussian-peak / exponential
+//    8 FP64-pipe instructions + 4 others instead of ~25 + ~15 for libdevice exp.  The Gaussian-peak / exponential
 //    families are FP64-issue-bound on B200 (64 DFMA/clk/SM vs 16 B/row at HBM speed), so the
-//    transcendental is the first thing to shave.  |rel err| < 2^-52 on [-708, 709].
+//    transcendental is the first thing to shave.  Error vs libm on |x| < 708: <= 1.5 ulp + 3.4e-17 |x| relative
+//    (the second term = a relative perturbation of the ARGUMENT by 0.3 ulp: less than the rounding error the
+//    argument already carries).
 //  * deterministic two-level reduction: fixed thread->row mapping, butterfly shuffles inside a warp,
 //    shared memory across warps in warp order, per-block partials in global memory, and the block that
 //    draws the last ticket adds the partials in block order.  The result does not depend on scheduling.
@@ -21,41 +23,52 @@ __shared__ double s_exp_tab[kExpTableSize];
 
 // Constants live in the constant bank so that DFMA/DADD take them as c[bank][offset] operands: a 64-bit
 // literal that is not representable as a 32-bit immediate otherwise costs two UMOV/IMAD.MOV per use.
-struct ExpConsts { double inv, shift, nln2hi, nln2lo, c4, c3; };
+struct ExpConsts { double inv, shift, nln2hi, c4; };
 static __constant__ ExpConsts kExp = {
     0x1.71547652b82fep+8,      // 256 / ln 2
     6755399441055744.0,        // 1.5 * 2^52: round-to-nearest-integer by addition
-    -0x1.62e42fefa39efp-9,     // -(ln 2 / 256) rounded to double
-    -0x1.abc9e3b39803fp-64,    // -(ln 2 / 256 - hi)
+    -0x1.62e42fefa39efp-9,     // -(ln 2 / 256) rounded to double (the 9.1e-20 it misses is the 3.4e-17 |x| above)
     0x1.5555555555555p-5,      // 1/24
-    0x1.5555555555555p-3,      // 1/6
 };
+// 1/6 with the low word zero: DFMA takes it as a 32-bit immediate (no register, no constant-bank slot next to c4).
+// It is 2.4e-7 low; on |r| <= ln2/512 that moves the result by <= 1e-16.
+#define SO_EXP_C3 __longlong_as_double(0x3FC5555500000000LL)
 
 // |x| >= 708 (result would be subnormal / overflow), inf and NaN take the libdevice path.
 constexpr int kExpHiLimit = 0x40862000;
 __device__ __forceinline__ int exp_abs_hi(double x) { return __double2hiint(x) & 0x7fffffff; }
+// The same test on the FP32 pipe: the high word of a double read as a float orders like the double's magnitude, and the
+// high word of an inf/NaN double is a NaN float, so !(|hi| < limit) is "out of range".  One FSETP with a free |.| modifier
+// per argument (predicates OR-ed) instead of LOP3 + integer max + ISETP; FP32 instructions are the cheapest thing to
+// issue next to DFMAs (tools/dfma_mix.cu).
+__device__ __forceinline__ bool exp_in_range(double x) { return fabsf(__int_as_float(__double2hiint(x))) < __int_as_float(kExpHiLimit); }
 
 // Fill the table.  Call from every thread of the block, then __syncthreads().
+// Entry j holds 2^(j/256) with (j << 12) subtracted from its high word: so_exp_fast then adds (k << 12) to the high
+// word, and since k - j = 256 e exactly that is the entry scaled by 2^e — one integer instruction instead of a shift,
+// a mask and an add.  (Non-FP64 instructions are not free next to DFMAs here: tools/dfma_mix.cu.)
 __device__ __forceinline__ void exp_table_init() {
-  for (int j = threadIdx.x; j < kExpTableSize; j += blockDim.x) s_exp_tab[j] = exp2((double)j * (1.0 / 256.0));
+  for (int j = threadIdx.x; j < kExpTableSize; j += blockDim.x) {
+    const double v = exp2((double)j * (1.0 / 256.0));
+    s_exp_tab[j] = __hiloint2double(__double2hiint(v) - (j << 12), __double2loint(v));
+  }
 }
 
-// exp(x) for |x| < 708, no range check, no branch: 9 FP64-pipe instructions + 1 LDS + ~5 integer ops.
+// exp(x) for |x| < 708, no range check, no branch: 8 FP64-pipe instructions + LOP3/SHL, LDS, IMAD.
 //   k = round(256 x / ln 2),  r = x - k ln2/256 (|r| <= ln2/512),  exp(x) = 2^(k>>8) * T[k&255] * (1 + r + r^2/2 + r^3/6 + r^4/24)
-// truncation error r^5/120 < 4e-17; measured against libm: <= 1 ulp.
+// truncation error r^5/120 < 4e-17.
 __device__ __forceinline__ double so_exp_fast(double x) {
   double kd = fma(x, kExp.inv, kExp.shift);
   const int ki = __double2loint(kd);
   kd -= kExp.shift;
-  double r = fma(kd, kExp.nln2hi, x);
-  r = fma(kd, kExp.nln2lo, r);
-  double q = fma(r, kExp.c4, kExp.c3);
+  const double r = fma(kd, kExp.nln2hi, x);
+  double q = fma(r, kExp.c4, SO_EXP_C3);
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   const double pm1 = q * r;
-  const double T = s_exp_tab[ki & (kExpTableSize - 1)];
-  const double res = fma(T, pm1, T);
-  return __hiloint2double(__double2hiint(res) + ((ki << 12) & 0xfff00000), __double2loint(res));
+  const double Tb = s_exp_tab[ki & (kExpTableSize - 1)];
+  const double T = __hiloint2double(__double2hiint(Tb) + (ki << 12), __double2loint(Tb));   // 2^(k/256), |x| < 708: normal
+  return fma(T, pm1, T);
 }
 
 // rare path (|x| >= 708, inf, NaN): a real call keeps the ~60 libdevice instructions out of the hot loop body
@@ -65,34 +78,35 @@ static __device__ __noinline__ double exp_slow(double x) { return exp(x); }
 // instructions.  |r| <= ln2/8192, truncation error r^4/24 < 3e-18.  Worth its shared memory only where the kernel
 // is FP64-issue-bound (every FP64 instruction costs >= 2 issue cycles and nothing else hides under it).
 constexpr int kExpBigBits = 12, kExpBigSize = 1 << kExpBigBits;
-struct ExpConstsBig { double inv, shift, nln2hi, nln2lo, c3; };
+struct ExpConstsBig { double inv, shift, nln2hi, c3; };
 static __constant__ ExpConstsBig kExpBig = {
     0x1.71547652b82fep+12,     // 4096 / ln 2
     6755399441055744.0,
     -0x1.62e42fefa39efp-13,    // -(ln 2 / 4096) rounded to double
-    -0x1.abc9e3b39803fp-68,    // -(ln 2 / 4096 - hi)
     0x1.5555555555555p-3,      // 1/6
 };
 __device__ __forceinline__ void exp_big_table_init(double* tab) {
-  for (int j = threadIdx.x; j < kExpBigSize; j += blockDim.x) tab[j] = exp2((double)j * (1.0 / kExpBigSize));
+  for (int j = threadIdx.x; j < kExpBigSize; j += blockDim.x) {
+    const double v = exp2((double)j * (1.0 / kExpBigSize));
+    tab[j] = __hiloint2double(__double2hiint(v) - (j << 8), __double2loint(v));     // pre-biased as in exp_table_init
+  }
 }
 __device__ __forceinline__ double so_exp_fast_big(double x, const double* __restrict__ tab) {
   double kd = fma(x, kExpBig.inv, kExpBig.shift);
   const int ki = __double2loint(kd);
   kd -= kExpBig.shift;
-  double r = fma(kd, kExpBig.nln2hi, x);
-  r = fma(kd, kExpBig.nln2lo, r);
+  const double r = fma(kd, kExpBig.nln2hi, x);
   double q = fma(r, kExpBig.c3, 0.5);
   q = fma(q, r, 1.0);
   const double pm1 = q * r;
-  const double T = tab[ki & (kExpBigSize - 1)];
-  const double res = fma(T, pm1, T);
-  return __hiloint2double(__double2hiint(res) + ((ki << 8) & 0xfff00000), __double2loint(res));
+  const double Tb = tab[ki & (kExpBigSize - 1)];
+  const double T = __hiloint2double(__double2hiint(Tb) + (ki << 8), __double2loint(Tb));
+  return fma(T, pm1, T);
 }
 
 // exp(x) with the range check folded in (one branch); used where the check is not hoisted by the caller.
 __device__ __forceinline__ double so_exp(double x) {
-  if (exp_abs_hi(x) >= kExpHiLimit) return exp_slow(x);
+  if (!exp_in_range(x)) return exp_slow(x);
   return so_exp_fast(x);
 }
 

@@ -626,6 +626,9 @@ k_gram_ws(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
       }
     }
     residual_phase(chunk + nworkers, it + 1);              // one chunk ahead of the DMMAs
+    // generic-proxy reads of this slot are ordered before the bulk copies that refill it after the barrier (the loads have
+    // completed by now — their values went into DMMAs — so the fence is free here; see k_scalar in so_scalar.cu)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     bar_block();                                           // everyone is done with this chunk
   }
   if (!bulk) asm volatile("cp.async.wait_all;" ::: "memory");

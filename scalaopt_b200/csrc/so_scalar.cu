@@ -521,16 +521,16 @@ __device__ __forceinline__ void process_rows(const typename Op::Args& args, cons
     }
   } else {
     double ea[G][NE];
-    int mx = 0;
+    bool ok = true;
 #pragma unroll
     for (int r = 0; r < G; ++r) {
       Op::args(args, t[r], ea[r]);
       if (CHECK) {
 #pragma unroll
-        for (int e = 0; e < NE; ++e) mx = max(mx, exp_abs_hi(ea[r][e]));
+        for (int e = 0; e < NE; ++e) ok = ok && exp_in_range(ea[r][e]);
       }
     }
-    if (!CHECK || mx < kExpHiLimit) {
+    if (!CHECK || ok) {
 #pragma unroll
       for (int r = 0; r < G; ++r)
 #pragma unroll
@@ -577,17 +577,17 @@ __device__ __noinline__ void process1_cold(const typename Op::Args& args, double
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The kernel.  A block walks chunks of 4 * TPB observations (grid-stride, fixed assignment, so the summation
-// order is fixed).  A chunk's t and y (2 x 8 KB at TPB = 256) are brought into a 4-deep shared-memory ring by
+// The kernel.  A block walks chunks of RPT * TPB observations (grid-stride, fixed assignment, so the summation
+// order is fixed).  A chunk's t and y (2 x 8-16 KB at TPB = 256) are brought into a 3-4-deep shared-memory ring by
 // TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) issued by thread 0: the loads cost no
-// registers and no issue slots in the compute warps, and 32-48 KB per block are in flight whatever the
-// occupancy.  Consumers signal "stage read" on an `empty` mbarrier (one arrive per warp); only the producer
-// thread ever waits on it, and it refills a stage one iteration after the block consumed it, so there is no
-// block-wide barrier in the loop and the warps of a block are free to drift out of phase.
-// What ncu showed on the way here (profiles/):
+// registers and no issue slots in the compute warps, and 64-96 KB per block are in flight whatever the occupancy.
+// A stage is released (fence.proxy.async + block barrier) after its rows were processed and refilled by thread 0
+// right after that barrier (see "Releasing a stage" in the loop).
+// What ncu / A-B runs showed on the way here (profiles/, gpurun_out/ab*.log):
 //   direct LDG.128                     FP64 pipe 63% busy, top stall long_scoreboard        r1_k2_v1_direct_ldg.json
 //   ring + __syncthreads per chunk     FP64 pipe 70% busy, 9% of samples on the barrier     r1_k2_v2_block_ring.json
 //   warp-private rings (1 KB copies)   slower than the block ring (54% vs 64% of roofline)  DESIGN.md
+//   barrier right after the LDS        2.5% faster than releasing at the end, but races with the refill (MODE 4 note below)
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int stages_for(int rpt, bool big = false) { return rpt >= 8 ? (big ? 2 : 3) : 4; }
 constexpr size_t ring_bytes(int tpb, int rpt, bool big) { return (size_t)stages_for(rpt, big) * tpb * rpt * 16; }
@@ -657,23 +657,33 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
       tv[j] = reinterpret_cast<const double2*>(st)[tid + j * TPB];
       yv[j] = Op::kNeedsY ? reinterpret_cast<const double2*>(st + kChunkRows)[tid + j * TPB] : make_double2(0.0, 0.0);
     }
-    if (MODE == 0) {
-      __syncthreads();                                          // every thread holds its rows: the stage can be refilled
+    // Releasing a stage.  The refill is an async-proxy (TMA) write to shared memory that this block has just read through
+    // the generic proxy; the two must be ordered, and a block barrier alone does not do that: LDS instructions may still
+    // be in flight when their warp passes BAR.SYNC.  (Seen for real: a variant of this kernel whose accumulators lived in
+    // local memory returned run-to-run different sums at 1e9 rows with the barrier right after the loads; with the
+    // proxy fence it was reproducible again.  tools/k2_ab.sh, gpurun_out/ab3.log.)
+    //   MODE 0 (default): process the rows, then fence.proxy.async + __syncthreads, then thread 0 refills the stage:
+    //           the loads have long completed (their values were consumed), so the fence costs nothing.
+    //   MODE 1: as MODE 0 with an `empty` mbarrier instead of the block barrier: only thread 0 waits for the other warps.
+    //   MODE 4: fence + barrier right after the loads (maximum prefetch distance, but every warp waits for its LDS data).
+    auto release_stage = [&]() {
+#ifndef SO_NO_PROXY_FENCE
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+      __syncthreads();
       if (tid == 0) {
         const int64_t nc = chunk + (int64_t)kStages * gridDim.x;
         if (nc < nchunks) issue(nc, stage);
       }
-    } else {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[stage]);             // this warp holds its rows of `stage`
+    };
+    if (MODE == 4) release_stage();
+    if (MODE == 2) {
+      // every warp that passes this barrier has finished the previous iteration: refill the stage consumed there.  The
+      // barrier sits where the warps wait for their LDS data anyway; prefetch distance kStages - 1 chunks.
+      __syncthreads();
       if (tid == 0 && it >= 1) {
-        // refill the stage the block consumed in the previous iteration (its readers are done or nearly so)
-        const int ps = (it - 1) % kStages;
         const int64_t nc = chunk + (int64_t)(kStages - 1) * gridDim.x;
-        if (nc < nchunks) {
-          mbar_wait(&s_empty[ps], (uint32_t)(((it - 1) / kStages) & 1));
-          issue(nc, ps);
-        }
+        if (nc < nchunks) issue(nc, (it - 1) % kStages);
       }
     }
     if constexpr (Op::G == 8 && RPT == 8) {
@@ -696,6 +706,24 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
       }
     }
     if constexpr (requires { Op::renorm(acc); }) Op::renorm(acc);
+    if (MODE == 0) {
+      release_stage();                                          // same sequence, but after the rows were consumed
+    } else if (MODE == 2) {
+#ifndef SO_NO_PROXY_FENCE
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this iteration's reads, before the refill one barrier later
+#endif
+    } else if (MODE == 1) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);
+      if (tid == 0) {
+        const int64_t nc = chunk + (int64_t)kStages * gridDim.x;
+        if (nc < nchunks) {
+          mbar_wait(&s_empty[stage], (uint32_t)((it / kStages) & 1));
+          issue(nc, stage);
+        }
+      }
+    }
   }
   if constexpr (requires { Op::kGroupFold; }) {
     if (blockIdx.x == 0 && tid == 0 && head) process1_cold<Op, BIG>(args, t[0], y[0], acc, big_tab);
@@ -743,6 +771,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
   constexpr int N = Fam::N;
   const typename Fam::Pre pre = Fam::prepare(p);
   switch (kind) {
+#ifndef SO_SCALAR_MINIMAL
     case kLossGrad: {
       if (want_grad) {
         using Op = OpLossGrad<Fam, true>;
@@ -755,6 +784,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       typename Op::Args a; a.pre = pre; a.scale[0] = 0.5;
       return launch_op<Op, 4>(s, a);
     }
+#endif
     case kNormalEq: {
       using Op = OpNormalEq<Fam>;
       typename Op::Args a; a.pre = pre;
@@ -771,13 +801,21 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
         // the headline kernel (BASELINE config 3): 2 rows per range-checked group, 8 rows per thread per chunk,
         // 2 blocks/SM.  A/B runs on one box (gpurun_out/call26-27): 4 rows per group -1 %, 4 rows per
         // chunk -3 %, 4096-entry exp table (degree-3 polynomial) +1.5 %, no range check at all +1.5 %, 20-24 warps/SM -8..-25 %.
-        using Op2 = OpNormalEq<Fam, 2>;
+#ifndef SO_K2_G
+#define SO_K2_G 2
+#define SO_K2_TPB 256
+#define SO_K2_MINB 2
+#define SO_K2_MODE 0
+#define SO_K2_RPT 8
+#endif
+        using Op2 = OpNormalEq<Fam, SO_K2_G>;
         typename Op2::Args a2; a2.pre = a.pre;
         for (int q2 = 0; q2 < Op2::Q; ++q2) { a2.scale[q2] = a.scale[q2]; a2.src[q2] = a.src[q2]; }
-        return launch_op_cfg<Op2, 256, 2, 0, 8, false, true>(s, a2);
+        return launch_op_cfg<Op2, SO_K2_TPB, SO_K2_MINB, SO_K2_MODE, SO_K2_RPT, false, true>(s, a2);
       }
       return launch_op<Op, (Op::Q < 21 ? 3 : 2)>(s, a);
     }
+#ifndef SO_SCALAR_MINIMAL
     case kLine: {
       // batches of up to 8 step sizes per pass; longer schedules take several passes into consecutive out slots
       // (the API layer asks for at most 8 per call for these families)
@@ -815,7 +853,8 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       a.scale[N] = 1.0;
       return launch_op_cfg<Op, 256, 1, 0, 8>(s, a);
     }
-    case kNll: break;      // served by launch_nll
+#endif
+    default: break;        // kNll is served by launch_nll
   }
   return SO_EINVAL;
 }
@@ -830,6 +869,9 @@ size_t scalar_partials_needed(Kind kind, int n, int k, int sm_count) {
 }
 
 int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* consts, int nconsts) {
+#ifdef SO_SCALAR_MINIMAL
+  return SO_EUNSUPPORTED;
+#endif
   if (s.f != 1) return SO_EINVAL;
   if (pdf != SO_PDF_GAUSS_EXPBKG) return SO_EUNSUPPORTED;
   if (n != 4 || nconsts < 1 || !consts) return SO_EINVAL;
@@ -849,9 +891,12 @@ int launch_scalar(Kind kind, const Shard& s, int family, const double* p, const 
                   const double* alpha, int k, int want_grad) {
   if (s.f != 1) return SO_EINVAL;
   switch (family) {
+#ifndef SO_SCALAR_MINIMAL
     case SO_FAMILY_EXPDECAY: if (n != 2) return SO_EINVAL; return launch_family<FamExpDecay>(kind, s, p, d, alpha, k, want_grad);
     case SO_FAMILY_GAUSS: if (n != 3) return SO_EINVAL; return launch_family<FamGauss>(kind, s, p, d, alpha, k, want_grad);
+#endif
     case SO_FAMILY_GAUSS_EXPBKG: if (n != 5) return SO_EINVAL; return launch_family<FamGaussExpBkg>(kind, s, p, d, alpha, k, want_grad);
+#ifndef SO_SCALAR_MINIMAL
     case SO_FAMILY_POLY:
       switch (n) {
         case 1: return launch_family<FamPoly<1>>(kind, s, p, d, alpha, k, want_grad);
@@ -864,6 +909,7 @@ int launch_scalar(Kind kind, const Shard& s, int family, const double* p, const 
         case 8: return launch_family<FamPoly<8>>(kind, s, p, d, alpha, k, want_grad);
         default: return SO_EUNSUPPORTED;
       }
+#endif
     default: return SO_EUNSUPPORTED;
   }
 }

@@ -1,0 +1,47 @@
+// k2_ab.cu — A/B harness for the headline kernel (K2, Gaussian peak + exponential background, n = 5).
+// Compiles scalaopt_b200/csrc/so_scalar.cu with SO_SCALAR_MINIMAL (+ the variant's -D flags) into ONE executable per
+// variant; tools/k2_ab.sh builds them and runs them back to back on the same box.  Prints kernel ms (CUDA events,
+// best and median of 20 launches after 3 warm-ups) and a checksum of the result.
+#define SO_SCALAR_MINIMAL
+#include "../scalaopt_b200/csrc/so_scalar.cu"
+#include <cstdio>
+#include <vector>
+
+__global__ void k_fill(double* t, double* y, int64_t rows) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+    const double tt = 4.0 * u, z = (tt - 2.0) / 0.5;
+    t[i] = tt;
+    y[i] = 2.0 * exp(-0.5 * z * z) + 1.0 * exp(-0.5 * tt) + 0.01 * ((double)((h >> 3) & 1023) / 1023.0 - 0.5);
+  }
+}
+
+int main(int argc, char** argv) {
+  const int64_t rows = argc > 1 ? atoll(argv[1]) : 1000000000ll;
+  const char* name = argc > 2 ? argv[2] : "variant";
+  double *t, *y, *partials, *out; unsigned int* ticket;
+  cudaMalloc(&t, rows * 8); cudaMalloc(&y, rows * 8);
+  cudaMalloc(&partials, 148 * 8 * 64 * 8); cudaMalloc(&out, 64 * 8); cudaMalloc(&ticket, 4); cudaMemset(ticket, 0, 4);
+  k_fill<<<148 * 8, 256>>>(t, y, rows);
+  if (cudaDeviceSynchronize() != cudaSuccess) { printf("fill failed\n"); return 1; }
+  so::Shard s; s.X = t; s.y = y; s.rows = rows; s.f = 1; s.partials = partials; s.partials_doubles = 148 * 8 * 64;
+  s.out = out; s.out_doubles = 64; s.ticket = ticket;
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0); s.sm_count = prop.multiProcessorCount;
+  const double p[5] = {1.9, 2.05, 0.52, 1.1, 0.45};
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  std::vector<float> ms;
+  for (int r = 0; r < 23; ++r) {
+    cudaEventRecord(e0);
+    const int rc = so::launch_scalar(so::kNormalEq, s, SO_FAMILY_GAUSS_EXPBKG, p, nullptr, 5, nullptr, 0, 0);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    if (rc <= 0 || cudaGetLastError() != cudaSuccess) { printf("launch failed rc=%d\n", rc); return 1; }
+    float m; cudaEventElapsedTime(&m, e0, e1); if (r >= 3) ms.push_back(m);
+  }
+  std::sort(ms.begin(), ms.end());
+  double h[21]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  double cs = 0; for (int i = 0; i < 21; ++i) cs += h[i] * (i + 1);
+  printf("{\"variant\": \"%s\", \"rows\": %lld, \"ms_best\": %.4f, \"ms_median\": %.4f, \"gbs_median\": %.1f, \"checksum\": %.17g, \"rtr\": %.17g}\n",
+         name, (long long)rows, ms.front(), ms[ms.size() / 2], rows * 16e-6 / ms[ms.size() / 2], cs, h[20]);
+  return 0;
+}
