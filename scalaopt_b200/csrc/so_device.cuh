@@ -183,6 +183,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ double2 ld_stream2(const double2* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 
+// lanes per output in the last block's walk over the per-block partials: the largest power of two <= 32 with
+// outputs * lanes <= threads (1 when there are more outputs than threads / 2)
+__device__ __forceinline__ int partials_lanes(int outputs, int threads) {
+  int G = 32;
+  while (G > 1 && outputs * G > threads) G >>= 1;
+  return G;
+}
+
 // Reduce Q per-thread accumulators over the grid, deterministically.
 //   acc[Q]      per-thread partial sums
 //   smem        >= (blockDim.x/32) * Q doubles of shared memory
@@ -214,13 +222,25 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[Q], double* smem, doub
   if (s_last) {
     __threadfence();
     // out[q] = scale[q] * S[src[q]]  (+ scale2[q] * S[qout + q] when the result is the sum of two accumulator sets)
-    for (int q = threadIdx.x; q < qout; q += blockDim.x) {
-      const int qs = src ? (int)src[q] : q;        // identical sums are kept once
+    // G lanes per output add the blocks b = sub, sub + G, ... in order and are then folded by a fixed butterfly: the order is
+    // a function of (gridDim, Q) only, and a 5-output kernel does not walk 1184 partials with one thread per output
+    // (that walk was 20 of the 25 us of a 1e6-row evaluation).
+    const int G = partials_lanes(qout, blockDim.x);
+    const int per_round = blockDim.x / G, sub = threadIdx.x % G;
+    for (int q0 = 0; q0 < qout; q0 += per_round) {
+      const int q = q0 + threadIdx.x / G;
+      const bool act = q < qout;
+      const int qs = act ? (src ? (int)src[q] : q) : 0;        // identical sums are kept once
       double s = 0.0, s2 = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * Q + qs]);
-      if (scale2) for (unsigned b = 0; b < gridDim.x; ++b) s2 += __ldcg(&partials[(size_t)b * Q + qout + q]);
-      const double v = scale ? s * scale[q] : s;
-      out[q] = scale2 ? fma(s2, scale2[q], v) : v;
+      if (act) {
+        for (unsigned b = sub; b < gridDim.x; b += G) s += __ldcg(&partials[(size_t)b * Q + qs]);
+        if (scale2) for (unsigned b = sub; b < gridDim.x; b += G) s2 += __ldcg(&partials[(size_t)b * Q + qout + q]);
+      }
+      for (int o = G >> 1; o >= 1; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      if (act && sub == 0) {
+        const double v = scale ? s * scale[q] : s;
+        out[q] = scale2 ? fma(s2, scale2[q], v) : v;
+      }
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
@@ -238,10 +258,14 @@ __device__ __forceinline__ void grid_reduce_block_vals(const double* block_vals,
   __syncthreads();
   if (s_last2) {
     __threadfence();
-    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    const int G = partials_lanes(Q, blockDim.x);
+    const int per_round = blockDim.x / G, sub = threadIdx.x % G;
+    for (int q0 = 0; q0 < Q; q0 += per_round) {
+      const int q = q0 + threadIdx.x / G;
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * Q + q]);
-      out[q] = scale ? s * scale[q] : s;
+      if (q < Q) for (unsigned b = sub; b < gridDim.x; b += G) s += __ldcg(&partials[(size_t)b * Q + q]);
+      for (int o = G >> 1; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (q < Q && sub == 0) out[q] = scale ? s * scale[q] : s;
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }

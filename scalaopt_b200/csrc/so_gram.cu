@@ -839,9 +839,15 @@ size_t gram_partials_needed(int n, int f, int sm_count) {
 }
 
 int launch_gram(const Shard& s, int fam, const Params& P) {
+#ifdef SO_GRAM_MINIMAL      // tools/gram_ab.cu: only the shapes under test
+  if (P.f == 32) return fam == kLinear ? launch_tri<kLinear, 4, true>(s, P) : launch_tri<kLogistic, 4, true>(s, P);
+  if (P.f == 33) return launch_tri<kLinear, 5, false>(s, P);
+  return SO_EUNSUPPORTED;
+#else
   if (P.n <= 8) return fam == kLinear ? dispatch_small<kLinear>(s, P) : dispatch_small<kLogistic>(s, P);
   if (P.n + 1 <= 48) return fam == kLinear ? dispatch_tri<kLinear>(s, P) : dispatch_tri<kLogistic>(s, P);
   return fam == kLinear ? launch_ws<kLinear>(s, P) : launch_ws<kLogistic>(s, P);
+#endif
 }
 
 }  // namespace wide

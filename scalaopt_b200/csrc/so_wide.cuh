@@ -105,10 +105,14 @@ __device__ __forceinline__ void finish_grid(const double* vals, int Q, int nscal
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    const int G = partials_lanes(Q, blockDim.x);              // lanes per output, see grid_reduce in so_device.cuh
+    const int per_round = blockDim.x / G, sub = threadIdx.x % G;
+    for (int q0 = 0; q0 < Q; q0 += per_round) {
+      const int q = q0 + threadIdx.x / G;
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * Q + q]);
-      out[q] = (q < nscaled) ? s * scale0 : s;
+      if (q < Q) for (unsigned b = sub; b < gridDim.x; b += G) s += __ldcg(&partials[(size_t)b * Q + q]);
+      for (int o = G >> 1; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (q < Q && sub == 0) out[q] = (q < nscaled) ? s * scale0 : s;
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
