@@ -256,12 +256,14 @@ def run_own(args):
     if rank == 0:
         sampler.start()
     kernel_ms = device_ms = 0.0
+    kernel_ms_best = float("inf")
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         JtJ, Jtr, rtr = ds.normal_eq(fam, params_for_step(i))
         st = ctx.stats()
         kernel_ms += st.kernel_ms
+        kernel_ms_best = min(kernel_ms_best, st.kernel_ms)
         device_ms += st.device_ms
     barrier()
     wall_s = time.perf_counter() - t0
@@ -327,16 +329,16 @@ def run_own(args):
                 traffic_src = tr["source"]
         except Exception:
             pass
-        # north_star's roofline is the SLOWER of bytes at HBM bandwidth and flops at FP64 peak; this kernel executes 47 FP64
+        # north_star's roofline is the SLOWER of bytes at HBM bandwidth and flops at FP64 peak; this kernel executes 45 FP64
         # instructions per observation (SASS of k_scalar<OpNormalEq<FamGaussExpBkg>>), which at the DFMA
         # rate measured on this pool (profiles/r1_fp64_peak.json) takes longer than its 16 bytes at the HBM rate
         fp64 = None
         try:
             pk = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_peak.json")))
             dfma_per_s = float(pk["dfma_tflops_burst"]) * 1e12 / 2.0
-            instr = 47.0 * m
+            instr = 45.0 * m
             bound_ms = instr / dfma_per_s * 1e3
-            fp64 = {"fp64_instr_per_observation": 47, "dfma_peak_instr_per_s": dfma_per_s, "bound_ms_per_launch": bound_ms,
+            fp64 = {"fp64_instr_per_observation": 45, "dfma_peak_instr_per_s": dfma_per_s, "bound_ms_per_launch": bound_ms,
                     "hbm_bound_ms_per_launch": alg_bytes / (hbm_peak * 1e9) * 1e3,
                     "frac_of_fp64_bound": bound_ms / (kernel_ms_max / args.steps),
                     "note": "explanatory only; roofline.frac above is against HBM"}
@@ -351,6 +353,10 @@ def run_own(args):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "k_scalar<OpNormalEq<FamGaussExpBkg>>", "algorithmic_bytes_per_launch": alg_bytes,
+                         # the timed region runs under the board's power cap (see "clocks"); the fastest single launch of the
+                         # region is reported beside the average the roofline fraction is computed from
+                         "fastest_launch": {"kernel_ms": kernel_ms_best, "achieved": alg_bytes / (kernel_ms_best * 1e-3) / 1e9,
+                                            "frac": alg_bytes / (kernel_ms_best * 1e-3) / 1e9 / hbm_peak},
                          "fp64": fp64},
             "clocks": clocks, "gpu_launches": int(launches),
         }
