@@ -98,12 +98,19 @@ struct so_ctx {
   std::mutex mu;
   std::string err;
   so_call_stats stats{};
+  uint64_t data_epoch = 1;        // bumped by everything that writes observations (append, load, clear, generate)
 };
 
 struct ShardMem {
   double* X = nullptr; double* y = nullptr;
   int64_t cap = 0;      // rows reserved on this device
   int64_t filled = 0;   // rows written so far
+  // f == 1: cached input range of the first `range_rows` rows as of data epoch `range_epoch` (views alias their
+  // parent's memory, hence a context-wide epoch rather than a per-data-set flag)
+  uint64_t range_epoch = 0;
+  int64_t range_rows = -1;
+  bool range_ok = false;
+  double tmin = 0.0, tmax = 0.0;
 };
 
 struct so_dataset {
@@ -242,6 +249,28 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
     if (rc0) return rc0;
     if (m_global < 1) return fail(ctx, SO_ESTATE, "data set is empty");
   }
+  // the two-exponential family's K2 drops its per-row exp range check when the shard's inputs allow it: one 8 B/row
+  // pass per data-set state (not per evaluation) finds their range
+  const bool wants_range = !nll && kind == kNormalEq && family == SO_FAMILY_GAUSS_EXPBKG && ds->f == 1;
+  for (int g = 0; g < G && wants_range; ++g) {
+    Device& dv = ctx->devs[g];
+    ShardMem& sm = ds->shards[g];
+    if (sm.filled < 1 || (sm.range_epoch == ctx->data_epoch && sm.range_rows == sm.filled)) continue;
+    int rc = ensure_workspace(ctx, dv, 1, 8);
+    if (rc) return rc;
+    SO_CUDA(ctx, cudaSetDevice(dv.id));
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(dv.out);
+    SO_CUDA(ctx, cudaMemsetAsync(buf, 0xFF, 8, dv.stream));
+    SO_CUDA(ctx, cudaMemsetAsync(buf + 1, 0, 16, dv.stream));
+    Shard sh; sh.X = sm.X; sh.rows = sm.filled; sh.f = 1; sh.stream = dv.stream; sh.sm_count = dv.sm_count;
+    rc = launch_range(sh, buf);
+    if (rc < 0) return fail(ctx, rc, "input-range kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->stats.total_launches += rc;
+    SO_CUDA(ctx, cudaMemcpyAsync(dv.hout, buf, 24, cudaMemcpyDeviceToHost, dv.stream));
+    SO_CUDA(ctx, cudaStreamSynchronize(dv.stream));
+    sm.range_ok = range_decode(reinterpret_cast<const unsigned long long*>(dv.hout), &sm.tmin, &sm.tmax);
+    sm.range_epoch = ctx->data_epoch; sm.range_rows = sm.filled;
+  }
   for (int g = 0; g < G; ++g) {
     Device& dv = ctx->devs[g];
     const ShardMem& sm = ds->shards[g];
@@ -258,6 +287,9 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
       sh.partials = dv.partials; sh.partials_doubles = dv.partials_cap;
       sh.out = dv.out; sh.out_doubles = dv.out_cap; sh.ticket = dv.ticket;
       sh.stream = dv.stream; sh.sm_count = dv.sm_count;
+      if (wants_range && sm.range_ok && sm.range_epoch == ctx->data_epoch && sm.range_rows == sm.filled) {
+        sh.has_range = true; sh.tmin = sm.tmin; sh.tmax = sm.tmax;
+      }
       if (kind == kQr) {      // every device writes its triangle into its own slot of a zeroed buffer: the sum is a gather
         const int slot = ctx->rank_mode ? ctx->rank : g, per = (n + 1) * (n + 1);
         SO_CUDA(ctx, cudaMemsetAsync(dv.out, 0, sizeof(double) * (size_t)Q, dv.stream));
@@ -597,6 +629,7 @@ extern "C" int so_dataset_append(so_dataset* ds, const double* X, const double* 
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_append: cannot append to a view");
+  ++ctx->data_epoch;
   if (rows < 0 || (rows > 0 && (!X || !y))) return fail(ctx, SO_EINVAL, "so_dataset_append: bad arguments");
   MemSource src(X, y);
   return ingest(ds, src, rows);
@@ -607,6 +640,7 @@ extern "C" int so_dataset_load_raw(so_dataset* ds, const char* path_X, const cha
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_load_raw: cannot load into a view");
+  ++ctx->data_epoch;
   if (rows < 0 || file_row_offset < 0) return fail(ctx, SO_EINVAL, "so_dataset_load_raw: bad arguments");
   FileSource src;
   src.fdx = open(path_X, O_RDONLY);
@@ -621,6 +655,7 @@ extern "C" int so_dataset_clear(so_dataset* ds) {
   if (!ds) return SO_EINVAL;
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
   if (ds->view) return fail(ds->ctx, SO_EINVAL, "so_dataset_clear: cannot clear a view");
+  ++ds->ctx->data_epoch;
   for (ShardMem& sm : ds->shards) sm.filled = 0;
   ds->global_m = -1;
   return SO_OK;
@@ -632,6 +667,7 @@ extern "C" int so_dataset_generate(so_dataset* ds, int family, const double* p_t
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_generate: cannot fill a view");
+  ++ctx->data_epoch;
   int rc = check_family(ctx, family, ds->f, n);
   if (rc) return rc;
   // the t grid of the scalar families spans the global data set: in rank mode every rank holds m rows

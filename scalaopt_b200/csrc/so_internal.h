@@ -21,6 +21,9 @@ struct Shard {
   unsigned int* ticket = nullptr;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
+  // f == 1 only: range of the inputs of this slice when it is known and all of them are finite (launch_range)
+  bool has_range = false;
+  double tmin = 0.0, tmax = 0.0;
 };
 
 enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4, kNll = 5, kQr = 6 };
@@ -59,6 +62,11 @@ int launch_wide(Kind kind, const Shard& s, int family, const double* p, const do
 int launch_mlp(Kind kind, const Shard& s, int family, const double* p, int n, int want_grad);
 int mlp_hidden_units(int f, int n);      // h from n = h (f + 2) + 1, or -1
 size_t mlp_partials_needed(Kind kind, int n, int sm_count);
+
+// min / max / non-finite count of the X stream of an f == 1 shard -> buf3 (device, order-preserving integer keys; the
+// caller presets buf3 = {~0, 0, 0} and decodes with range_decode).  One pass at 8 B/row, once per data-set state.
+int launch_range(const Shard& s, unsigned long long* buf3);
+bool range_decode(const unsigned long long* host3, double* tmin, double* tmax);   // false: no rows or a non-finite input
 
 // sum_i -2 log pdf(p, x_i) -> out[0]; reads the X stream only
 int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* consts, int nconsts);

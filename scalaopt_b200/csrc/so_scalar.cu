@@ -138,6 +138,13 @@ struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) {
     return fma(-c.B, ex[1], fma(-c.A, ex[0], y));
   }
+  // true when both exp arguments stay inside (-700, 700) for every t in [tmin, tmax] (they are monotone or convex in t,
+  // so the end points decide); NaN anywhere compares false.  708 is the limit of so_exp_fast: 1 % of margin for rounding.
+  static bool args_in_range(const Pre& c, double tmin, double tmax) {
+    const double z0 = std::fabs(tmin * c.sr2 + c.nmsr2), z1 = std::fabs(tmax * c.sr2 + c.nmsr2);
+    const double zm = z0 > z1 ? z0 : z1, tm = std::fabs(tmin) > std::fabs(tmax) ? std::fabs(tmin) : std::fabs(tmax);
+    return zm * zm < 700.0 && std::fabs(c.nlam) * tm < 700.0;
+  }
   // Gaussian part as in FamGauss; exponential part: h3 = -t e d4, h4 = -t e d3 + B t^2 e d4
   struct HPre { FamGauss::HGauss g; double nd4, nd3, Bd4; };
   static HPre hprepare(const double* p, const double* d) {
@@ -178,9 +185,9 @@ struct FamPoly {       // f = sum_k p_k t^k
 // ---------------------------------------------------------------------------------------------------
 // Per-kind row operators.  NEXP exp arguments per row, G rows per range-checked group.
 // ---------------------------------------------------------------------------------------------------
-template <class Fam, bool GRAD>
+template <class Fam, bool GRAD, int GROUP = 4>
 struct OpLossGrad {
-  static constexpr int N = Fam::N, Q = GRAD ? 1 + N : 1, NEXP = Fam::NE, G = 4;
+  static constexpr int N = Fam::N, Q = GRAD ? 1 + N : 1, NEXP = Fam::NE, G = GROUP;
   static constexpr bool kHasSrc = false;
   static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre; double scale[Q]; };
@@ -249,12 +256,12 @@ struct OpLine {
   }
 };
 
-template <class Fam>
+template <class Fam, int GROUP = 2>
 struct OpHessVec {
   // H d = (1/m) sum_i [ (J_f . d) J_f - rho (d2f/dp2 . d) ]  with J_f = D o u:
   //   acc[0..N)  = sum (dd . u) u_i      (dd = D o d; scaled by D_i on the way out)
   //   acc[N..2N) = sum rho h_i           (subtracted on the way out)
-  static constexpr int N = Fam::N, Q = 2 * N, NEXP = Fam::NE, G = 2;
+  static constexpr int N = Fam::N, Q = 2 * N, NEXP = Fam::NE, G = GROUP;
   static constexpr bool kHasSrc = false;
   static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre; typename Fam::HPre h; double dd[N]; double scale[N]; double scale2[N]; };
@@ -766,25 +773,41 @@ int launch_op_cfg(const Shard& s, const typename Op::Args& args) {
 template <class Op, int MINBLOCKS>
 int launch_op(const Shard& s, const typename Op::Args& args) { return launch_op_cfg<Op, kThreads, MINBLOCKS, 0, (MINBLOCKS <= 2 ? 8 : 4)>(s, args); }
 
+// launch configurations of the kernels that are FP64-issue-bound for the two-exponential family; overridable for the
+// A/B harness (tools/k2_ab.sh)
+// (gpurun_out/ab8.log, 1e9 rows: K1 2 rows per range-checked group 2.76 ms vs 2.99 with 4; K4 4 rows per group, 2 blocks
+// per SM, 8 rows per thread and chunk 3.88 ms vs 4.26)
+#ifndef SO_K1_G
+#define SO_K1_G 2
+#define SO_K1_MINB 3
+#define SO_K1_RPT 4
+#endif
+#ifndef SO_K4_G
+#define SO_K4_G 4
+#define SO_K4_MINB 2
+#define SO_K4_RPT 8
+#endif
 template <class Fam>
 int launch_family(Kind kind, const Shard& s, const double* p, const double* d, const double* alpha, int k, int want_grad) {
   constexpr int N = Fam::N;
   const typename Fam::Pre pre = Fam::prepare(p);
   switch (kind) {
-#ifndef SO_SCALAR_MINIMAL
     case kLossGrad: {
       if (want_grad) {
-        using Op = OpLossGrad<Fam, true>;
+        using Op = OpLossGrad<Fam, true, SO_K1_G>;
         typename Op::Args a; a.pre = pre;
         a.scale[0] = 0.5;
         for (int i = 0; i < N; ++i) a.scale[1 + i] = -pre.D[i];
-        return launch_op<Op, 3>(s, a);
+        return launch_op_cfg<Op, kThreads, SO_K1_MINB, 0, SO_K1_RPT>(s, a);
       }
+#ifndef SO_SCALAR_MINIMAL
       using Op = OpLossGrad<Fam, false>;
       typename Op::Args a; a.pre = pre; a.scale[0] = 0.5;
       return launch_op<Op, 4>(s, a);
-    }
+#else
+      return SO_EUNSUPPORTED;
 #endif
+    }
     case kNormalEq: {
       using Op = OpNormalEq<Fam>;
       typename Op::Args a; a.pre = pre;
@@ -808,6 +831,14 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
 #define SO_K2_MODE 0
 #define SO_K2_RPT 8
 #endif
+        // every exp argument in range for this shard's inputs (known after launch_range): no per-row range check, and
+        // then 4 rows per group are the better grouping (gpurun_out/ab5-7.log: 3.22 vs 3.31 ms per 1e9 rows)
+        if (s.has_range && Fam::args_in_range(pre, s.tmin, s.tmax)) {
+          using Op4 = OpNormalEq<Fam, 4>;
+          typename Op4::Args a4; a4.pre = a.pre;
+          for (int q2 = 0; q2 < Op4::Q; ++q2) { a4.scale[q2] = a.scale[q2]; a4.src[q2] = a.src[q2]; }
+          return launch_op_cfg<Op4, 256, 2, 0, 8, false, false>(s, a4);
+        }
         using Op2 = OpNormalEq<Fam, SO_K2_G>;
         typename Op2::Args a2; a2.pre = a.pre;
         for (int q2 = 0; q2 < Op2::Q; ++q2) { a2.scale[q2] = a.scale[q2]; a2.src[q2] = a.src[q2]; }
@@ -840,12 +871,14 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       if (k <= 4) return run(std::integral_constant<int, 4>());
       return run(std::integral_constant<int, 8>());
     }
+#endif
     case kHessVec: {
-      using Op = OpHessVec<Fam>;
+      using Op = OpHessVec<Fam, SO_K4_G>;
       typename Op::Args a; a.pre = pre; a.h = Fam::hprepare(p, d);
       for (int i = 0; i < N; ++i) { a.dd[i] = pre.D[i] * d[i]; a.scale[i] = pre.D[i]; a.scale2[i] = -1.0; }
-      return launch_op<Op, 3>(s, a);
+      return launch_op_cfg<Op, kThreads, SO_K4_MINB, 0, SO_K4_RPT>(s, a);
     }
+#ifndef SO_SCALAR_MINIMAL
     case kQr: {
       using Op = OpQr<Fam>;
       typename Op::Args a; a.pre = pre;
@@ -859,7 +892,54 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
   return SO_EINVAL;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Input range of an f == 1 shard: min, max and the number of non-finite values, as order-preserving 64-bit keys
+// combined with integer atomics (exact and order-independent, unlike a floating-point reduction would need to be).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long range_key(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void __launch_bounds__(256) k_range(const double* __restrict__ t, int64_t rows, unsigned long long* __restrict__ buf3) {
+  double lo = INFINITY, hi = -INFINITY;
+  unsigned int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = ld_stream(t + i);
+    if (!(fabs(v) <= 1.7976931348623157e308)) ++bad;      // inf or NaN
+    lo = fmin(lo, v); hi = fmax(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&buf3[0], range_key(lo));
+    atomicMax(&buf3[1], range_key(hi));
+    if (bad) atomicAdd(&buf3[2], (unsigned long long)bad);
+  }
+}
+
 }  // namespace
+
+int launch_range(const Shard& s, unsigned long long* buf3) {
+  if (s.f != 1 || s.rows < 1) return SO_EINVAL;
+  const int64_t want = (s.rows + 256 * 8 - 1) / (256 * 8);
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)s.sm_count * 8);
+  k_range<<<grid, 256, 0, s.stream>>>(s.X, s.rows, buf3);
+  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
+}
+
+bool range_decode(const unsigned long long* h, double* tmin, double* tmax) {
+  if (h[2] != 0 || h[0] > h[1]) return false;
+  auto dec = [](unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double d; std::memcpy(&d, &b, sizeof d); return d;
+  };
+  *tmin = dec(h[0]); *tmax = dec(h[1]);
+  return std::isfinite(*tmin) && std::isfinite(*tmax);
+}
 
 size_t scalar_partials_needed(Kind kind, int n, int k, int sm_count) {
   // at most 8 resident 256-thread blocks per SM, Q <= 45 (polynomial n = 8 normal equations)

@@ -20,6 +20,7 @@ __global__ void k_fill(double* t, double* y, int64_t rows) {
 int main(int argc, char** argv) {
   const int64_t rows = argc > 1 ? atoll(argv[1]) : 1000000000ll;
   const char* name = argc > 2 ? argv[2] : "variant";
+  const int kind = argc > 3 ? atoi(argv[3]) : 2;          // 1 = K1 loss+gradient, 2 = K2 normal equations, 4 = K4 Hessian.vector
   double *t, *y, *partials, *out; unsigned int* ticket;
   cudaMalloc(&t, rows * 8); cudaMalloc(&y, rows * 8);
   cudaMalloc(&partials, 148 * 8 * 64 * 8); cudaMalloc(&out, 64 * 8); cudaMalloc(&ticket, 4); cudaMemset(ticket, 0, 4);
@@ -29,19 +30,21 @@ int main(int argc, char** argv) {
   s.out = out; s.out_doubles = 64; s.ticket = ticket;
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0); s.sm_count = prop.multiProcessorCount;
   const double p[5] = {1.9, 2.05, 0.52, 1.1, 0.45};
+  const double d[5] = {0.3, -0.2, 0.1, 0.25, -0.15};
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   std::vector<float> ms;
   for (int r = 0; r < 23; ++r) {
     cudaEventRecord(e0);
-    const int rc = so::launch_scalar(so::kNormalEq, s, SO_FAMILY_GAUSS_EXPBKG, p, nullptr, 5, nullptr, 0, 0);
+    const int rc = so::launch_scalar((so::Kind)kind, s, SO_FAMILY_GAUSS_EXPBKG, p, d, 5, nullptr, 0, 1);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     if (rc <= 0 || cudaGetLastError() != cudaSuccess) { printf("launch failed rc=%d\n", rc); return 1; }
     float m; cudaEventElapsedTime(&m, e0, e1); if (r >= 3) ms.push_back(m);
   }
   std::sort(ms.begin(), ms.end());
-  double h[21]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
-  double cs = 0; for (int i = 0; i < 21; ++i) cs += h[i] * (i + 1);
-  printf("{\"variant\": \"%s\", \"rows\": %lld, \"ms_best\": %.4f, \"ms_median\": %.4f, \"gbs_median\": %.1f, \"checksum\": %.17g, \"rtr\": %.17g}\n",
-         name, (long long)rows, ms.front(), ms[ms.size() / 2], rows * 16e-6 / ms[ms.size() / 2], cs, h[20]);
+  const int Q = kind == 2 ? 21 : (kind == 1 ? 6 : 5);
+  double h[21] = {0}; cudaMemcpy(h, out, sizeof(double) * Q, cudaMemcpyDeviceToHost);
+  double cs = 0; for (int i = 0; i < Q; ++i) cs += h[i] * (i + 1);
+  printf("{\"variant\": \"%s\", \"rows\": %lld, \"ms_best\": %.4f, \"ms_median\": %.4f, \"gbs_median\": %.1f, \"checksum\": %.17g, \"last\": %.17g}\n",
+         name, (long long)rows, ms.front(), ms[ms.size() / 2], rows * 16e-6 / ms[ms.size() / 2], cs, h[Q - 1]);
   return 0;
 }
