@@ -118,6 +118,46 @@ def test_extreme_parameters_take_the_slow_exp_path(native, oracle, gpu_ctx):
     ds.free()
 
 
+def test_normal_equations_pick_the_exp_range_check_from_the_input_range(native, oracle, gpu_ctx):
+    """K2 of the two-exponential family drops its per-row exp range check when the shard's input range keeps every
+    argument inside (-700, 700); whichever variant runs, the sums match the oracle, and the cached range follows the data:
+    same parameters, new data with far-out inputs in the same reservation -> the checked kernel again."""
+    fam = oracle.GAUSS_EXPBKG
+    truth = np.array([2.0, 0.5, 0.05, 1.0, 3.0])
+    m = 6000
+    X, y = oracle.generate(fam, m, 1, truth, noise_sigma=0.05)
+    ds = native.Dataset(gpu_ctx, m, 1).append(X, y)
+
+    def check(p, X, y):
+        JtJ, Jtr, rtr = ds.normal_eq(fam, p)
+        JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p)
+        assert_gram(JtJ, JtJ_o); assert_vec(Jtr, Jtr_o, what="Jtr"); assert_loss(rtr, rtr_o)
+
+    check(truth * 1.1, X, y)                                     # inputs in [0, 1]: every argument small -> check-free kernel
+    check(np.array([2.0, 0.5, 0.001, 1.0, 900.0]), X, y)         # same data, arguments up to 1.2e5 -> checked kernel, slow exp
+    launches = gpu_ctx.stats().total_launches
+    check(truth * 0.9, X, y)
+    assert gpu_ctx.stats().total_launches == launches + 1        # the range pass runs once per data-set state, not per call
+    # new data in the same reservation: inputs far from the peak (exp underflows to 0 for those rows)
+    X2 = X.copy(); X2[::7] = 40.0; X2[3] = -2.0
+    ds.clear(); ds.append(X2, y)
+    launches = gpu_ctx.stats().total_launches
+    check(truth * 1.1, X2, y)                                    # (40 - 0.55)^2 / (2 0.055^2) = 2.6e5 -> checked kernel again
+    assert gpu_ctx.stats().total_launches == launches + 2        # range pass + K2
+    # a view sees its own range
+    v = ds.slice(4, 7)
+    JtJ, Jtr, rtr = v.normal_eq(fam, truth * 1.1)
+    JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X2[4:7], y[4:7], truth * 1.1)
+    assert_gram(JtJ, JtJ_o); assert_vec(Jtr, Jtr_o, what="Jtr"); assert_loss(rtr, rtr_o)
+    v.free()
+    # a non-finite input: no usable range, the checked kernel propagates it like the reference (NaN sums)
+    X3 = X.copy(); X3[11] = np.nan
+    ds.clear(); ds.append(X3, y)
+    JtJ, Jtr, rtr = ds.normal_eq(fam, truth * 1.1)
+    assert np.isnan(rtr) and np.isnan(JtJ).any()
+    ds.free()
+
+
 def test_errors_are_reported_not_swallowed(native, gpu_ctx):
     ds = native.Dataset(gpu_ctx, 16, 1)
     with pytest.raises(native.NativeError):       # empty data set
