@@ -775,12 +775,16 @@ int launch_op(const Shard& s, const typename Op::Args& args) { return launch_op_
 
 // launch configurations of the kernels that are FP64-issue-bound for the two-exponential family; overridable for the
 // A/B harness (tools/k2_ab.sh)
-// (gpurun_out/ab8.log, 1e9 rows: K1 2 rows per range-checked group 2.76 ms vs 2.99 with 4; K4 4 rows per group, 2 blocks
-// per SM, 8 rows per thread and chunk 3.88 ms vs 4.26)
+// (profiles/r1_k1_k4_ab_configs.log, 1e9 rows: K1 2 rows per range-checked group 2.76 ms vs 2.99 with 4, 2 blocks per SM
+// and 8 rows per thread and chunk 2.71, check-free with 4 rows per group 2.56; K4 4 rows per group, 2 blocks per SM,
+// 8 rows per thread and chunk 3.88 ms vs 4.26, check-free 3.63)
 #ifndef SO_K1_G
 #define SO_K1_G 2
-#define SO_K1_MINB 3
-#define SO_K1_RPT 4
+#define SO_K1_MINB 2
+#define SO_K1_RPT 8
+#endif
+#ifndef SO_K1_NC_G
+#define SO_K1_NC_G 4
 #endif
 #ifndef SO_K4_G
 #define SO_K4_G 4
@@ -794,6 +798,15 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
   switch (kind) {
     case kLossGrad: {
       if (want_grad) {
+        if constexpr (requires { Fam::args_in_range(pre, 0.0, 0.0); }) {
+          if (s.has_range && Fam::args_in_range(pre, s.tmin, s.tmax)) {      // check-free variant, see kNormalEq
+            using Opn = OpLossGrad<Fam, true, SO_K1_NC_G>;
+            typename Opn::Args an; an.pre = pre;
+            an.scale[0] = 0.5;
+            for (int i = 0; i < N; ++i) an.scale[1 + i] = -pre.D[i];
+            return launch_op_cfg<Opn, kThreads, SO_K1_MINB, 0, SO_K1_RPT, false, false>(s, an);
+          }
+        }
         using Op = OpLossGrad<Fam, true, SO_K1_G>;
         typename Op::Args a; a.pre = pre;
         a.scale[0] = 0.5;
@@ -876,6 +889,10 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       using Op = OpHessVec<Fam, SO_K4_G>;
       typename Op::Args a; a.pre = pre; a.h = Fam::hprepare(p, d);
       for (int i = 0; i < N; ++i) { a.dd[i] = pre.D[i] * d[i]; a.scale[i] = pre.D[i]; a.scale2[i] = -1.0; }
+      if constexpr (requires { Fam::args_in_range(pre, 0.0, 0.0); }) {
+        if (s.has_range && Fam::args_in_range(pre, s.tmin, s.tmax))
+          return launch_op_cfg<Op, kThreads, SO_K4_MINB, 0, SO_K4_RPT, false, false>(s, a);
+      }
       return launch_op_cfg<Op, kThreads, SO_K4_MINB, 0, SO_K4_RPT>(s, a);
     }
 #ifndef SO_SCALAR_MINIMAL

@@ -29,6 +29,7 @@ int main(int argc, char** argv) {
   so::Shard s; s.X = t; s.y = y; s.rows = rows; s.f = 1; s.partials = partials; s.partials_doubles = 148 * 8 * 64;
   s.out = out; s.out_doubles = 64; s.ticket = ticket;
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0); s.sm_count = prop.multiProcessorCount;
+  if (argc > 4 && atoi(argv[4])) { s.has_range = true; s.tmin = 0.0; s.tmax = 4.0; }     // inputs of k_fill: check-free K2
   const double p[5] = {1.9, 2.05, 0.52, 1.1, 0.45};
   const double d[5] = {0.3, -0.2, 0.1, 0.25, -0.15};
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
