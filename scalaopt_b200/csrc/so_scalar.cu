@@ -847,10 +847,16 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
         // every exp argument in range for this shard's inputs (known after launch_range): no per-row range check, and
         // then 4 rows per group are the better grouping (gpurun_out/ab5-7.log: 3.22 vs 3.31 ms per 1e9 rows)
         if (s.has_range && Fam::args_in_range(pre, s.tmin, s.tmax)) {
-          using Op4 = OpNormalEq<Fam, 4>;
+#ifndef SO_K2NC_G
+#define SO_K2NC_G 4
+#define SO_K2NC_TPB 256
+#define SO_K2NC_MINB 2
+#define SO_K2NC_RPT 8
+#endif
+          using Op4 = OpNormalEq<Fam, SO_K2NC_G>;
           typename Op4::Args a4; a4.pre = a.pre;
           for (int q2 = 0; q2 < Op4::Q; ++q2) { a4.scale[q2] = a.scale[q2]; a4.src[q2] = a.src[q2]; }
-          return launch_op_cfg<Op4, 256, 2, 0, 8, false, false>(s, a4);
+          return launch_op_cfg<Op4, SO_K2NC_TPB, SO_K2NC_MINB, 0, SO_K2NC_RPT, false, false>(s, a4);
         }
         using Op2 = OpNormalEq<Fam, SO_K2_G>;
         typename Op2::Args a2; a2.pre = a.pre;
