@@ -26,6 +26,8 @@ struct Shard {
   double tmin = 0.0, tmax = 0.0;
 };
 
+constexpr int SO_QR_WIDE_MAX_N = 8;     // TSQR of the linear-predictor families: n + 1 <= 9 columns per thread
+
 enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4, kNll = 5, kQr = 6 };
 
 // number of doubles each evaluation leaves in Shard::out (before the 1/m normalisation, which the

@@ -247,6 +247,7 @@ int launch_mapped(const Shard& s, const Params& P, int want_grad) {
 
 int launch_line(const Shard& s, int fam, const Params& P);                      // so_wide_line.cu
 int launch_gram(const Shard& s, int fam, const Params& P);                      // so_gram.cu
+int launch_qr(const Shard& s, int fam, const Params& P);                        // so_wide_qr.cu (n <= 8)
 size_t gram_partials_needed(int n, int f, int sm_count);                        // so_gram.cu
 
 }  // namespace wide
@@ -286,6 +287,8 @@ int launch_wide(Kind kind, const Shard& s, int family, const double* p, const do
       return launch_line(s, fam, P);
     case kNormalEq:
       return launch_gram(s, fam, P);
+    case kQr:
+      return n <= SO_QR_WIDE_MAX_N ? launch_qr(s, fam, P) : SO_EUNSUPPORTED;
     case kNll: break;      // single-input pdfs only (launch_nll)
   }
   return SO_EINVAL;

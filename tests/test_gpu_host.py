@@ -47,7 +47,7 @@ def test_gpu_objective_answers_the_objective_function_interface(native, oracle, 
     f.free(); ds.free()
 
 
-CASES = ["gauss_expbkg", "lm_spec_linear", "lm_spec_exponential", "expdecay_large", "poly"]
+CASES = ["gauss_expbkg", "lm_spec_linear", "lm_spec_exponential", "expdecay_large", "poly", "linear_small"]
 
 
 @pytest.mark.parametrize("mode", ["k2", "k2-speculative", "tsqr"])
@@ -57,12 +57,16 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
     sums serve the next Jacobian request; tsqr: the (n+1)-row system is the R factor from so_eval_qr."""
     tsqr, speculate = mode == "tsqr", mode != "k2"
     if tsqr and case == "lm_spec_linear":
-        pytest.skip("TSQR covers the single-input families")
+        pytest.skip("TSQR covers the single-input families and linear / logistic rows with n <= 8 (this case has n = 11)")
     if case == "gauss_expbkg":         # BASELINE config 3 at oracle-sized m
         fam, n = oracle.GAUSS_EXPBKG, 5
         truth = np.array([2.0, 0.5, 0.05, 1.0, 3.0])
         X, y = oracle.generate(fam, 200_000, 1, truth, noise_sigma=0.05)
         start = truth * 1.1
+    elif case == "linear_small":      # linear regression with intercept, n = 4: the narrow-row TSQR (so_wide_qr.cu)
+        fam, n = oracle.LINEAR, 4
+        X, y = oracle.generate(fam, 30_000, 3, [80.0, 0.0, 1.0, 2.0])
+        start = np.zeros(4)
     elif case == "lm_spec_linear":
         (X, y, start), _ = lm_spec_data(oracle)
         fam, n = oracle.LINEAR, 11

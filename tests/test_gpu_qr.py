@@ -55,6 +55,52 @@ def test_tsqr_matches_reference_qr_and_lapack(native, oracle, gpu_ctx, name, tru
     ds.free()
 
 
+WIDE_CASES = [("LINEAR", 1), ("LINEAR", 3), ("LINEAR", 7), ("LINEAR_NOINT", 2), ("LINEAR_NOINT", 4), ("LINEAR_NOINT", 8),
+              ("LOGISTIC", 2), ("LOGISTIC", 4), ("LOGISTIC", 7)]
+
+
+@pytest.mark.parametrize("name,f", WIDE_CASES)
+@pytest.mark.parametrize("m", [50_001, 11])
+def test_tsqr_of_the_narrow_linear_predictor_families(native, oracle, gpu_ctx, name, f, m):
+    """so_eval_qr for linear (+- intercept) and logistic rows with n <= 8: same three references as above."""
+    fam = getattr(oracle, name)
+    if name == "LINEAR":
+        truth = np.concatenate([[80.0], np.arange(f, dtype=float)])
+    elif name == "LINEAR_NOINT":
+        truth = np.arange(1, f + 1, dtype=float) / f
+    else:
+        truth = np.array([(((j % 7) - 3) / 4.0) for j in range(f + 1)])
+    X, y = oracle.generate(fam, m, f, truth)
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    p = truth * 0.9 + 0.05
+    n = p.size
+    R = ds.qr(fam, p)
+    assert gpu_ctx.stats().launches == 1
+    assert R.shape == (n + 1, n + 1) and np.all(np.tril(R, -1) == 0.0)
+    JtJ, Jtr, rtr = oracle.normal_eq(fam, X, y, p)
+    G = np.block([[JtJ, Jtr[:, None]], [Jtr[None, :], np.array([[rtr]])]])
+    scale = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
+    assert np.max(np.abs(R.T @ R - G) / scale) < 1e-11
+    ab = oracle.jacobian_matrix(fam, X, y, p)
+    q = oracle.qr(ab, n, pivoting=False)
+    Rn = _normalise(R)
+    Rref = q.Rmat()
+    sref = np.where(np.diag(Rref) < 0, -1.0, 1.0)
+    colnorm = np.sqrt(np.diag(JtJ))
+    np.testing.assert_allclose(Rn[:n, :n] / colnorm, (Rref * sref[:, None]) / colnorm, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(Rn[:n, n], q.qtb[:n] * sref, rtol=0, atol=1e-9 * np.sqrt(rtr))
+    Rl = _normalise(np.linalg.qr(ab, mode="r"))
+    np.testing.assert_allclose(Rn / np.append(colnorm, np.sqrt(rtr)), Rl / np.append(colnorm, np.sqrt(rtr)), rtol=0, atol=1e-9)
+    ds.free()
+
+
+def test_tsqr_beyond_the_catalogue_is_an_error(native, gpu_ctx):
+    ds = native.Dataset(gpu_ctx, 32, 9).append(np.ones((32, 9)), np.ones(32))
+    with pytest.raises(native.NativeError):
+        ds.qr(native.LINEAR_NOINT, np.ones(9))            # n = 9 > 8: no per-thread triangle of that size
+    ds.free()
+
+
 def test_tsqr_does_not_square_the_condition_number(native, oracle, gpu_ctx):
     """A degree-5 polynomial on t in [10, 10.5]: cond(J) ~ 1e11, so J^T J is numerically singular (cond ~ 1e22) and the
     Cholesky route loses everything, while Householder on the rows keeps R to cond * eps."""

@@ -121,7 +121,7 @@ def main():
                          (128, 100_000_000), (128, 1_000_000)):
                 truth = [(j + 1) / n for j in range(n)]
                 ds = run_family(ctx, f"cfg5 linear n={n} m={m:.0e}", native.LINEAR_NOINT, m, n, truth, 1.0,
-                                ["K1", "K2"], flops_gram=(n + 1) * (n + 2) + 0.0)
+                                ["K1", "K2"] + (["TSQR"] if n <= 8 else []), flops_gram=(n + 1) * (n + 2) + 0.0)
                 ds.free()
 
 
