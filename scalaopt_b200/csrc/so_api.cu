@@ -252,7 +252,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
   // the two-exponential family's K1/K2/K4 drop their per-row exp range check when the shard's inputs allow it: one
   // 8 B/row pass per data-set state (not per evaluation) finds their range
   const bool wants_range = !nll && family == SO_FAMILY_GAUSS_EXPBKG && ds->f == 1 &&
-                           (kind == kNormalEq || (kind == kLossGrad && want_grad) || kind == kHessVec);
+                           (kind == kNormalEq || (kind == kLossGrad && want_grad) || kind == kHessVec || kind == kLine);
   for (int g = 0; g < G && wants_range; ++g) {
     Device& dv = ctx->devs[g];
     ShardMem& sm = ds->shards[g];

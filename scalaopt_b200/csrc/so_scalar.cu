@@ -232,9 +232,9 @@ struct OpNormalEq {
   }
 };
 
-template <class Fam, int KB>
+template <class Fam, int KB, int GROUP = (KB <= 1 ? 4 : (KB <= 2 ? 2 : 1))>
 struct OpLine {
-  static constexpr int N = Fam::N, Q = 2 * KB, NEXP = KB * Fam::NE, G = (KB <= 1 ? 4 : (KB <= 2 ? 2 : 1));
+  static constexpr int N = Fam::N, Q = 2 * KB, NEXP = KB * Fam::NE, G = GROUP;
   static constexpr bool kHasSrc = false;
   static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre[KB]; double dd[KB][N]; double scale[Q]; };   // dd = D(p + alpha d) o d
@@ -651,11 +651,21 @@ int launch_op(const Shard& s, const typename Op::Args& args) { return launch_op_
 #ifndef SO_K1_NC_G
 #define SO_K1_NC_G 4
 #endif
+#ifndef SO_K3_G1
+#define SO_K3_G1 4      // rows per range-checked group of the line kernels with 1 / 2 step sizes per pass
+#define SO_K3_G2 2
+#endif
 #ifndef SO_K4_G
 #define SO_K4_G 4
 #define SO_K4_MINB 2
 #define SO_K4_RPT 8
 #endif
+// families that can tell from the input range that no exp argument leaves the fast path's domain
+template <class Fam> constexpr bool kFamHasRange = requires(const typename Fam::Pre& c) { Fam::args_in_range(c, 0.0, 0.0); };
+template <class Fam> bool fam_in_range(const typename Fam::Pre& c, double lo, double hi) {
+  if constexpr (kFamHasRange<Fam>) return Fam::args_in_range(c, lo, hi);
+  else return false;
+}
 template <class Fam>
 int launch_family(Kind kind, const Shard& s, const double* p, const double* d, const double* alpha, int k, int want_grad) {
   constexpr int N = Fam::N;
@@ -730,16 +740,17 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       }
       return launch_op<Op, (Op::Q < 21 ? 3 : 2)>(s, a);
     }
-#ifndef SO_SCALAR_MINIMAL
     case kLine: {
       // batches of up to 8 step sizes per pass; longer schedules take several passes into consecutive out slots
       // (the API layer asks for at most 8 per call for these families)
       if (k < 1 || k > 8) return SO_EINVAL;
       auto run = [&](auto KBtag) -> int {
         constexpr int KB = decltype(KBtag)::value;
-        using Op = OpLine<Fam, KB>;
+        constexpr int GR = KB <= 1 ? SO_K3_G1 : (KB <= 2 ? SO_K3_G2 : 1);
+        using Op = OpLine<Fam, KB, GR>;
         typename Op::Args a;
         double pk[N];
+        bool in_range = s.has_range;
         for (int kk = 0; kk < KB; ++kk) {
           const double al = alpha[kk < k ? kk : k - 1];          // pad by repeating the last step size
           for (int i = 0; i < N; ++i) pk[i] = p[i] + d[i] * al;  // ptInit.x + ptInit.d * a1, StrongWolfe.scala:97
@@ -747,15 +758,19 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
           for (int i = 0; i < N; ++i) a.dd[kk][i] = a.pre[kk].D[i] * d[i];
           a.scale[kk] = 0.5;
           a.scale[KB + kk] = -1.0;
+          in_range = in_range && fam_in_range<Fam>(a.pre[kk], s.tmin, s.tmax);
         }
-        return launch_op<Op, (KB >= 8 ? 1 : 2)>(s, a);
+        constexpr int MB = KB >= 8 ? 1 : 2, RP = 8;
+        if constexpr (kFamHasRange<Fam>) {
+          if (in_range) return launch_op_cfg<Op, kThreads, MB, 0, RP, false, false>(s, a);     // check-free, see kNormalEq
+        }
+        return launch_op_cfg<Op, kThreads, MB, 0, RP>(s, a);
       };
       if (k == 1) return run(std::integral_constant<int, 1>());
       if (k == 2) return run(std::integral_constant<int, 2>());
       if (k <= 4) return run(std::integral_constant<int, 4>());
       return run(std::integral_constant<int, 8>());
     }
-#endif
     case kHessVec: {
       using Op = OpHessVec<Fam, SO_K4_G>;
       typename Op::Args a; a.pre = pre; a.h = Fam::hprepare(p, d);

@@ -31,20 +31,22 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0); s.sm_count = prop.multiProcessorCount;
   if (argc > 4 && atoi(argv[4])) { s.has_range = true; s.tmin = 0.0; s.tmax = 4.0; }     // inputs of k_fill: check-free K2
   const double p[5] = {1.9, 2.05, 0.52, 1.1, 0.45};
-  const double d[5] = {0.3, -0.2, 0.1, 0.25, -0.15};
+  const double d[5] = {0.03, -0.02, 0.01, 0.025, -0.015};
+  const double alphas[8] = {0.5, 1.0, 0.25, 2.0, 0.125, 1.5, 0.75, 3.0};
+  const int nalpha = argc > 6 ? atoi(argv[6]) : 1;         // kind 3 (K3 line search): step sizes per pass
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   std::vector<float> ms;
   const int launches = argc > 5 ? atoi(argv[5]) : 23;      // > 23: sustained (power-capped) behaviour, mean of the last 2/3
   for (int r = 0; r < launches; ++r) {
     cudaEventRecord(e0);
-    const int rc = so::launch_scalar((so::Kind)kind, s, SO_FAMILY_GAUSS_EXPBKG, p, d, 5, nullptr, 0, 1);
+    const int rc = so::launch_scalar((so::Kind)kind, s, SO_FAMILY_GAUSS_EXPBKG, p, d, 5, alphas, kind == 3 ? nalpha : 0, 1);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     if (rc <= 0 || cudaGetLastError() != cudaSuccess) { printf("launch failed rc=%d\n", rc); return 1; }
     float m; cudaEventElapsedTime(&m, e0, e1); if (r >= (launches > 23 ? launches / 3 : 3)) ms.push_back(m);
   }
   double mean = 0; for (float m : ms) mean += m; mean /= ms.size();
   std::sort(ms.begin(), ms.end());
-  const int Q = kind == 2 ? 21 : (kind == 1 ? 6 : 5);
+  const int Q = kind == 2 ? 21 : (kind == 1 ? 6 : (kind == 3 ? 2 * so::scalar_line_block(nalpha) : 5));
   double h[21] = {0}; cudaMemcpy(h, out, sizeof(double) * Q, cudaMemcpyDeviceToHost);
   double cs = 0; for (int i = 0; i < Q; ++i) cs += h[i] * (i + 1);
   printf("{\"variant\": \"%s\", \"rows\": %lld, \"ms_best\": %.4f, \"ms_median\": %.4f, \"ms_mean\": %.4f, \"gbs_median\": %.1f, \"checksum\": %.17g, \"last\": %.17g}\n",

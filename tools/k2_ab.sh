@@ -11,5 +11,5 @@ if [ "$1" = build ]; then
   done
   wait
 else
-  for rep in 1 2; do for v in $VARIANTS; do name=${v%%:*}; ./ab/k2_$name ${ROWS:-1000000000} $name ${KIND:-2} ${RANGE:-0} ${LAUNCHES:-23}; done; done
+  for rep in 1 2; do for v in $VARIANTS; do name=${v%%:*}; ./ab/k2_$name ${ROWS:-1000000000} $name ${KIND:-2} ${RANGE:-0} ${LAUNCHES:-23} ${NALPHA:-1}; done; done
 fi
