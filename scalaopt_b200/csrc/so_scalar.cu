@@ -54,6 +54,8 @@ struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarqua
     f = c.p0 * ex[0];
   }
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) { return fma(-c.p0, ex[0], y); }
+  // sum_i dd_i u_i without forming u (the line-search kernel needs only this combination): Horner in t
+  __device__ static __forceinline__ double dirder(const Pre&, const double* dd, double t, const double* ex) { return ex[0] * fma(t, dd[1], dd[0]); }
   // B_i += rho * (d2f/dp2 . d)_i :  h0 = t e d1,  h1 = t e d0 + p0 t^2 e d1
   struct HPre { double d0, d1, p0d1; };
   static HPre hprepare(const double* p, const double* d) { HPre h; h.d0 = d[0]; h.d1 = d[1]; h.p0d1 = p[0] * d[1]; return h; }
@@ -86,6 +88,10 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
     f = c.A * ex[0];
   }
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) { return fma(-c.A, ex[0], y); }
+  __device__ static __forceinline__ double dirder(const Pre& c, const double* dd, double t, const double* ex) {
+    const double zz = fma(t, c.sr2, c.nmsr2);
+    return ex[0] * fma(zz, fma(zz, dd[2], dd[1]), dd[0]);          // g (dd0 + zz dd1 + zz^2 dd2)
+  }
   // B_i += rho * (d2f/dp2 . d)_i in Horner form in v = zz = z/sqrt2 with host-side coefficients (see hprepare):
   //   h0 = g v (a0 + a1 v),  h1 = g (b0 + v (b1 + v (b2 + v b3))),  h2 = g v (c0 + v (c1 + v (c2 + v c3)))
   struct HGauss { double a0, a1, b0, b1, b2, b3, c0, c1, c2, c3; };
@@ -138,6 +144,11 @@ struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),
   // y - f in two FMAs (the accumulating kernels only need the residual)
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) {
     return fma(-c.B, ex[1], fma(-c.A, ex[0], y));
+  }
+  __device__ static __forceinline__ double dirder(const Pre& c, const double* dd, double t, const double* ex) {
+    const double zz = fma(t, c.sr2, c.nmsr2);
+    const double h1 = fma(zz, fma(zz, dd[2], dd[1]), dd[0]), h2 = fma(t, dd[4], dd[3]);
+    return fma(ex[0], h1, ex[1] * h2);                             // g (dd0 + zz dd1 + zz^2 dd2) + e (dd3 + t dd4): 5 instead of 3 + 5
   }
   // true when both exp arguments stay inside (-700, 700) for every t in [tmin, tmax] (they are monotone or convex in t,
   // so the end points decide); NaN anywhere compares false.  708 is the limit of so_exp_fast: 1 % of margin for rounding.
@@ -245,12 +256,18 @@ struct OpLine {
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
-      double f, u[N];
-      Fam::finish(a.pre[k], t, ex + k * Fam::NE, f, u);
-      const double rho = Fam::residual(a.pre[k], y, ex + k * Fam::NE, f);
-      double jd = 0.0;
+      double rho, jd;
+      if constexpr (requires { Fam::dirder(a.pre[k], a.dd[k], t, ex); }) {     // residual from the exponentials, J.d in Horner form
+        rho = Fam::residual(a.pre[k], y, ex + k * Fam::NE, 0.0);
+        jd = Fam::dirder(a.pre[k], a.dd[k], t, ex + k * Fam::NE);
+      } else {
+        double f, u[N];
+        Fam::finish(a.pre[k], t, ex + k * Fam::NE, f, u);
+        rho = Fam::residual(a.pre[k], y, ex + k * Fam::NE, f);
+        jd = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) jd = fma(a.dd[k][i], u[i], jd);
+        for (int i = 0; i < N; ++i) jd = fma(a.dd[k][i], u[i], jd);
+      }
       acc[k] = fma(rho, rho, acc[k]);
       acc[KB + k] = fma(rho, jd, acc[KB + k]);
     }
