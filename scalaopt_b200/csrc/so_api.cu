@@ -249,10 +249,10 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
     if (rc0) return rc0;
     if (m_global < 1) return fail(ctx, SO_ESTATE, "data set is empty");
   }
-  // the two-exponential family's K1/K2/K4 drop their per-row exp range check when the shard's inputs allow it: one
+  // the two-exponential family's K1-K4 and the likelihood kernel drop their per-row exp range check when the shard's inputs allow it: one
   // 8 B/row pass per data-set state (not per evaluation) finds their range
-  const bool wants_range = !nll && family == SO_FAMILY_GAUSS_EXPBKG && ds->f == 1 &&
-                           (kind == kNormalEq || (kind == kLossGrad && want_grad) || kind == kHessVec || kind == kLine);
+  const bool wants_range = ds->f == 1 && (nll ? true : family == SO_FAMILY_GAUSS_EXPBKG &&
+                           (kind == kNormalEq || (kind == kLossGrad && want_grad) || kind == kHessVec || kind == kLine));
   for (int g = 0; g < G && wants_range; ++g) {
     Device& dv = ctx->devs[g];
     ShardMem& sm = ds->shards[g];

@@ -324,13 +324,19 @@ struct PdfGaussExpBkg {
     a[1] = fma(x, c.nlam, c.lamx);               // -lambda (x - xMin)
   }
   __device__ static __forceinline__ double value(const Pre& c, const double* ex) { return fma(c.cS, ex[0], c.cB * ex[1]); }
+  // both exp arguments inside (-700, 700) for every x in [xmin, xmax] (end points decide); NaN compares false
+  static bool args_in_range(const Pre& c, double xmin, double xmax) {
+    const double z0 = std::fabs(xmin * c.sr2 + c.nmsr2), z1 = std::fabs(xmax * c.sr2 + c.nmsr2), zm = z0 > z1 ? z0 : z1;
+    const double b0 = std::fabs(xmin * c.nlam + c.lamx), b1 = std::fabs(xmax * c.nlam + c.lamx);
+    return zm * zm < 700.0 && b0 < 700.0 && b1 < 700.0;
+  }
 };
 
-template <class Pdf>
+template <class Pdf, int GROUP = 4>
 struct OpNll {
   // acc[0] = product of pdf mantissas (renormalised), acc[1] = exponent sum (as an integer in the low word),
   // acc[2] = sum of logs taken on the slow path; finalize() folds them into acc[0] = sum log pdf
-  static constexpr int Q = 3, NEXP = Pdf::NE, G = 4;
+  static constexpr int Q = 3, NEXP = Pdf::NE, G = GROUP;
   static constexpr bool kHasSrc = false, kNeedsY = false;
   struct Args { typename Pdf::Pre pre; double scale[Q]; };
   __device__ static __forceinline__ void init(double (&acc)[Q]) { acc[0] = 1.0; acc[1] = 0.0; acc[2] = 0.0; }
@@ -868,20 +874,29 @@ size_t scalar_partials_needed(Kind kind, int n, int k, int sm_count) {
   return (size_t)sm_count * 8 * (size_t)Q;
 }
 
-int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* consts, int nconsts) {
-#ifdef SO_SCALAR_MINIMAL
-  return SO_EUNSUPPORTED;
+#ifndef SO_NLL_G
+#define SO_NLL_G 2      // gpurun_out/ab11.log: 2 rows per checked group 2.36 ms vs 2.56 with 4; check-free with 4: 2.27 ms per 1e9 rows
+#define SO_NLL_MINB 3
+#define SO_NLL_RPT 4
+#define SO_NLL_NC_G 4
 #endif
+int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* consts, int nconsts) {
   if (s.f != 1) return SO_EINVAL;
   if (pdf != SO_PDF_GAUSS_EXPBKG) return SO_EUNSUPPORTED;
   if (n != 4 || nconsts < 1 || !consts) return SO_EINVAL;
-  using Op = OpNll<PdfGaussExpBkg>;
+  const PdfGaussExpBkg::Pre pre = PdfGaussExpBkg::prepare(p, consts);
+  // FP64-issue-bound (two exponentials per 8-byte observation: 22 FP64 + ~20 other instructions/row)
+  if (s.has_range && PdfGaussExpBkg::args_in_range(pre, s.tmin, s.tmax)) {       // check-free, see kNormalEq
+    using Opn = OpNll<PdfGaussExpBkg, SO_NLL_NC_G>;
+    Opn::Args an; an.pre = pre;
+    an.scale[0] = -2.0; an.scale[1] = 0.0; an.scale[2] = 0.0;
+    return launch_op_cfg<Opn, kThreads, SO_NLL_MINB, 0, SO_NLL_RPT, false, false>(s, an);
+  }
+  using Op = OpNll<PdfGaussExpBkg, SO_NLL_G>;
   Op::Args a;
-  a.pre = PdfGaussExpBkg::prepare(p, consts);
+  a.pre = pre;
   a.scale[0] = -2.0; a.scale[1] = 0.0; a.scale[2] = 0.0;       // sum - 2.0 * Math.log(pdf)
-  // FP64-issue-bound (two exponentials per 8-byte observation: 24 FP64 instructions/row); 8 rows per chunk or 2/4
-  // blocks per SM measured within 5 % of this configuration
-  return launch_op_cfg<Op, kThreads, 3, 0, 4>(s, a);
+  return launch_op_cfg<Op, kThreads, SO_NLL_MINB, 0, SO_NLL_RPT>(s, a);
 }
 
 // padded width of the kLine result for the scalar families (so_api reads phi at [0,k) and dphi at [KB, KB+k))

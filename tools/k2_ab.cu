@@ -39,14 +39,15 @@ int main(int argc, char** argv) {
   const int launches = argc > 5 ? atoi(argv[5]) : 23;      // > 23: sustained (power-capped) behaviour, mean of the last 2/3
   for (int r = 0; r < launches; ++r) {
     cudaEventRecord(e0);
-    const int rc = so::launch_scalar((so::Kind)kind, s, SO_FAMILY_GAUSS_EXPBKG, p, d, 5, alphas, kind == 3 ? nalpha : 0, 1);
+    const double pn[4] = {0.3, 2.0, 0.5, 0.5}, cn[1] = {0.0};
+    const int rc = kind == 5 ? so::launch_nll(s, SO_PDF_GAUSS_EXPBKG, pn, 4, cn, 1) : so::launch_scalar((so::Kind)kind, s, SO_FAMILY_GAUSS_EXPBKG, p, d, 5, alphas, kind == 3 ? nalpha : 0, 1);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     if (rc <= 0 || cudaGetLastError() != cudaSuccess) { printf("launch failed rc=%d\n", rc); return 1; }
     float m; cudaEventElapsedTime(&m, e0, e1); if (r >= (launches > 23 ? launches / 3 : 3)) ms.push_back(m);
   }
   double mean = 0; for (float m : ms) mean += m; mean /= ms.size();
   std::sort(ms.begin(), ms.end());
-  const int Q = kind == 2 ? 21 : (kind == 1 ? 6 : (kind == 3 ? 2 * so::scalar_line_block(nalpha) : 5));
+  const int Q = kind == 2 ? 21 : (kind == 1 ? 6 : (kind == 3 ? 2 * so::scalar_line_block(nalpha) : (kind == 5 ? 1 : 5)));
   double h[21] = {0}; cudaMemcpy(h, out, sizeof(double) * Q, cudaMemcpyDeviceToHost);
   double cs = 0; for (int i = 0; i < Q; ++i) cs += h[i] * (i + 1);
   printf("{\"variant\": \"%s\", \"rows\": %lld, \"ms_best\": %.4f, \"ms_median\": %.4f, \"ms_mean\": %.4f, \"gbs_median\": %.1f, \"checksum\": %.17g, \"last\": %.17g}\n",
