@@ -804,15 +804,21 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       }
       return launch_op_cfg<Op, kThreads, SO_K4_MINB, 0, SO_K4_RPT>(s, a);
     }
-#ifndef SO_SCALAR_MINIMAL
     case kQr: {
       using Op = OpQr<Fam>;
       typename Op::Args a; a.pre = pre;
       for (int i = 0; i < N; ++i) a.scale[i] = -pre.D[i];          // J = -sign(rho) df/dp, r = |rho|: rows +-(-D u | rho)
       a.scale[N] = 1.0;
-      return launch_op_cfg<Op, 256, 1, 0, 8>(s, a);
-    }
+      // C <= 6 columns (<= 170 registers): 3 blocks of 128 threads per SM = 12 warps instead of one block of 8
+      // (n = 5 on 1e9 rows: 7.74 vs 8.53 ms; 2 x 192 threads 8.27, 4 x 96 8.19, 6 x 64 8.23); wider triangles need the
+      // whole register file of one 256-thread block
+#ifdef SO_QR_TPB
+      return launch_op_cfg<Op, SO_QR_TPB, SO_QR_MINB, 0, 8>(s, a);
+#else
+      if constexpr (Op::C <= 6) return launch_op_cfg<Op, 128, 3, 0, 8>(s, a);
+      else return launch_op_cfg<Op, 256, 1, 0, 8>(s, a);
 #endif
+    }
     default: break;        // kNll is served by launch_nll
   }
   return SO_EINVAL;

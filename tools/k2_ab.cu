@@ -47,8 +47,8 @@ int main(int argc, char** argv) {
   }
   double mean = 0; for (float m : ms) mean += m; mean /= ms.size();
   std::sort(ms.begin(), ms.end());
-  const int Q = kind == 2 ? 21 : (kind == 1 ? 6 : (kind == 3 ? 2 * so::scalar_line_block(nalpha) : (kind == 5 ? 1 : 5)));
-  double h[21] = {0}; cudaMemcpy(h, out, sizeof(double) * Q, cudaMemcpyDeviceToHost);
+  const int Q = kind == 2 ? 21 : (kind == 1 ? 6 : (kind == 3 ? 2 * so::scalar_line_block(nalpha) : (kind == 5 ? 1 : (kind == 6 ? 36 : 5))));
+  double h[64] = {0}; cudaMemcpy(h, out, sizeof(double) * Q, cudaMemcpyDeviceToHost);
   double cs = 0; for (int i = 0; i < Q; ++i) cs += h[i] * (i + 1);
   printf("{\"variant\": \"%s\", \"rows\": %lld, \"ms_best\": %.4f, \"ms_median\": %.4f, \"ms_mean\": %.4f, \"gbs_median\": %.1f, \"checksum\": %.17g, \"last\": %.17g}\n",
          name, (long long)rows, ms.front(), ms[ms.size() / 2], mean, rows * 16e-6 / ms[ms.size() / 2], cs, h[Q - 1]);
