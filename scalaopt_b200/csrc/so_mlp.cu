@@ -43,16 +43,28 @@ k_mlp(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, 
 #pragma unroll
     for (int i = 0; i < F; ++i) x[i] = ld_stream(X + row * F + i);
     const double yv = ld_stream(y + row);
-    double o[H], E = 0.0;
+    double o[H], E = 0.0, ej[H], exj[H];
+    bool ok = true;
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       double e = 0.0;
 #pragma unroll
       for (int i = 0; i < F; ++i) e = fma(x[i], W.w[j][1 + i], e);
       e += W.w[j][0];                               // weights(0) + (inputs dot weights.tail), Neuron.scala:42-43
-      const double ex = so_exp(-fabs(e));
-      const double inv = so_rcp_fast(1.0 + ex);
-      o[j] = e >= 0.0 ? inv : ex * inv;
+      ej[j] = e;
+      ok = ok && exp_in_range(e);
+    }
+    if (ok) {                                       // one range check for the hidden layer: the H exponentials run branch-free
+#pragma unroll
+      for (int j = 0; j < H; ++j) exj[j] = so_exp_fast(-fabs(ej[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < H; ++j) exj[j] = exp_slow(-fabs(ej[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const double inv = so_rcp_fast(1.0 + exj[j]);
+      o[j] = ej[j] >= 0.0 ? inv : exj[j] * inv;
       E = fma(o[j], W.v[1 + j], E);
     }
     E += W.v[0];
