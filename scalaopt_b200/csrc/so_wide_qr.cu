@@ -18,12 +18,12 @@ namespace so {
 namespace wide {
 namespace {
 
-template <int FAM, int NP, int ICPT>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int FAM, int NP, int ICPT, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
 k_qr_small(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
            double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   constexpr int C = NP + 1, Q = C * (C + 1) / 2, F = NP - ICPT, B = C <= 6 ? 8 : 4;
-  __shared__ double s_red[kWarps * Q];
+  __shared__ double s_red[(TPB / 32) * Q];
   __shared__ double s_scale[C];
   if (FAM == kLogistic) exp_table_init();
   if (threadIdx.x < C) s_scale[threadIdx.x] = (threadIdx.x < NP && FAM == kLinear) ? -1.0 : 1.0;
@@ -34,8 +34,8 @@ k_qr_small(const double* __restrict__ X, const double* __restrict__ y, int64_t r
   double p[NP];
 #pragma unroll
   for (int i = 0; i < NP; ++i) p[i] = P.p[i];
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t row0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; row0 < rows; row0 += B * stride) {
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  for (int64_t row0 = (int64_t)blockIdx.x * TPB + threadIdx.x; row0 < rows; row0 += B * stride) {
     double a[B][C];
     static_for<B>([&](auto I) {
       constexpr int i = decltype(I)::value;
@@ -65,12 +65,14 @@ k_qr_small(const double* __restrict__ X, const double* __restrict__ y, int64_t r
 
 template <int FAM, int NP, int ICPT>
 int launch_qr_cfg(const Shard& s, const Params& P) {
-  auto kern = k_qr_small<FAM, NP, ICPT>;
-  constexpr int C = NP + 1, Q = C * (C + 1) / 2;
-  const int64_t want = std::max<int64_t>(1, (s.rows + kThreads - 1) / kThreads);
-  const int grid = (int)std::min<int64_t>(want, (int64_t)s.sm_count);          // one block per SM (register-heavy)
+  // up to 6 columns: 3 blocks of 128 threads per SM (12 warps) instead of one block of 256 (as for the single-input
+  // families, so_scalar.cu); wider triangles need the whole register file of one 256-thread block
+  constexpr int C = NP + 1, Q = C * (C + 1) / 2, TPB = C <= 6 ? 128 : 256, MINB = C <= 6 ? 3 : 1;
+  auto kern = k_qr_small<FAM, NP, ICPT, TPB, MINB>;
+  const int64_t want = std::max<int64_t>(1, (s.rows + TPB - 1) / TPB);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)s.sm_count * MINB);
   if ((size_t)grid * Q > s.partials_doubles || (size_t)C * C > s.out_doubles) return SO_ENOMEM;
-  kern<<<grid, kThreads, 0, s.stream>>>(s.X, s.y, s.rows, P, s.partials, s.out, s.ticket);
+  kern<<<grid, TPB, 0, s.stream>>>(s.X, s.y, s.rows, P, s.partials, s.out, s.ticket);
   return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
 }
 
