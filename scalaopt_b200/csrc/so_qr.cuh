@@ -32,11 +32,27 @@ __device__ __forceinline__ double fast_sqrt(double x) {
   return fma(0.5 * r, fma(-sq, sq, x), sq);     // one correction step on sqrt itself
 }
 
-// zero, subnormal or huge column norms: IEEE sqrt and division, out of line
-__device__ __noinline__ void householder_slow(double t2, double rjj, double& nrm, double& beta) {
-  nrm = t2 > 0.0 ? sqrt(t2) : 0.0;
+// Columns whose squared norm is outside [1e-280, 1e280] (zero, subnormal, tiny next to nothing, or huge) take this
+// path.  A Householder reflection depends only on the DIRECTION of v = (R_jj - alpha; a_:j), so the column is first
+// multiplied by an exact power of two that brings its largest entry near 1; norm, alpha, vp and beta are then formed
+// from the scaled column with IEEE sqrt and division, out of line, and alpha goes back to the column's own scale.
+// Without the rescaling 2 / v.v overflows for a column of size ~1e-160 and below — e.g. the rounding residue a far
+// Gaussian tail leaves in a column after the previous reflection (found by
+// tests/test_gpu_scalar.py::test_two_exponential_family_at_random_parameters: NaN triangles).
+__device__ __noinline__ double householder_scale(double amax, int& e) {
+  e = 0;
+  if (!(amax > 0.0) || !(amax < 1.0e308)) return 1.0;      // zero column; inf / NaN: left to propagate through the products
+  (void)frexp(amax, &e);                                   // amax = m 2^e, m in [0.5, 1)
+  e = e < -1000 ? -1000 : (e > 1000 ? 1000 : e);
+  return ldexp(1.0, -e);
+}
+__device__ __noinline__ void householder_slow(double t2, double rjj, int e, double& alpha, double& vp, double& beta) {
+  const double nrm = t2 > 0.0 ? sqrt(t2) : 0.0;
   const double den = nrm * (nrm + fabs(rjj));
   beta = den > 0.0 ? 1.0 / den : 0.0;
+  const double as = rjj > 0.0 ? -nrm : nrm;
+  vp = rjj - as;
+  alpha = ldexp(as, e);
 }
 
 // compile-time loops: every index of R[] and a[][] below is a constant expression whatever the unroller decides
@@ -53,15 +69,22 @@ __device__ __forceinline__ void qr_fold(double (&R)[C * (C + 1) / 2], double (&a
     static_for<B>([&](auto I) { constexpr int i = decltype(I)::value; sigma = fma(a[i][j], a[i][j], sigma); });
     const double rjj = R[tri_idx<C>(j, j)];
     const double t2 = fma(rjj, rjj, sigma);
-    double nrm, beta;
+    double alpha, vp, beta;
     if (t2 > 1.0e-280 && t2 < 1.0e280) {                   // the MUFU seeds flush subnormals: normal range only
-      nrm = fast_sqrt(t2);
+      const double nrm = fast_sqrt(t2);
       beta = fast_rcp(nrm * (nrm + fabs(rjj)));            // 2 / v.v,  v.v = -2 alpha vp = 2 nrm (nrm + |R_jj|)
-    } else {
-      householder_slow(t2, rjj, nrm, beta);
+      alpha = rjj > 0.0 ? -nrm : nrm;                      // -sign(R_jj) ||(R_jj; a_:j)||: no cancellation in vp
+      vp = rjj - alpha;
+    } else {                                               // rare: rescaled reflector (see householder_scale)
+      double amax = fabs(rjj);
+      static_for<B>([&](auto I) { constexpr int i = decltype(I)::value; amax = fmax(amax, fabs(a[i][j])); });
+      int e;
+      const double sc = householder_scale(amax, e);
+      const double rs = rjj * sc;
+      double sig = 0.0;
+      static_for<B>([&](auto I) { constexpr int i = decltype(I)::value; a[i][j] *= sc; sig = fma(a[i][j], a[i][j], sig); });
+      householder_slow(fma(rs, rs, sig), rs, e, alpha, vp, beta);
     }
-    const double alpha = rjj > 0.0 ? -nrm : nrm;           // -sign(R_jj) ||(R_jj; a_:j)||: no cancellation in vp
-    const double vp = rjj - alpha;
     R[tri_idx<C>(j, j)] = alpha;
     static_for<C - 1 - j>([&](auto K) {
       constexpr int k = j + 1 + decltype(K)::value;

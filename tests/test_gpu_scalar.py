@@ -158,6 +158,46 @@ def test_normal_equations_pick_the_exp_range_check_from_the_input_range(native, 
     ds.free()
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_two_exponential_family_at_random_parameters(native, oracle, gpu_ctx, seed):
+    """K1-K4 and the TSQR at parameter vectors drawn around (and far from) the truth, on inputs spread over [-3, 5]:
+    some draws keep every exp argument in the fast path's range (check-free kernels), some do not (checked kernels,
+    libdevice exp for the far rows) — the choice must never show in the sums."""
+    fam = oracle.GAUSS_EXPBKG
+    rng = np.random.default_rng(1000 + seed)
+    m = 4001
+    truth = np.array([2.0, 0.5, 0.05, 1.0, 3.0])
+    X = rng.uniform(-3.0, 5.0, size=(m, 1))
+    t = X[:, 0]
+    y = truth[0] * np.exp(-0.5 * ((t - truth[1]) / truth[2]) ** 2) + truth[3] * np.exp(-truth[4] * t) + 0.05 * rng.standard_normal(m)
+    scale = [1.0, 1.0, 10.0 ** rng.uniform(-2.5, 1.0), 1.0, 10.0 ** rng.uniform(-1.0, 1.0)]     # sigma, lambda over decades
+    p = truth * np.array(scale) * rng.uniform(0.8, 1.2, size=5)
+    if seed % 3 == 0:
+        p[4] = -abs(p[4]) * 0.3                                  # growing background: positive exp arguments
+    ds = _upload(native, gpu_ctx, X, y)
+    with np.errstate(over="ignore", invalid="ignore"):
+        loss_o = oracle.apply(fam, X, y, p)
+        JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p)
+    if not (np.isfinite(loss_o) and np.all(np.isfinite(JtJ_o)) and np.all(np.isfinite(Jtr_o)) and np.abs(JtJ_o).max() < 1e140):
+        ds.free(); pytest.skip("the reference overflows (or its sums cannot be squared by the comparison) at this draw")
+    loss, grad = ds.loss_grad(fam, p)
+    assert_loss(loss, loss_o)
+    assert_vec(grad, oracle.gradient(fam, X, y, p), rtol=1e-11)
+    JtJ, Jtr, rtr = ds.normal_eq(fam, p)
+    assert np.all(np.isfinite(JtJ)) and np.all(np.isfinite(Jtr)), (p, JtJ)
+    assert_gram(JtJ, JtJ_o); assert_vec(Jtr, Jtr_o, rtol=1e-11, what="Jtr"); assert_loss(rtr, rtr_o)
+    d = rng.standard_normal(5) * 0.01 * np.abs(p)
+    phi, dphi = ds.line(fam, p, d, [0.0, 0.5, 1.0])
+    phi_o, dphi_o = oracle.line(fam, X, y, p, d, [0.0, 0.5, 1.0])
+    assert_vec(phi, phi_o, what="phi"); assert_vec(dphi, dphi_o, rtol=1e-10, what="dphi")
+    assert_vec(ds.hess_vec(fam, p, d), oracle.hess_vec(fam, X, y, p, d), rtol=1e-10, what="Hd")
+    R = ds.qr(fam, p)
+    G = np.block([[JtJ_o, Jtr_o[:, None]], [Jtr_o[None, :], np.array([[rtr_o]])]])
+    sc = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
+    assert np.max(np.abs(R.T @ R - G) / sc) < 1e-10
+    ds.free()
+
+
 def test_errors_are_reported_not_swallowed(native, gpu_ctx):
     ds = native.Dataset(gpu_ctx, 16, 1)
     with pytest.raises(native.NativeError):       # empty data set
