@@ -198,6 +198,52 @@ def test_two_exponential_family_at_random_parameters(native, oracle, gpu_ctx, se
     ds.free()
 
 
+@pytest.mark.parametrize("name", ["GAUSS", "EXPDECAY", "POLY"])
+@pytest.mark.parametrize("seed", range(6))
+def test_other_single_input_families_at_random_parameters(native, oracle, gpu_ctx, name, seed):
+    """same idea for the one-exponential families and the polynomial: inputs over [-3, 5], widths / rates over decades"""
+    fam = getattr(oracle, name)
+    rng = np.random.default_rng(2000 + seed)
+    m = 3001
+    t = rng.uniform(-3.0, 5.0, size=m)
+    if name == "GAUSS":
+        truth = np.array([2.0, 0.5, 0.3])
+        y = truth[0] * np.exp(-0.5 * ((t - truth[1]) / truth[2]) ** 2)
+        p = truth * np.array([1.0, 1.0, 10.0 ** rng.uniform(-2.5, 1.0)]) * rng.uniform(0.8, 1.2, size=3)
+    elif name == "EXPDECAY":
+        truth = np.array([2.0, -1.3])
+        y = truth[0] * np.exp(truth[1] * t)
+        p = truth * np.array([1.0, 10.0 ** rng.uniform(-1.0, 1.3)]) * rng.uniform(0.8, 1.2, size=2) * (1.0 if seed % 2 else -1.0)
+    else:
+        truth = np.array([1.0, -2.0, 0.5, 3.0, -0.25])
+        y = sum(c * t ** k for k, c in enumerate(truth))
+        p = truth * 10.0 ** rng.uniform(-2.0, 2.0, size=5) * rng.choice([-1.0, 1.0], size=5)
+    y = y + 0.05 * rng.standard_normal(m)
+    X = t.reshape(-1, 1)
+    n = p.size
+    with np.errstate(over="ignore", invalid="ignore"):
+        loss_o = oracle.apply(fam, X, y, p)
+        JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p)
+    if not (np.isfinite(loss_o) and np.all(np.isfinite(JtJ_o)) and np.all(np.isfinite(Jtr_o)) and np.abs(JtJ_o).max() < 1e140):
+        pytest.skip("the reference overflows at this draw")
+    ds = _upload(native, gpu_ctx, X, y)
+    loss, grad = ds.loss_grad(fam, p)
+    assert_loss(loss, loss_o)
+    assert_vec(grad, oracle.gradient(fam, X, y, p), rtol=1e-11)
+    JtJ, Jtr, rtr = ds.normal_eq(fam, p)
+    assert_gram(JtJ, JtJ_o); assert_vec(Jtr, Jtr_o, rtol=1e-11, what="Jtr"); assert_loss(rtr, rtr_o)
+    d = rng.standard_normal(n) * 0.01 * np.abs(p)
+    phi, dphi = ds.line(fam, p, d, [0.0, 0.5, 1.0])
+    phi_o, dphi_o = oracle.line(fam, X, y, p, d, [0.0, 0.5, 1.0])
+    assert_vec(phi, phi_o, what="phi"); assert_vec(dphi, dphi_o, rtol=1e-10, what="dphi")
+    assert_vec(ds.hess_vec(fam, p, d), oracle.hess_vec(fam, X, y, p, d), rtol=1e-10, what="Hd")
+    R = ds.qr(fam, p)
+    G = np.block([[JtJ_o, Jtr_o[:, None]], [Jtr_o[None, :], np.array([[rtr_o]])]])
+    sc = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
+    assert np.max(np.abs(R.T @ R - G) / sc) < 1e-10
+    ds.free()
+
+
 def test_errors_are_reported_not_swallowed(native, gpu_ctx):
     ds = native.Dataset(gpu_ctx, 16, 1)
     with pytest.raises(native.NativeError):       # empty data set

@@ -106,3 +106,47 @@ def test_device_generated_logistic_data_is_usable(native, oracle, gpu_ctx):
     assert loss == pytest.approx(np.log(2.0), rel=1e-12)       # CE at p = 0
     assert_vec(grad, oracle.gradient(fam, X, y, p))
     ds.free()
+
+
+@pytest.mark.parametrize("name,f", [("LINEAR", 3), ("LINEAR", 20), ("LINEAR_NOINT", 7), ("LINEAR_NOINT", 33), ("LINEAR", 64),
+                                    ("LOGISTIC", 4), ("LOGISTIC", 17), ("LOGISTIC", 40)])
+@pytest.mark.parametrize("seed", range(3))
+def test_linear_predictor_families_at_random_scales(native, oracle, gpu_ctx, name, f, seed):
+    """columns scaled over six decades, random parameters: K1-K4, K2 and (n <= 8) the TSQR against the oracle"""
+    fam = getattr(oracle, name)
+    rng = np.random.default_rng(3000 + 17 * f + seed)
+    m = 2503
+    colscale = 10.0 ** rng.uniform(-3.0, 3.0, size=f)
+    X = rng.standard_normal((m, f)) * colscale
+    icpt = 0 if name == "LINEAR_NOINT" else 1
+    w = rng.standard_normal(f) / colscale / np.sqrt(f)
+    z = X @ w + (0.3 if icpt else 0.0)
+    if name == "LOGISTIC":
+        y = (rng.random(m) < 1.0 / (1.0 + np.exp(-z))).astype(float)
+    else:
+        y = z + 0.1 * rng.standard_normal(m)
+    p = np.concatenate([[0.1] if icpt else [], w * rng.uniform(0.5, 1.5, size=f)])
+    n = p.size
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    loss, grad = ds.loss_grad(fam, p)
+    assert_loss(loss, oracle.apply(fam, X, y, p))
+    assert_vec(grad, oracle.gradient(fam, X, y, p), rtol=1e-11)
+    d = np.concatenate([[0.01] if icpt else [], 0.05 * rng.standard_normal(f) / colscale / np.sqrt(f)])   # |x . d| ~ 0.05 per row
+    phi, dphi = ds.line(fam, p, d, [0.0, 0.5, 1.0, 2.0])
+    phi_o, dphi_o = oracle.line(fam, X, y, p, d, [0.0, 0.5, 1.0, 2.0])
+    assert_vec(phi, phi_o, what="phi"); assert_vec(dphi, dphi_o, rtol=1e-10, what="dphi")
+    assert_vec(ds.hess_vec(fam, p, d), oracle.hess_vec(fam, X, y, p, d), rtol=1e-10, what="Hd")
+    JtJ, Jtr, rtr = ds.normal_eq(fam, p)
+    JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p)
+    if name == "LOGISTIC":
+        dg = np.sqrt(np.diag(JtJ_o)); np.testing.assert_allclose(JtJ / np.outer(dg, dg), JtJ_o / np.outer(dg, dg), rtol=0, atol=1e-11)
+    else:
+        assert_gram(JtJ, JtJ_o)
+    assert_vec(Jtr / np.sqrt(np.diag(JtJ_o)), Jtr_o / np.sqrt(np.diag(JtJ_o)), rtol=1e-10, what="Jtr (column-scaled)")
+    assert_loss(rtr, rtr_o)
+    if n <= 8:
+        R = ds.qr(fam, p)
+        G = np.block([[JtJ_o, Jtr_o[:, None]], [Jtr_o[None, :], np.array([[rtr_o]])]])
+        sc = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
+        assert np.max(np.abs(R.T @ R - G) / sc) < 1e-10
+    ds.free()
