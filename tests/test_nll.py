@@ -44,6 +44,26 @@ def test_gpu_nll_matches_oracle(native, oracle, gpu_ctx, m):
     ds.free()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_gpu_nll_at_random_parameters(native, oracle, gpu_ctx, seed):
+    """widths and rates over decades: some draws keep both exp arguments in the fast path's range (check-free kernel), some
+    underflow the Gaussian for most events (checked kernel, libdevice exp); finite or infinite, the sums agree"""
+    rng = np.random.default_rng(4000 + seed)
+    m = 5003
+    sig = rng.random(m) < 0.3
+    x = np.where(sig, rng.normal(125.0, 10.0, m), 50.0 - np.log(rng.random(m)) / 0.05)
+    p = [rng.uniform(0.05, 0.95), 125.0 * rng.uniform(0.9, 1.1), 10.0 * 10.0 ** rng.uniform(-1.5, 1.0), 0.05 * 10.0 ** rng.uniform(-1.5, 1.2)]
+    ds = native.Dataset(gpu_ctx, m, 1).append(x.reshape(-1, 1), np.zeros(m))
+    got = ds.nll(native.PDF_GAUSS_EXPBKG, p, XMIN)
+    ref = oracle.nll(oracle.PDF_GAUSS_EXPBKG, x, p, XMIN)
+    if np.isfinite(ref):
+        assert abs(got - ref) <= 1e-12 * abs(ref), (p, got, ref)
+    else:
+        assert got == ref or (np.isnan(got) and np.isnan(ref)), (p, got, ref)
+    ds.free()
+
+
 def test_max_likelihood_fit_with_nelder_mead(oracle):
     """ExSignalPlusBackgroundFit.scala:56-66: maxLikelihoodFit(pdf, data, p0) with its default method NelderMead."""
     from scalaopt_b200 import host
