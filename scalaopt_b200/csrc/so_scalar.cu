@@ -783,7 +783,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
           a.scale[KB + kk] = -1.0;
           in_range = in_range && fam_in_range<Fam>(a.pre[kk], s.tmin, s.tmax);
         }
-        constexpr int MB = KB >= 6 ? 1 : 2, RP = 8;
+        constexpr int MB = KB >= 5 ? 1 : 2, RP = 8;
         if constexpr (kFamHasRange<Fam>) {
           if (in_range) return launch_op_cfg<Op, kThreads, MB, 0, RP, false, false>(s, a);     // check-free, see kNormalEq
         }
@@ -793,7 +793,9 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       if (k == 2) return run(std::integral_constant<int, 2>());
       if (k == 3) return run(std::integral_constant<int, 3>());
       if (k == 4) return run(std::integral_constant<int, 4>());
-      if (k <= 6) return run(std::integral_constant<int, 6>());
+      if (k == 5) return run(std::integral_constant<int, 5>());
+      if (k == 6) return run(std::integral_constant<int, 6>());
+      if (k == 7) return run(std::integral_constant<int, 7>());
       return run(std::integral_constant<int, 8>());
     }
     case kHessVec: {
@@ -908,7 +910,7 @@ int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* co
 }
 
 // padded width of the kLine result for the scalar families (so_api reads phi at [0,k) and dphi at [KB, KB+k))
-int scalar_line_block(int k) { return k <= 4 ? k : (k <= 6 ? 6 : 8); }
+int scalar_line_block(int k) { return k; }     // one instantiation per k = 1..8: no padded step sizes
 
 int launch_scalar(Kind kind, const Shard& s, int family, const double* p, const double* d, int n,
                   const double* alpha, int k, int want_grad) {
