@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SO_ABI_VERSION 1
+#define SO_ABI_VERSION 2
 
 /* error codes */
 #define SO_OK            0
@@ -222,8 +222,19 @@ typedef struct so_call_stats {
   int64_t launches;        /* kernels launched by the last call (all GPUs of this process) */
   int64_t total_launches;  /* kernels launched since so_init */
   int64_t total_evals;     /* so_eval_* calls since so_init */
+  /* ABI 2 */
+  double  finish_ms;       /* last call: time the folding block spent in the cross-GPU exchange + host delivery (device clock;
+                              includes waiting for the slowest GPU); part of kernel_ms when finished_on_device */
+  double  sum_kernel_ms;   /* kernel_ms, device_ms, finish_ms summed over the calls since so_init / so_stats_reset, */
+  double  sum_device_ms;   /*   so that a caller timing many evaluations need not ask after each one */
+  double  sum_finish_ms;
+  double  min_kernel_ms;   /* fastest kernel_ms since so_init / so_stats_reset (0: none yet) */
+  int64_t finished_on_device; /* last call: 1 = cross-GPU sum and host delivery done by the evaluation kernel itself (results up to
+                              4096 doubles), 0 = NCCL all-reduce + device-to-host copy */
 } so_call_stats;
+/* Event times are collected lazily: so_stats waits for the last evaluation's events (microseconds), the evaluation calls do not. */
 int so_stats(so_ctx* ctx, so_call_stats* out);
+int so_stats_reset(so_ctx* ctx);   /* zero the sum_* / min_* counters */
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@
 #include <nccl.h>   // types only: the library is dlopen'ed on first multi-GPU use (see NcclApi)
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -40,6 +41,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -58,7 +60,7 @@ struct NcclApi {
     if (!field) { error = std::string("libnccl lacks ") + sym; handle = nullptr; return false; }
     SO_BIND(GetUniqueId, "ncclGetUniqueId") SO_BIND(CommInitAll, "ncclCommInitAll")
     SO_BIND(CommInitRank, "ncclCommInitRank") SO_BIND(CommDestroy, "ncclCommDestroy")
-    SO_BIND(AllReduce, "ncclAllReduce") SO_BIND(GroupStart, "ncclGroupStart") SO_BIND(GroupEnd, "ncclGroupEnd")
+    SO_BIND(AllReduce, "ncclAllReduce") SO_BIND(AllGather, "ncclAllGather") SO_BIND(GroupStart, "ncclGroupStart") SO_BIND(GroupEnd, "ncclGroupEnd")
     SO_BIND(GetErrorString, "ncclGetErrorString")
 #undef SO_BIND
     return true;
@@ -73,20 +75,35 @@ bool nccl_ready(std::string* why) {
   return false;
 }
 
+// timing events of one evaluation; two sets alternate so that the previous call's times are read while the current
+// call's kernel runs
+struct EvSet { cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; bool pending = false; bool finished_on_device = false; };
+
 struct Device {
   int id = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   double* partials = nullptr; size_t partials_cap = 0;
   double* out = nullptr;      size_t out_cap = 0;
-  double* hout = nullptr;     // pinned, out_cap doubles
-  unsigned int* ticket = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  double* hout = nullptr;     // pinned, out_cap doubles (results too large for the mailboxes)
+  // control blocks (so_internal.h): ctl0 = leave the sums on the device, ctl1 = sum across GPUs + deliver to the host
+  Ctl* ctl0 = nullptr; Ctl* ctl1 = nullptr;
+  unsigned long long* seq_dev = nullptr;          // device: exchanges finished
+  unsigned long long seq_host = 0;                // exchanges issued by the host
+  char* mailbox = nullptr;                        // own mailbox: flags [2][kMaxRanks] u64 (256 B) + slots [2][kMaxRanks][kMailCap] doubles
+  void* peer_open[kMaxRanks] = {};                // rank mode: peers' mailboxes opened with cudaIpcOpenMemHandle
+  double* hres = nullptr;                         // mapped pinned: kMailCap + 4 doubles, then flag and error words
+  unsigned long long* hflag = nullptr;
+  unsigned long long* herr = nullptr;
+  EvSet ev[2];
+  int ev_turn = 0;
   ncclComm_t comm = nullptr;
   // ingest: two pinned staging buffers (allocated on first use) and the events that mark them free again
   void* stage[2] = {nullptr, nullptr};
   cudaEvent_t stage_free[2] = {nullptr, nullptr};
 };
+constexpr size_t kMailFlagBytes = 256;
+constexpr size_t kMailBytes = kMailFlagBytes + sizeof(double) * 2 * kMaxRanks * kMailCap;
 
 }  // namespace
 
@@ -98,6 +115,8 @@ struct so_ctx {
   std::mutex mu;
   std::string err;
   so_call_stats stats{};
+  bool finish_multi = false;      // mailboxes of all GPUs / ranks are wired: results up to kMailCap doubles are summed by so_finish
+  bool poisoned = false;          // a peer timed out inside an exchange: sequence numbers can no longer be trusted
   uint64_t data_epoch = 1;        // bumped by everything that writes observations (append, load, clear, generate)
 };
 
@@ -146,12 +165,147 @@ int setup_device(so_ctx* ctx, Device& d) {
   if (prop.major < 10) return fail(ctx, SO_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", d.id, prop.major, prop.minor);
   d.sm_count = prop.multiProcessorCount;
   SO_CUDA(ctx, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-  SO_CUDA(ctx, cudaEventCreate(&d.ev0));
-  SO_CUDA(ctx, cudaEventCreate(&d.ev1));
-  SO_CUDA(ctx, cudaEventCreate(&d.ev2));
-  SO_CUDA(ctx, cudaMalloc(&d.ticket, 4 * sizeof(unsigned int)));      // [0] last-block ticket, [1..2] grid barrier of k_gram_ws
-  SO_CUDA(ctx, cudaMemset(d.ticket, 0, 4 * sizeof(unsigned int)));
+  for (EvSet& es : d.ev) {
+    SO_CUDA(ctx, cudaEventCreate(&es.e0));
+    SO_CUDA(ctx, cudaEventCreate(&es.e1));
+    SO_CUDA(ctx, cudaEventCreate(&es.e2));
+  }
+  // control blocks + sequence word in one allocation; own mailbox; host-visible result block
+  char* cb = nullptr;
+  SO_CUDA(ctx, cudaMalloc(&cb, 2 * 512 + 256));
+  SO_CUDA(ctx, cudaMemset(cb, 0, 2 * 512 + 256));
+  static_assert(sizeof(Ctl) <= 512, "Ctl size");
+  d.ctl0 = reinterpret_cast<Ctl*>(cb);
+  d.ctl1 = reinterpret_cast<Ctl*>(cb + 512);
+  d.seq_dev = reinterpret_cast<unsigned long long*>(cb + 1024);
+  SO_CUDA(ctx, cudaMalloc(&d.mailbox, kMailBytes));
+  SO_CUDA(ctx, cudaMemset(d.mailbox, 0, kMailBytes));
+  void* hp = nullptr;
+  SO_CUDA(ctx, cudaHostAlloc(&hp, sizeof(double) * (kMailCap + 4) + 128, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(hp, 0, sizeof(double) * (kMailCap + 4) + 128);
+  d.hres = static_cast<double*>(hp);
+  d.hflag = reinterpret_cast<unsigned long long*>(d.hres + kMailCap + 4);
+  d.herr = d.hflag + 8;
+  SO_CUDA(ctx, cudaDeviceSynchronize());
   return SO_OK;
+}
+
+unsigned long long peer_timeout_ns() {
+  const char* env = getenv("SCALAOPT_PEER_TIMEOUT_MS");
+  const double ms = env && *env ? atof(env) : 20000.0;
+  return (unsigned long long)(std::max(1.0, ms) * 1.0e6);
+}
+
+// Write the two control blocks of device `d`: rank `rank` of `world`, mailboxes[r] = rank r's mailbox as mapped HERE.
+int write_ctl(so_ctx* ctx, Device& d, int rank, int world, char* const* mailboxes) {
+  SO_CUDA(ctx, cudaSetDevice(d.id));
+  Ctl c{};
+  c.world = world; c.rank = rank; c.cap = kMailCap;
+  c.seq = d.seq_dev;
+  void* dp = nullptr;
+  SO_CUDA(ctx, cudaHostGetDevicePointer(&dp, d.hres, 0));
+  c.host_out = static_cast<double*>(dp);
+  c.host_flag = reinterpret_cast<unsigned long long*>(c.host_out + kMailCap + 4);
+  c.host_err = c.host_flag + 8;
+  c.timeout_ns = peer_timeout_ns();
+  for (int r = 0; r < world; ++r) {
+    c.flags[r] = reinterpret_cast<unsigned long long*>(mailboxes[r]);
+    c.slots[r] = reinterpret_cast<double*>(mailboxes[r] + kMailFlagBytes);
+  }
+  c.mode = 0;
+  SO_CUDA(ctx, cudaMemcpy(d.ctl0, &c, sizeof c, cudaMemcpyHostToDevice));
+  c.mode = 1;
+  SO_CUDA(ctx, cudaMemcpy(d.ctl1, &c, sizeof c, cudaMemcpyHostToDevice));
+  return SO_OK;
+}
+
+// single-process mode: peer access between every pair of the context's GPUs
+int wire_local(so_ctx* ctx) {
+  const int G = (int)ctx->devs.size();
+  bool all = G <= kMaxRanks;
+  for (int a = 0; a < G && all; ++a)
+    for (int b = 0; b < G && all; ++b) {
+      if (a == b) continue;
+      if (ctx->devs[a].id == ctx->devs[b].id) { all = false; break; }   // two shards on one GPU must never wait on each other
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctx->devs[a].id, ctx->devs[b].id) != cudaSuccess || !can) { all = false; break; }
+      cudaSetDevice(ctx->devs[a].id);
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctx->devs[b].id, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) { cudaGetLastError(); all = false; }
+    }
+  ctx->finish_multi = all && G > 1;
+  for (int g = 0; g < G; ++g) {
+    char* boxes[kMaxRanks] = {};
+    if (ctx->finish_multi) { for (int r = 0; r < G; ++r) boxes[r] = ctx->devs[r].mailbox; }
+    else boxes[0] = ctx->devs[g].mailbox;
+    // without peer access every device is a world of its own for so_finish; the cross-GPU sum then stays with NCCL
+    int rc = ctx->finish_multi ? write_ctl(ctx, ctx->devs[g], g, G, boxes) : write_ctl(ctx, ctx->devs[g], 0, 1, boxes);
+    if (rc) return rc;
+  }
+  return SO_OK;
+}
+
+// rank mode: exchange the mailboxes' IPC handles through the NCCL communicator that was just created
+struct PeerCard { cudaIpcMemHandle_t handle; unsigned long long host_hash; char bus[32]; int ok; int pad; };
+int wire_ranks(so_ctx* ctx) {
+  Device& d = ctx->devs[0];
+  const int W = ctx->world;
+  char* boxes[kMaxRanks] = {};
+  boxes[0] = d.mailbox;
+  if (W == 1) return write_ctl(ctx, d, 0, 1, boxes);
+  bool ok = W <= kMaxRanks;
+  if (const char* env = getenv("SCALAOPT_NO_PEER_FINISH")) if (*env && *env != '0') ok = false;
+  PeerCard mine{};
+  mine.ok = ok ? 1 : 0;
+  if (ok && cudaIpcGetMemHandle(&mine.handle, d.mailbox) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  {
+    char host[256] = {};
+    gethostname(host, sizeof host - 1);
+    std::string key(host);
+    if (FILE* fp = fopen("/proc/sys/kernel/random/boot_id", "r")) { char b[64] = {}; if (fgets(b, sizeof b, fp)) key += b; fclose(fp); }
+    unsigned long long h = 1469598103934665603ull;
+    for (unsigned char ch : key) { h ^= ch; h *= 1099511628211ull; }
+    mine.host_hash = h;
+    cudaDeviceGetPCIBusId(mine.bus, sizeof mine.bus, d.id);
+  }
+  static_assert(sizeof(PeerCard) % 8 == 0, "PeerCard size");
+  std::vector<PeerCard> cards(W);
+  char* dbuf = nullptr;
+  SO_CUDA(ctx, cudaSetDevice(d.id));
+  SO_CUDA(ctx, cudaMalloc(&dbuf, sizeof(PeerCard) * (size_t)(W + 1)));
+  SO_CUDA(ctx, cudaMemcpy(dbuf + sizeof(PeerCard) * (size_t)W, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  SO_NCCL(ctx, g_nccl.AllGather(dbuf + sizeof(PeerCard) * (size_t)W, dbuf, sizeof(PeerCard), ncclChar, d.comm, d.stream));
+  SO_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  SO_CUDA(ctx, cudaMemcpy(cards.data(), dbuf, sizeof(PeerCard) * (size_t)W, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < W && ok; ++r) {
+    if (!cards[r].ok || cards[r].host_hash != mine.host_hash) ok = false;
+    for (int q = 0; q < r && ok; ++q) if (strncmp(cards[q].bus, cards[r].bus, sizeof mine.bus) == 0) ok = false;   // two ranks on one GPU
+  }
+  for (int r = 0; r < W && ok; ++r) {
+    if (r == ctx->rank) { boxes[r] = d.mailbox; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, cards[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    d.peer_open[r] = ptr;
+    boxes[r] = static_cast<char*>(ptr);
+  }
+  // everybody or nobody: a rank that could not map a peer takes all ranks back to the NCCL sum
+  double* flag = reinterpret_cast<double*>(dbuf);
+  const double v = ok ? 0.0 : 1.0;
+  SO_CUDA(ctx, cudaMemcpy(flag, &v, sizeof v, cudaMemcpyHostToDevice));
+  SO_NCCL(ctx, g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclSum, d.comm, d.stream));
+  SO_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  double bad = 0.0;
+  SO_CUDA(ctx, cudaMemcpy(&bad, flag, sizeof bad, cudaMemcpyDeviceToHost));
+  cudaFree(dbuf);
+  ctx->finish_multi = bad == 0.0;
+  if (!ctx->finish_multi) {
+    for (int r = 0; r < W; ++r) if (d.peer_open[r]) { cudaIpcCloseMemHandle(d.peer_open[r]); d.peer_open[r] = nullptr; }
+    char* own[kMaxRanks] = {};
+    own[0] = d.mailbox;
+    return write_ctl(ctx, d, 0, 1, own);
+  }
+  return write_ctl(ctx, d, ctx->rank, W, boxes);
 }
 
 int ensure_workspace(so_ctx* ctx, Device& d, size_t partials, size_t out) {
@@ -177,17 +331,37 @@ int ensure_workspace(so_ctx* ctx, Device& d, size_t partials, size_t out) {
   return SO_OK;
 }
 
+// rank mode: nobody unmaps or frees a mailbox while a peer may still be using it
+void rank_barrier(so_ctx* ctx) {
+  if (!(ctx->rank_mode && ctx->use_nccl && ctx->finish_multi && !ctx->poisoned)) return;
+  Device& d = ctx->devs[0];
+  if (!d.comm || !d.out) return;
+  cudaSetDevice(d.id);
+  if (g_nccl.AllReduce(d.out, d.out, 1, ncclDouble, ncclSum, d.comm, d.stream) == ncclSuccess) cudaStreamSynchronize(d.stream);
+}
+
 void teardown(so_ctx* ctx) {
+  rank_barrier(ctx);
+  for (Device& d : ctx->devs) {
+    cudaSetDevice(d.id);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    for (void*& pp : d.peer_open) if (pp) { cudaIpcCloseMemHandle(pp); pp = nullptr; }
+  }
+  rank_barrier(ctx);
   for (Device& d : ctx->devs) {
     cudaSetDevice(d.id);
     if (d.comm) g_nccl.CommDestroy(d.comm);
     if (d.partials) cudaFree(d.partials);
     if (d.out) cudaFree(d.out);
     if (d.hout) cudaFreeHost(d.hout);
-    if (d.ticket) cudaFree(d.ticket);
-    if (d.ev0) cudaEventDestroy(d.ev0);
-    if (d.ev1) cudaEventDestroy(d.ev1);
-    if (d.ev2) cudaEventDestroy(d.ev2);
+    if (d.ctl0) cudaFree(d.ctl0);
+    if (d.mailbox) cudaFree(d.mailbox);
+    if (d.hres) cudaFreeHost(d.hres);
+    for (EvSet& es : d.ev) {
+      if (es.e0) cudaEventDestroy(es.e0);
+      if (es.e1) cudaEventDestroy(es.e1);
+      if (es.e2) cudaEventDestroy(es.e2);
+    }
     for (int k = 0; k < 2; ++k) { if (d.stage[k]) cudaFreeHost(d.stage[k]); if (d.stage_free[k]) cudaEventDestroy(d.stage_free[k]); }
     if (d.stream) cudaStreamDestroy(d.stream);
   }
@@ -232,13 +406,72 @@ int global_rows(so_dataset* ds, int64_t* m) {
   return SO_OK;
 }
 
-// Run one evaluation: launch per device, sum across devices/ranks, copy the (Q+1) doubles to host.
+// Times of an earlier evaluation whose events have completed by now: read them and add them to the context's counters.
+void resolve_events(so_ctx* ctx, Device& dv, EvSet& es, double* kernel_ms, double* device_ms) {
+  if (!es.pending) return;
+  es.pending = false;
+  cudaSetDevice(dv.id);
+  cudaEventSynchronize(es.e2);
+  float a = 0.f, b = 0.f;
+  cudaEventElapsedTime(&a, es.e0, es.e1);
+  cudaEventElapsedTime(&b, es.e0, es.e2);
+  *kernel_ms = std::max(*kernel_ms, (double)a);
+  *device_ms = std::max(*device_ms, (double)b);
+}
+
+// Per-call times are known once the call's events have completed; so_stats() and the next evaluation collect them.
+void collect_stats(so_ctx* ctx, int turn) {
+  double k = 0.0, d = 0.0;
+  bool any = false;
+  for (Device& dv : ctx->devs) { any = any || dv.ev[turn].pending; resolve_events(ctx, dv, dv.ev[turn], &k, &d); }
+  if (!any) return;
+  ctx->stats.kernel_ms = k;
+  ctx->stats.device_ms = d;
+  ctx->stats.sum_kernel_ms += k;
+  ctx->stats.sum_device_ms += d;
+  ctx->stats.min_kernel_ms = ctx->stats.min_kernel_ms > 0.0 ? std::min(ctx->stats.min_kernel_ms, k) : k;
+}
+
+// the times of the most recent evaluation (waits for its events: the kernel has delivered, they complete within microseconds)
+void settle_last(so_ctx* ctx) {
+  if (ctx->devs.empty()) return;
+  const int last = ctx->devs[0].ev_turn ^ 1;
+  collect_stats(ctx, last ^ 1);
+  collect_stats(ctx, last);
+}
+
+// Wait until device `dv` has delivered result number `seq` into its host block.
+int wait_delivery(so_ctx* ctx, Device& dv, unsigned long long seq) {
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned long long spins = 0;
+  while (__atomic_load_n(dv.hflag, __ATOMIC_ACQUIRE) < seq) {
+    __builtin_ia32_pause();
+    if ((++spins & 0x3fffull) == 0) {
+      cudaError_t e = cudaStreamQuery(dv.stream);
+      if (e == cudaSuccess) {                      // the stream drained: the result must be there
+        if (__atomic_load_n(dv.hflag, __ATOMIC_ACQUIRE) >= seq) break;
+        ctx->poisoned = true;
+        return fail(ctx, SO_ECUDA, "evaluation kernel on device %d finished without delivering result %llu", dv.id, seq);
+      }
+      if (e != cudaErrorNotReady) { ctx->poisoned = true; return fail(ctx, SO_ECUDA, "evaluation on device %d failed: %s", dv.id, cudaGetErrorString(e)); }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(600)) { ctx->poisoned = true; return fail(ctx, SO_ECUDA, "evaluation on device %d did not finish within 600 s", dv.id); }
+    }
+  }
+  if (__atomic_load_n(dv.herr, __ATOMIC_ACQUIRE) != 0) {
+    ctx->poisoned = true;
+    return fail(ctx, SO_ENCCL, "device %d: a peer GPU did not post its sums within the exchange timeout (result %llu)", dv.id, seq);
+  }
+  return SO_OK;
+}
+
+// Run one evaluation: launch per device, sum across devices/ranks, result in host memory.
 // On return `res` holds the summed raw sums and res[Q] the global number of rows.
 struct NllCall { int pdf; const double* consts; int nconsts; };
 
 int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const double* d, int n, const double* alpha,
              int k, int want_grad, int Q, std::vector<double>& res, const NllCall* nll = nullptr) {
   so_ctx* ctx = ds->ctx;
+  if (ctx->poisoned) return fail(ctx, SO_ESTATE, "context unusable after a failed cross-GPU exchange: %s", std::string(ctx->err).c_str());
   const bool scalar = nll != nullptr || family_is_scalar_t(family);
   const int G = (int)ctx->devs.size();
   int64_t rows_local = 0, launches = 0;
@@ -272,6 +505,26 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
     sm.range_ok = range_decode(reinterpret_cast<const unsigned long long*>(dv.hout), &sm.tmin, &sm.tmax);
     sm.range_epoch = ctx->data_epoch; sm.range_rows = sm.filled;
   }
+  // Who sums across GPUs?  Results that fit a mailbox slot: the kernel itself (so_finish), one launch per GPU and nothing
+  // else.  Larger ones (the Gram of several hundred parameters; the TSQR triangles of several GPUs, which are gathered, not
+  // summed): NCCL all-reduce + device-to-host copy.
+  const int ranks = ctx->rank_mode ? ctx->world : G;
+  const bool fin = Q <= kMailCap && (ranks == 1 || (ctx->finish_multi && kind != kQr));
+  const int turn = ctx->devs[0].ev_turn;
+  // on any failure below: leave the streams idle and the counters of the control blocks at zero
+  auto bail = [&](int rc) {
+    for (Device& dv : ctx->devs) {
+      cudaSetDevice(dv.id);
+      cudaStreamSynchronize(dv.stream);
+      cudaMemsetAsync(dv.ctl0, 0, 4 * sizeof(unsigned int), dv.stream);
+      cudaMemsetAsync(dv.ctl1, 0, 4 * sizeof(unsigned int), dv.stream);
+      cudaStreamSynchronize(dv.stream);
+      dv.ev[turn].pending = false;
+    }
+    cudaGetLastError();
+    if (fin && ranks > 1) ctx->poisoned = true;       // peers may be waiting for sums that will never come
+    return rc;
+  };
   for (int g = 0; g < G; ++g) {
     Device& dv = ctx->devs[g];
     const ShardMem& sm = ds->shards[g];
@@ -279,21 +532,23 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
                                  : scalar ? scalar_partials_needed(kind, n, k, dv.sm_count)
                                           : wide_partials_needed(kind, family, n, ds->f, k, dv.sm_count);
     int rc = ensure_workspace(ctx, dv, need_partials, (size_t)Q + 2);
-    if (rc) return rc;
-    SO_CUDA(ctx, cudaSetDevice(dv.id));
-    SO_CUDA(ctx, cudaEventRecord(dv.ev0, dv.stream));
+    if (rc) return bail(rc);
+    EvSet& es = dv.ev[turn];
+    if (cudaSetDevice(dv.id) != cudaSuccess || cudaEventRecord(es.e0, dv.stream) != cudaSuccess)
+      return bail(fail(ctx, SO_ECUDA, "device %d: %s", dv.id, cudaGetErrorString(cudaGetLastError())));
+    Shard sh;
+    sh.X = sm.X; sh.y = sm.y; sh.rows = sm.filled; sh.f = ds->f;
+    sh.partials = dv.partials; sh.partials_doubles = dv.partials_cap;
+    sh.out = dv.out; sh.out_doubles = dv.out_cap;
+    sh.ticket = reinterpret_cast<unsigned int*>(fin ? dv.ctl1 : dv.ctl0);
+    sh.stream = dv.stream; sh.sm_count = dv.sm_count;
     if (sm.filled > 0) {
-      Shard sh;
-      sh.X = sm.X; sh.y = sm.y; sh.rows = sm.filled; sh.f = ds->f;
-      sh.partials = dv.partials; sh.partials_doubles = dv.partials_cap;
-      sh.out = dv.out; sh.out_doubles = dv.out_cap; sh.ticket = dv.ticket;
-      sh.stream = dv.stream; sh.sm_count = dv.sm_count;
       if (wants_range && sm.range_ok && sm.range_epoch == ctx->data_epoch && sm.range_rows == sm.filled) {
         sh.has_range = true; sh.tmin = sm.tmin; sh.tmax = sm.tmax;
       }
-      if (kind == kQr) {      // every device writes its triangle into its own slot of a zeroed buffer: the sum is a gather
+      if (kind == kQr && ranks > 1) {      // every device writes its triangle into its own slot of a zeroed buffer: the sum is a gather
         const int slot = ctx->rank_mode ? ctx->rank : g, per = (n + 1) * (n + 1);
-        SO_CUDA(ctx, cudaMemsetAsync(dv.out, 0, sizeof(double) * (size_t)Q, dv.stream));
+        cudaMemsetAsync(dv.out, 0, sizeof(double) * (size_t)Q, dv.stream);
         sh.out = dv.out + (size_t)slot * per;
         sh.out_doubles = (size_t)per;
       }
@@ -302,55 +557,82 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
                : scalar ? launch_scalar(kind, sh, family, p, d, n, alpha, k, want_grad)
                         : launch_wide(kind, sh, family, p, d, n, alpha, k, want_grad);
       if (rc < 0) {
-        if (rc == SO_EUNSUPPORTED) return fail(ctx, rc, "family %d with n=%d, f=%d, k=%d is outside the kernel catalogue", family, n, ds->f, k);
+        if (rc == SO_EUNSUPPORTED) return bail(fail(ctx, rc, "family %d with n=%d, f=%d, k=%d is outside the kernel catalogue", family, n, ds->f, k));
         cudaError_t e = cudaGetLastError();
-        return fail(ctx, rc, "kernel launch failed (%d): %s", rc, cudaGetErrorString(e));
+        return bail(fail(ctx, rc, "kernel launch failed (%d): %s", rc, cudaGetErrorString(e)));
       }
       launches += rc;
     } else {
-      SO_CUDA(ctx, cudaMemsetAsync(dv.out, 0, sizeof(double) * (size_t)Q, dv.stream));
+      cudaMemsetAsync(dv.out, 0, sizeof(double) * (size_t)Q, dv.stream);      // an empty shard contributes zeros
+      sh.device_finish = false;
     }
-    SO_CUDA(ctx, cudaEventRecord(dv.ev1, dv.stream));
+    cudaEventRecord(es.e1, dv.stream);
+    if (fin && !sh.device_finish) {
+      sh.out = dv.out;
+      rc = launch_finish(sh, Q);
+      if (rc < 0) return bail(fail(ctx, rc, "k_finish launch failed: %s", cudaGetErrorString(cudaGetLastError())));
+      launches += rc;
+    }
+    if (fin) {
+      ++dv.seq_host;
+      cudaEventRecord(es.e2, dv.stream);
+      es.pending = true;
+    }
     rows_local += sm.filled;
   }
-  if (ctx->use_nccl) {
-    SO_NCCL(ctx, g_nccl.GroupStart());
+  if (fin) {
+    // while the kernels run: the times of the previous evaluation
+    collect_stats(ctx, turn ^ 1);
+    for (int g = 0; g < G; ++g) {
+      int rc = wait_delivery(ctx, ctx->devs[g], ctx->devs[g].seq_host);
+      if (rc) return rc;
+    }
+    const Device& d0 = ctx->devs[0];
+    res.assign(d0.hres, d0.hres + Q);
+    ctx->stats.finish_ms = (d0.hres[kMailCap + 1] - d0.hres[kMailCap]) * 1.0e-6;
+    ctx->stats.sum_finish_ms += ctx->stats.finish_ms;
+  } else {
+    if (ctx->use_nccl) {
+      ncclResult_t first = ncclSuccess;
+      g_nccl.GroupStart();
+      for (int g = 0; g < G; ++g) {
+        Device& dv = ctx->devs[g];
+        ncclResult_t r = g_nccl.AllReduce(dv.out, dv.out, (size_t)Q, ncclDouble, ncclSum, dv.comm, dv.stream);
+        if (r != ncclSuccess && first == ncclSuccess) first = r;
+      }
+      ncclResult_t r = g_nccl.GroupEnd();               // always close the group, also after a failed enqueue
+      if (first == ncclSuccess) first = r;
+      if (first != ncclSuccess) return bail(fail(ctx, SO_ENCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(first)));
+    }
+    {
+      Device& d0 = ctx->devs[0];
+      cudaSetDevice(d0.id);
+      cudaMemcpyAsync(d0.hout, d0.out, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, d0.stream);
+    }
     for (int g = 0; g < G; ++g) {
       Device& dv = ctx->devs[g];
-      SO_NCCL(ctx, g_nccl.AllReduce(dv.out, dv.out, (size_t)Q, ncclDouble, ncclSum, dv.comm, dv.stream));
+      cudaSetDevice(dv.id);
+      cudaEventRecord(dv.ev[turn].e2, dv.stream);
+      dv.ev[turn].pending = true;
     }
-    SO_NCCL(ctx, g_nccl.GroupEnd());
+    collect_stats(ctx, turn ^ 1);
+    for (int g = 0; g < G; ++g) {
+      Device& dv = ctx->devs[g];
+      cudaSetDevice(dv.id);
+      cudaError_t e = cudaStreamSynchronize(dv.stream);
+      if (e != cudaSuccess) return bail(fail(ctx, SO_ECUDA, "evaluation on device %d failed: %s", dv.id, cudaGetErrorString(e)));
+    }
+    res.assign(ctx->devs[0].hout, ctx->devs[0].hout + Q);
+    ctx->stats.finish_ms = 0.0;
   }
-  {
-    Device& d0 = ctx->devs[0];
-    SO_CUDA(ctx, cudaSetDevice(d0.id));
-    SO_CUDA(ctx, cudaMemcpyAsync(d0.hout, d0.out, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, d0.stream));
-  }
-  for (int g = 0; g < G; ++g) {
-    Device& dv = ctx->devs[g];
-    SO_CUDA(ctx, cudaSetDevice(dv.id));
-    SO_CUDA(ctx, cudaEventRecord(dv.ev2, dv.stream));
-  }
-  double kernel_ms = 0.0, device_ms = 0.0;
-  for (int g = 0; g < G; ++g) {
-    Device& dv = ctx->devs[g];
-    SO_CUDA(ctx, cudaSetDevice(dv.id));
-    SO_CUDA(ctx, cudaStreamSynchronize(dv.stream));
-    float a = 0.f, b = 0.f;
-    cudaEventElapsedTime(&a, dv.ev0, dv.ev1);
-    cudaEventElapsedTime(&b, dv.ev0, dv.ev2);
-    kernel_ms = std::max(kernel_ms, (double)a);
-    device_ms = std::max(device_ms, (double)b);
-  }
-  res.assign(ctx->devs[0].hout, ctx->devs[0].hout + Q);
+  for (Device& dv : ctx->devs) dv.ev_turn = turn ^ 1;
   res.push_back((double)m_global);
   ctx->stats.rows = rows_local;
   ctx->stats.bytes = rows_local * 8 * (int64_t)(nll ? 1 : ds->f + 1);
-  ctx->stats.kernel_ms = kernel_ms;
-  ctx->stats.device_ms = device_ms;
   ctx->stats.launches = launches;
   ctx->stats.total_launches += launches;
   ctx->stats.total_evals += 1;
+  ctx->stats.finished_on_device = fin ? 1 : 0;
   return SO_OK;
 }
 
@@ -391,6 +673,7 @@ extern "C" int so_init(int ngpus, const int* device_ids, so_ctx** out) {
     for (int g = 0; g < ngpus; ++g) ctx->devs[g].comm = comms[g];
     ctx->use_nccl = true;
   }
+  if (int rc = wire_local(ctx)) { g_init_error = ctx->err; teardown(ctx); delete ctx; return rc; }
   *out = ctx;
   return SO_OK;
 }
@@ -433,6 +716,7 @@ extern "C" int so_init_rank(int device_id, int rank, int world, const void* nccl
     }
     ctx->use_nccl = true;
   }
+  if ((rc = wire_ranks(ctx))) { g_init_error = ctx->err; teardown(ctx); delete ctx; return rc; }
   *out = ctx;
   return SO_OK;
 }
@@ -446,7 +730,16 @@ extern "C" void so_shutdown(so_ctx* ctx) {
 extern "C" int so_stats(so_ctx* ctx, so_call_stats* out) {
   if (!ctx || !out) return SO_EINVAL;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  settle_last(ctx);
   *out = ctx->stats;
+  return SO_OK;
+}
+
+extern "C" int so_stats_reset(so_ctx* ctx) {
+  if (!ctx) return SO_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  settle_last(ctx);
+  ctx->stats.sum_kernel_ms = ctx->stats.sum_device_ms = ctx->stats.sum_finish_ms = ctx->stats.min_kernel_ms = 0.0;
   return SO_OK;
 }
 
@@ -766,6 +1059,7 @@ static int loss_grad_unlocked(so_dataset* ds, int family, const double* x, int n
   *loss = res[0] / m;
   if (grad) for (int i = 0; i < n; ++i) grad[i] = res[1 + i] / m;
   if (acc) {
+    settle_last(ctx);
     acc->kernel_ms += ctx->stats.kernel_ms; acc->device_ms += ctx->stats.device_ms; acc->launches += ctx->stats.launches;
     acc->rows += ctx->stats.rows; acc->bytes += ctx->stats.bytes;
   }
@@ -888,11 +1182,14 @@ extern "C" int so_eval_line(so_dataset* ds, int family, const double* p, const d
     if (rc) return rc;
     const double m = res[2 * KB];
     for (int j = 0; j < kk; ++j) { phi[k0 + j] = res[j] / m; dphi[k0 + j] = res[KB + j] / m; }
+    if (k > chunk) settle_last(ctx);
     acc.kernel_ms += ctx->stats.kernel_ms; acc.device_ms += ctx->stats.device_ms; acc.launches += ctx->stats.launches;
     acc.rows += ctx->stats.rows; acc.bytes += ctx->stats.bytes;
   }
-  ctx->stats.kernel_ms = acc.kernel_ms; ctx->stats.device_ms = acc.device_ms; ctx->stats.launches = acc.launches;
-  ctx->stats.rows = acc.rows; ctx->stats.bytes = acc.bytes;
+  if (k > chunk) {        // several passes: their times add up (a single pass keeps the lazily collected per-call times)
+    ctx->stats.kernel_ms = acc.kernel_ms; ctx->stats.device_ms = acc.device_ms; ctx->stats.launches = acc.launches;
+    ctx->stats.rows = acc.rows; ctx->stats.bytes = acc.bytes;
+  }
   return SO_OK;
 }
 

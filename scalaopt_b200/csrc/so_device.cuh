@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "so_internal.h"
+
 namespace so {
 
 constexpr int kExpTableSize = 256;
@@ -191,6 +193,82 @@ __device__ __forceinline__ int partials_lanes(int outputs, int threads) {
   return G;
 }
 
+// ---- so_finish: cross-GPU sum over NVLink peer memory + delivery to the host, by the block that folded the partials ----
+// (protocol: Ctl in so_internal.h).  Called by ALL threads of that one block after it wrote out[0, Q).
+__device__ __forceinline__ unsigned long long so_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void so_finish(unsigned int* ticket, const double* out, int Q) {
+  const Ctl* c = reinterpret_cast<const Ctl*>(ticket);
+  if (c->mode == 0) return;
+  const unsigned long long t0 = so_globaltimer();
+  __syncthreads();                                      // out[] as written by this block's threads
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(c->seq) + 1ull;
+  const int W = c->world, me = c->rank, cap = c->cap;
+  const int par = (int)(seq & 1ull);
+  __shared__ int s_timed_out;
+  if (threadIdx.x == 0) s_timed_out = 0;
+  if (W > 1) {
+    const size_t mine = (size_t)(par * kMaxRanks + me) * cap;
+#pragma unroll 1
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+      const double v = __ldcg(out + q);
+#pragma unroll 1
+      for (int r = 0; r < W; ++r) st_relaxed_sys(c->slots[r] + mine + q, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < W) {
+      st_release_sys(c->flags[threadIdx.x] + par * kMaxRanks + me, seq);           // my sums have landed at rank threadIdx.x
+      const unsigned long long* f = c->flags[me] + par * kMaxRanks + threadIdx.x;  // ... and rank threadIdx.x's at mine?
+      const unsigned long long give_up = so_globaltimer() + c->timeout_ns;
+      while (ld_acquire_sys(f) < seq) {
+        if (so_globaltimer() > give_up) { s_timed_out = 1; break; }
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+      double s = 0.0;
+#pragma unroll 1
+      for (int r = 0; r < W; ++r) s += ld_relaxed_sys(c->slots[me] + (size_t)(par * kMaxRanks + r) * cap + q);
+      c->host_out[q] = s;
+    }
+  } else {
+#pragma unroll 1
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) c->host_out[q] = __ldcg(out + q);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *c->seq = seq;
+    c->host_out[cap] = (double)t0;                      // device timestamps (ns): entry into so_finish, delivery
+    c->host_out[cap + 1] = (double)so_globaltimer();
+    if (s_timed_out) *reinterpret_cast<volatile unsigned long long*>(c->host_err) = seq;
+    __threadfence_system();
+    st_release_sys(c->host_flag, seq);
+  }
+}
+
 // Reduce Q per-thread accumulators over the grid, deterministically.
 //   acc[Q]      per-thread partial sums
 //   smem        >= (blockDim.x/32) * Q doubles of shared memory
@@ -243,6 +321,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[Q], double* smem, doub
       }
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    so_finish(ticket, out, qout);
   }
 }
 
@@ -268,6 +347,7 @@ __device__ __forceinline__ void grid_reduce_block_vals(const double* block_vals,
       if (q < Q && sub == 0) out[q] = scale ? s * scale[q] : s;
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    so_finish(ticket, out, Q);
   }
 }
 

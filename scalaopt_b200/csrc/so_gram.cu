@@ -299,6 +299,7 @@ k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t r
       out[q] = s * sgn;
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    so_finish(ticket, out, Qo);
   }
 }
 
@@ -825,6 +826,7 @@ int launch_ws(const Shard& s, const Params& P) {
   double* partials = s.partials; double* outp = s.out; unsigned int* ticket = s.ticket;
   void* args[] = {&Xp, &yp, &rows, const_cast<Params*>(&P), &b, &partials, &outp, &ticket};
   if (cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(kWsThreads), args, b.smem, s.stream) != cudaSuccess) return SO_ECUDA;
+  s.device_finish = false;      // every block emits a slice of the result: the cross-GPU sum is a launch of its own (k_finish)
   return 1;
 }
 

@@ -7,6 +7,34 @@
 
 namespace so {
 
+// ---- control block of an evaluation stream (device memory; one per delivery mode per device) ------------------------
+// Every evaluation kernel gets a pointer to it as its `ticket` argument: the first four words are the counters the
+// kernels always used (last-block ticket, grid barrier of k_gram_ws); behind them sits the description of what the block
+// that folds the per-block partials does with the result (so_finish, so_device.cuh):
+//   mode 0  leave the sums in `out` (the host sums across GPUs with NCCL and copies them back — large results)
+//   mode 1  the cross-GPU SUM and the delivery to the host happen inside the same kernel: the folding block stores its Q
+//           sums into every rank's mailbox over NVLink (peer-mapped pointers: cudaDeviceEnablePeerAccess in one process,
+//           cudaIpcOpenMemHandle between ranks), raises a flag there, waits for the flags of all ranks in its own
+//           mailbox, adds the `world` slots in RANK ORDER (every rank gets the same bits) and writes the totals plus a
+//           sequence number into mapped pinned host memory, where the calling thread is polling.  No collective launch,
+//           no device-to-host copy, no stream synchronisation on the way (spark-apps/.../SparkDataSetConverter.scala:42-45
+//           does this sum as rdd.aggregate on the driver).
+// Mailboxes are double-buffered on the parity of the sequence number: a rank can be at most one call ahead of a peer
+// (it cannot finish call c+1 before every peer has posted its sums for c+1, i.e. has finished reading call c).
+constexpr int kMaxRanks = 8;
+constexpr int kMailCap = 4096;          // doubles per (parity, source rank) slot: results up to this size take mode 1
+struct Ctl {
+  unsigned int ticket[4];
+  int mode, world, rank, cap;
+  unsigned long long* seq;              // device word shared by the control blocks of a device: exchanges finished
+  double* host_out;                     // mapped pinned: cap doubles of result + 4 doubles of device timestamps
+  unsigned long long* host_flag;        // mapped pinned: sequence number of the result host_out holds
+  unsigned long long* host_err;         // mapped pinned: set when a peer did not show up within timeout_ns
+  unsigned long long timeout_ns;
+  double* slots[kMaxRanks];             // slots[r] = rank r's mailbox data  [2][kMaxRanks][cap]
+  unsigned long long* flags[kMaxRanks]; // flags[r] = rank r's mailbox flags [2][kMaxRanks]
+};
+
 // One GPU's resident shard (or a slice of it) plus the workspace the kernels reduce through.
 struct Shard {
   const double* X = nullptr;   // rows x f, row-major
@@ -18,7 +46,9 @@ struct Shard {
   size_t partials_doubles = 0;
   double* out = nullptr;       // reduced result of the running evaluation
   size_t out_doubles = 0;
-  unsigned int* ticket = nullptr;
+  unsigned int* ticket = nullptr;   // -> Ctl (above)
+  // set to false by a launcher whose kernel does not end in so_finish (k_gram_ws): the API layer then runs k_finish
+  mutable bool device_finish = true;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   // f == 1 only: range of the inputs of this slice when it is known and all of them are finite (launch_range)
@@ -75,6 +105,9 @@ int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* co
 
 // padded width KB of the kLine result of launch_scalar: phi at out[0,k), dphi at out[KB, KB+k)
 int scalar_line_block(int k);
+
+// the cross-GPU sum + host delivery of `q` doubles at s.out as a launch of its own (kernels that do not end in so_finish)
+int launch_finish(const Shard& s, int q);
 
 // synthetic data
 int launch_generate(const Shard& s, double* X, double* y, int family, const double* p_true, int n, uint64_t seed,

@@ -166,6 +166,7 @@ __device__ __forceinline__ void qr_grid_reduce(double (&R)[C * (C + 1) / 2], dou
         for (int k = 0; k < C; ++k) out[j * C + k] = k >= j ? R[tri_idx<C>(j, k)] * colscale[k] : 0.0;
       *ticket = 0u;
     }
+    so_finish(ticket, out, C * C);
   }
 }
 

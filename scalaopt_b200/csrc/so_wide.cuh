@@ -115,6 +115,7 @@ __device__ __forceinline__ void finish_grid(const double* vals, int Q, int nscal
       if (q < Q && sub == 0) out[q] = (q < nscaled) ? s * scale0 : s;
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    so_finish(ticket, out, Q);
   }
 }
 

@@ -118,7 +118,7 @@ class GpuMSEFunction : public MSEFunction {
     if (const Entry* e = find(x)) { counters.cache_hits++; return e->loss; }
     if (const LineEntry* le = find_on_ray(x)) { counters.line_hits++; return le->phi; }
     if (on_ray_beta(x)) return score_ray(x).phi;
-    if (loss_only_mode && speculate && use_tsqr && trials_since_jacobian == 0) {
+    if (loss_only_mode && speculate && use_tsqr && loss_scale() > 0.0 && trials_since_jacobian == 0) {
       // same idea on the TSQR route: r^T r is the squared norm of R's last column
       ++trials_since_jacobian;
       spec.R.assign((size_t)(n + 1) * (n + 1), 0.0);
@@ -127,7 +127,7 @@ class GpuMSEFunction : public MSEFunction {
       counters.k2_passes++; counters.spec_passes++;
       double rtr = 0.0;
       for (int i = 0; i <= n; ++i) rtr += spec.R[(size_t)i * (n + 1) + n] * spec.R[(size_t)i * (n + 1) + n];
-      const double loss = rtr / (2.0 * (double)data->size());
+      const double loss = rtr * loss_scale() / (double)data->size();
       remember(x, loss, nullptr);
       return loss;
     }
@@ -189,7 +189,8 @@ class GpuMSEFunction : public MSEFunction {
       }
       double rtr = 0.0;
       for (int i = 0; i <= n; ++i) rtr += Rf[(size_t)i * (n + 1) + n] * Rf[(size_t)i * (n + 1) + n];
-      { int64_t m = data->size(); remember(p, rtr / (2.0 * (double)m), nullptr); }
+      // the loss at p is a function of r^T r only for the MSE families (cross-entropy: K1 computes it when LM asks)
+      if (loss_scale() > 0.0) { int64_t m = data->size(); remember(p, rtr * loss_scale() / (double)m, nullptr); }
       std::vector<AugmentedRow> rows;
       for (int i = 0; i <= n; ++i)
         rows.emplace_back(Vec(Rf.begin() + (size_t)i * (n + 1), Rf.begin() + (size_t)i * (n + 1) + n), Rf[(size_t)i * (n + 1) + n], (int64_t)i);
@@ -206,8 +207,7 @@ class GpuMSEFunction : public MSEFunction {
     }
     // the loss at p comes for free: sum r^2 / (2m) for the MSE families; FFNeuralNetwork's MSE loss is not halved
     // (FFNeuralNetwork.scala:70-72); the cross-entropy families' loss is not a function of r^T r
-    if (family == SO_FAMILY_MLP_MSE) { int64_t m = data->size(); remember(p, rtr / (double)m, nullptr); }
-    else if (family != SO_FAMILY_LOGISTIC && family != SO_FAMILY_MLP_CE) { int64_t m = data->size(); remember(p, rtr / (2.0 * (double)m), nullptr); }
+    if (loss_scale() > 0.0) { int64_t m = data->size(); remember(p, rtr * loss_scale() / (double)m, nullptr); }
     // Cholesky JtJ = R^T R (upper R), q = R^-T Jtr, rho = sqrt(max(0, rtr - q.q)); O(n^3) on the host
     std::vector<Vec> R(n, Vec(n, 0.0));
     Vec q(n, 0.0);

@@ -27,7 +27,7 @@ EXPORTS = [
     "so_host_alloc", "so_host_free",
     "so_dataset_create", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
     "so_dataset_size", "so_dataset_head", "so_dataset_slice", "so_dataset_free",
-    "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_qr", "so_eval_line", "so_eval_hess_vec", "so_eval_nll", "so_stats",
+    "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_qr", "so_eval_line", "so_eval_hess_vec", "so_eval_nll", "so_stats", "so_stats_reset",
 ]
 
 
@@ -39,7 +39,9 @@ class NativeError(RuntimeError):
 
 class CallStats(C.Structure):
     _fields_ = [("rows", C.c_int64), ("bytes", C.c_int64), ("kernel_ms", C.c_double), ("device_ms", C.c_double),
-                ("launches", C.c_int64), ("total_launches", C.c_int64), ("total_evals", C.c_int64)]
+                ("launches", C.c_int64), ("total_launches", C.c_int64), ("total_evals", C.c_int64),
+                ("finish_ms", C.c_double), ("sum_kernel_ms", C.c_double), ("sum_device_ms", C.c_double),
+                ("sum_finish_ms", C.c_double), ("min_kernel_ms", C.c_double), ("finished_on_device", C.c_int64)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -96,6 +98,7 @@ def load():
     L.so_eval_hess_vec.argtypes = [vp, i32, _dp, _dp, i32, _dp]
     L.so_eval_nll.argtypes = [vp, i32, _dp, i32, _dp, i32, _dp]
     L.so_stats.argtypes = [vp, C.POINTER(CallStats)]
+    L.so_stats_reset.argtypes = [vp]
     _lib = L
     return L
 
@@ -166,6 +169,9 @@ class Context:
         st = CallStats()
         self.check(load().so_stats(self._h, C.byref(st)))
         return st
+
+    def stats_reset(self):
+        self.check(load().so_stats_reset(self._h))
 
     def close(self):
         if self._h:

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native):
     missing = [s for s in declared if not hasattr(lib, s)]
     assert missing == []
     assert sorted(native.EXPORTS) == declared
-    assert lib.so_abi_version() == 1
+    assert lib.so_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_gpu(native):

@@ -102,6 +102,27 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
     f_gpu.free(); ds.free()
 
 
+@pytest.mark.parametrize("mode", ["k2", "k2-speculative", "tsqr"])
+def test_levenberg_marquardt_logistic_regression_matches_oracle(native, oracle, host, gpu_ctx, mode):
+    """FFNeuralNetworkTrainerSpec.scala:320-351 (logistic regression by LM) on the GPU.  The loss of this family is the
+    mean cross-entropy, NOT r^T r / 2m: with TSQR (or speculation) on, every loss LM sees must still be the K1 loss."""
+    X, y, truth = logistic_spec_data(oracle)
+    ds, f_gpu = _gpu(native, host, gpu_ctx, oracle.LOGISTIC, X, y, 3, tsqr=mode == "tsqr", speculate=mode != "k2")
+    f_ref = oracle_objective(host, oracle, oracle.LOGISTIC, X, y, 3)
+    start = [-0.5, 0.6, 0.6]
+    x_gpu, r_gpu = host.minimize(host.LEVENBERG_MARQUARDT, f_gpu, start)
+    x_ref, r_ref = host.minimize(host.LEVENBERG_MARQUARDT, f_ref, start)
+    assert r_gpu.iterations == r_ref.iterations
+    assert r_gpu.inner_iterations == r_ref.inner_iterations
+    np.testing.assert_allclose(x_gpu, x_ref, rtol=1e-8, atol=1e-8)
+    c = f_gpu.counters()
+    assert c["spec_passes"] == 0                             # nothing to speculate on: the loss is not a function of r^T r
+    assert c["k1_passes"] == r_gpu.inner_iterations          # one cross-entropy loss pass per trial point
+    # every loss the optimizer saw is the cross-entropy at that point
+    assert f_gpu(x_gpu) == pytest.approx(oracle.apply(oracle.LOGISTIC, X, y, x_gpu), rel=1e-12)
+    f_gpu.free(); ds.free()
+
+
 def test_bfgs_logistic_regression_matches_oracle(native, oracle, host, gpu_ctx):
     """FFNeuralNetworkTrainerSpec.scala:189-220 on the GPU."""
     X, y, truth = logistic_spec_data(oracle)
