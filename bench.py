@@ -13,6 +13,13 @@ One "step" = one evaluation of (loss, J^T r, J^T J) over the whole resident data
 vector.  `value` is timed with the observations already in HBM; `e2e` re-ingests the observations from
 pinned host memory (H2D) inside every timed step and reads the result back, through the same C ABI.
 Inputs are larger than L2 (16 GB vs 126 MB), so no L2 flush is needed between iterations.
+
+Scaling.  The default line is WEAK scaling (10^9 observations per GPU).  BASELINE configs[2] read literally is STRONG
+scaling — 10^9 observations in total on 1/2/4/8 GPUs — and every run measures that too, in the same process, on a second
+resident data set of 10^9/N observations per GPU: `roofline.strong_scaling` (observations/s, per-call overhead) and
+`e2e.lm` (Levenberg-Marquardt iterations/s, weak and strong).  `--scaling strong` makes the strong numbers the headline.
+Before anything is timed, `config.parity` holds a rank-mode parity check of K1-K4 (+TSQR) against the CPU oracle on
+10^6 observations per rank (tests/rank_parity.py), so every N of a scaling run carries its own correctness statement.
 """
 from __future__ import annotations
 
@@ -48,6 +55,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows observations per GPU; strong: --rows-total observations over all GPUs")
+    ap.add_argument("--rows-total", type=int, default=1_000_000_000, help="observations of the strong-scaling data set")
+    ap.add_argument("--strong-steps", type=int, default=None, help="timed steps of the strong-scaling leg (default: max(steps, 200))")
+    ap.add_argument("--parity-rows", type=int, default=1_000_000, help="observations per rank of the parity check")
     return ap.parse_args()
 
 
@@ -189,8 +203,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args, args.gpus), reference_sample_rows_per_step=m,
+                       note=f"CPU arm: rate measured on a bounded sample of {m} observations per step, not on 1e9"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -198,19 +213,66 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, rows_per_gpu=None, scaling="weak"):
+    rows = args.rows if rows_per_gpu is None else rows_per_gpu
     return {
         "workload": "BASELINE configs[2]: Levenberg-Marquardt Gaussian-peak + exponential-background fit, "
                     "n=5 params, fp64 (t,y) observations, normal-equation evaluation (loss + J^T r + J^T J)",
-        "family": "gauss_expbkg", "n_params": 5, "rows_per_gpu": args.rows, "rows_total": args.rows * world,
-        "bytes_per_row": 16, "parallelism": f"dp{world} (row shards, one NCCL all-reduce of 21 doubles per evaluation)",
-        "l2_policy": "inputs larger than L2 (16 GB per GPU vs 126 MB), no flush needed",
+        "family": "gauss_expbkg", "n_params": 5, "rows_per_gpu": rows, "rows_total": rows * world,
+        "scaling": scaling, "bytes_per_row": 16,
+        "parallelism": f"dp{world} (row shards; the 21-double cross-GPU sum is done by the evaluation kernel's folding "
+                       f"block over NVLink peer memory, results delivered to mapped host memory)",
+        "l2_policy": "inputs larger than L2 (>= 2 GB per GPU vs 126 MB), no flush needed",
     }
 
 
 # ------------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------------
+class K2Loop:
+    """K blocking so_eval_normal_eq calls through the C ABI with every argument marshalled once (what a JNI caller with
+    pinned arrays does): the per-call cost of the harness is one ctypes foreign call."""
+
+    def __init__(self, native, ctx, ds, fam):
+        import ctypes as C
+        self.fn = native.load().so_eval_normal_eq
+        self.ctx, self.h, self.fam = ctx, ds._h, fam
+        dp = C.POINTER(C.c_double)
+        self.params = [np.ascontiguousarray(params_for_step(i)) for i in range(50)]
+        self.pp = [a.ctypes.data_as(dp) for a in self.params]
+        self.JtJ, self.Jtr, self.rtr = np.empty((5, 5)), np.empty(5), C.c_double()
+        self.pJ, self.pr, self.prt = self.JtJ.ctypes.data_as(dp), self.Jtr.ctypes.data_as(dp), C.byref(self.rtr)
+
+    def run(self, steps, first=0):
+        fn, h, fam, pp, pJ, pr, prt = self.fn, self.h, self.fam, self.pp, self.pJ, self.pr, self.prt
+        for i in range(first, first + steps):
+            rc = fn(h, fam, pp[i % 50], 5, pJ, pr, prt)
+            if rc != 0:
+                self.ctx.check(rc)
+
+
+def time_k2(native, ctx, ds, fam, steps, warmup, barrier, max_over_ranks, sampler=None):
+    """-> dict: wall seconds (max over ranks) of `steps` evaluations, CUDA-event kernel/device time, time inside the
+    in-kernel exchange, launches."""
+    loop = K2Loop(native, ctx, ds, fam)
+    loop.run(warmup)
+    ctx.stats_reset()
+    launches0 = ctx.stats().total_launches
+    if sampler is not None:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    loop.run(steps, first=warmup)
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler is not None else {}
+    st = ctx.stats()
+    return {"wall_s": max_over_ranks(wall_s), "kernel_ms": max_over_ranks(st.sum_kernel_ms),
+            "device_ms": max_over_ranks(st.sum_device_ms), "finish_ms": max_over_ranks(st.sum_finish_ms),
+            "kernel_ms_best": st.min_kernel_ms, "launches": int(st.total_launches - launches0), "clocks": clocks,
+            "finished_on_device": int(st.finished_on_device)}
+
+
 def run_own(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,36 +305,55 @@ def run_own(args):
 
     fam = native.GAUSS_EXPBKG
     ctx = native.Context(rank=rank, world=world, device_id=local_rank, nccl_uid=uid)
-    m = args.rows
+
+    # ---- parity in rank mode, before anything is timed (the oracle is the checker here, nothing else) ----
+    parity = None
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import rank_parity
+        allsum, allgather = rank_parity.torch_collectives(dist, world)
+        parity = rank_parity.check(native, ctx, rank, world, args.parity_rows, allsum, allgather)
+        parity["what"] = ("K1-K4 + TSQR through the C ABI in rank mode vs the CPU oracle summed over ranks, relative errors; "
+                          "tolerances 1e-12 (loss, gradient, phi), 1e-11 (J^T J, J^T r, dphi, Hd, R^T R)")
+        if not parity["ok"]:
+            raise SystemExit(f"rank-mode parity FAILED: {parity}")
+
+    strong_rows = args.rows_total // world
+    strong_rows -= strong_rows & 1
+    headline_strong = args.scaling == "strong"
+    m = strong_rows if headline_strong else args.rows
     ds = native.Dataset(ctx, m, 1).generate(fam, TRUTH, seed=SEED, noise_sigma=NOISE, row_offset=rank * m)
     total_rows = ds.size()
     assert total_rows == m * world
 
     # ---- value: observations resident in HBM ----
-    for i in range(args.warmup):
-        ds.normal_eq(fam, params_for_step(i))
-    launches0 = ctx.stats().total_launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    kernel_ms = device_ms = 0.0
-    kernel_ms_best = float("inf")
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        JtJ, Jtr, rtr = ds.normal_eq(fam, params_for_step(i))
-        st = ctx.stats()
-        kernel_ms += st.kernel_ms
-        kernel_ms_best = min(kernel_ms_best, st.kernel_ms)
-        device_ms += st.device_ms
-    barrier()
-    wall_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else {}
-    launches = ctx.stats().total_launches - launches0
-    wall_s = max_over_ranks(wall_s)
-    device_ms = max_over_ranks(device_ms)
-    kernel_ms_max = max_over_ranks(kernel_ms)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    head = time_k2(native, ctx, ds, fam, args.steps, args.warmup, barrier, max_over_ranks, sampler)
+    wall_s, launches, clocks = head["wall_s"], head["launches"], head["clocks"]
+    kernel_ms_max, device_ms, kernel_ms_best = head["kernel_ms"], head["device_ms"], head["kernel_ms_best"]
     value = total_rows * args.steps / wall_s
+
+    # ---- strong scaling: the SAME 10^9-observation data set on 1/2/4/8 GPUs ----
+    strong = None
+    ds_s = None
+    if not args.no_strong:
+        if headline_strong or (world == 1 and m == strong_rows):
+            ds_s = ds
+        else:
+            ds_s = native.Dataset(ctx, strong_rows, 1).generate(fam, TRUTH, seed=SEED, noise_sigma=NOISE,
+                                                                row_offset=rank * strong_rows)
+        ssteps = args.strong_steps if args.strong_steps is not None else max(args.steps, 200)
+        r = time_k2(native, ctx, ds_s, fam, ssteps, max(args.warmup, 5), barrier, max_over_ranks)
+        per_call_ms = 1e3 * r["wall_s"] / ssteps
+        strong = {
+            "rows_total": strong_rows * world, "rows_per_gpu": strong_rows, "n_gpus": world, "steps": ssteps,
+            "observations_per_s": strong_rows * world * ssteps / r["wall_s"], "ms_per_call": per_call_ms,
+            "kernel_ms_per_call": r["kernel_ms"] / ssteps, "kernel_ms_fastest": r["kernel_ms_best"],
+            # kernel_ms includes the in-kernel exchange (and the wait for the slowest GPU) when finished_on_device
+            "exchange_ms_per_call": r["finish_ms"] / ssteps,
+            "host_overhead_ms_per_call": per_call_ms - r["kernel_ms"] / ssteps,
+            "finished_on_device": r["finished_on_device"],
+        }
 
     # ---- LM iterations/s through the host-side mirror of LevenbergMarquardt.minimize ----
     lm = None
@@ -283,8 +364,18 @@ def run_own(args):
             # the same fit with one K1 loss pass per trial point + one K2 pass per outer iteration (no speculation)
             plain = sohost.bench_lm(ctx, ds, fam, TRUTH * 1.1, barrier, max_over_ranks, speculate=False)
             lm["without_speculation"] = {k: plain[k] for k in ("seconds", "iterations", "iterations_per_s", "k2_passes", "k1_passes")}
+            lm["rows_total"] = total_rows
+            if ds_s is not None:
+                if ds_s is ds:
+                    lm["strong"] = {k: lm[k] for k in ("seconds", "iterations", "iterations_per_s", "k2_passes", "k1_passes")}
+                else:
+                    ls = sohost.bench_lm(ctx, ds_s, fam, TRUTH * 1.1, barrier, max_over_ranks)
+                    lm["strong"] = {k: ls[k] for k in ("seconds", "iterations", "iterations_per_s", "k2_passes", "k1_passes", "minimiser")}
+                lm["strong"]["rows_total"] = strong_rows * world
         except Exception as e:  # the evaluation numbers stand on their own
             lm = {"unavailable": f"{type(e).__name__}: {e}"}
+    if ds_s is not None and ds_s is not ds:
+        ds_s.free()
 
     # ---- e2e: host buffers, H2D of the observations + evaluation + result read-back, every step ----
     e2e = None
@@ -297,7 +388,8 @@ def run_own(args):
         import oracle
         oracle.build()
         threads = host_threads()
-        v, ms = cpu_single_pass(threads)
+        v, ms = cpu_single_pass(threads, budget_s=8.0)
+        v1, ms1 = cpu_single_pass(1, budget_s=4.0)
         mref = reference_sample_rows(threads, target_s=2.0)
         Xr, yr = oracle.generate(oracle.GAUSS_EXPBKG, mref, 1, TRUTH, SEED, NOISE)
         t0 = time.perf_counter()
@@ -306,6 +398,8 @@ def run_own(args):
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{ms} observations, single-pass analytic loss+J^T r+J^T J, oracle par[{threads}] "
                          f"({cpu_model_name()}); the JVM/Spark reference cannot run here (no JVM)",
+               "seq": {"value": v1, "unit": UNIT, "cores": 1,
+                       "sample": f"{ms1} observations, same single-pass evaluation, oracle seq (models SeqDataSet)"},
                "reference_algorithm": {"value": vref, "unit": UNIT, "cores": threads,
                                        "sample": f"{mref} observations, FD Jacobian + 11-pass QR + loss pass "
                                                  f"(what LevenbergMarquardt.iterate does per outer iteration)"}}
@@ -321,12 +415,13 @@ def run_own(args):
         alg_bytes = 16.0 * m                                   # per launch: one GPU's shard, 16 B per observation
         ach = alg_bytes / (kernel_ms_max / args.steps * 1e-3) / 1e9
         # DRAM bytes of one launch from the committed `ncu --set full` capture (only if it was taken at this launch size)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_at = None, None, None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
             if int(tr["rows_per_launch"]) == int(m):
                 traffic = float(tr["dram_read_bytes"]) + float(tr["dram_write_bytes"])
                 traffic_src = tr["source"]
+                traffic_at = tr.get("measured_at")
         except Exception:
             pass
         # north_star's roofline is the SLOWER of bytes at HBM bandwidth and flops at FP64 peak; this kernel executes 45 FP64
@@ -344,28 +439,43 @@ def run_own(args):
                     "note": "explanatory only; roofline.frac above is against HBM"}
         except Exception:
             pass
+        if strong is not None:
+            sb = 16.0 * strong["rows_per_gpu"]
+            strong["achieved_gbs_per_gpu"] = sb / (strong["kernel_ms_per_call"] * 1e-3) / 1e9
+            strong["frac_of_hbm"] = strong["achieved_gbs_per_gpu"] / hbm_peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world, m, args.scaling),
             "device_ms_per_step": device_ms / args.steps, "kernel_ms_per_step": kernel_ms_max / args.steps,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "traffic_measured_at": traffic_at,
+                         "peak_source": peak_src,
                          "kernel": "k_scalar<OpNormalEq<FamGaussExpBkg>>", "algorithmic_bytes_per_launch": alg_bytes,
                          # the timed region runs under the board's power cap (see "clocks"); the fastest single launch of the
                          # region is reported beside the average the roofline fraction is computed from
                          "fastest_launch": {"kernel_ms": kernel_ms_best, "achieved": alg_bytes / (kernel_ms_best * 1e-3) / 1e9,
                                             "frac": alg_bytes / (kernel_ms_best * 1e-3) / 1e9 / hbm_peak},
+                         "exchange_ms_per_step": head["finish_ms"] / args.steps,
+                         "host_overhead_ms_per_step": 1e3 * wall_s / args.steps - kernel_ms_max / args.steps,
                          "fp64": fp64},
             "clocks": clocks, "gpu_launches": int(launches),
         }
+        if strong is not None:
+            line["roofline"]["strong_scaling"] = strong
+            line["strong"] = strong
+        if parity is not None:
+            line["config"]["parity"] = parity
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if lm is not None:
             line["lm"] = lm
+            if e2e is not None:
+                # the driver keeps the sub-keys of `e2e`: LM iterations/s (the metric's second half) travels there too
+                line["e2e"]["lm"] = {k: lm[k] for k in ("iterations", "iterations_per_s", "seconds", "rows_total", "strong") if k in lm}
         print(json.dumps(line), flush=True)
     ds.free()
     ctx.close()
@@ -412,7 +522,17 @@ def run_e2e(args, native, ctx, ds, fam, m, world, barrier, max_over_ranks):
         step(i)
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
+    numa = None
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(torch.cuda.current_device())
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        numa = {"gpu_pci": bus, "gpu_numa_node": int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())}
+    except Exception:
+        pass
     out = {"value": rows * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * rows * world,
+           "h2d_gbs_per_gpu": 16 * rows * steps / dt / 1e9, "h2d_gbs_aggregate": 16 * rows * world * steps / dt / 1e9,
+           "host_numa": numa,
            "d2h_bytes_per_step": 21 * 8, "steps": steps, "ms_per_step": 1e3 * dt / steps,
            "rows_per_gpu": rows,
            "what": "so_dataset_clear + so_dataset_append(pinned host -> HBM) + so_eval_normal_eq per step"}

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sched.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 #include <nccl.h>   // types only: the library is dlopen'ed on first multi-GPU use (see NcclApi)
 
@@ -158,6 +160,59 @@ int fail(so_ctx* ctx, int code, const char* fmt, ...) {
   do { ncclResult_t r_ = (call);                                                                      \
     if (r_ != ncclSuccess) return fail((ctx), SO_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
 
+// Host memory that a GPU reads over PCIe should live on the NUMA node that GPU hangs off: with the pinned buffers of
+// 4-8 ranks all on node 0 the copies of the GPUs of the other socket cross the inter-socket link and round 1's ingest
+// stopped scaling at ~110 GB/s per box.  While one of these is alive the calling thread runs on (and therefore allocates
+// from) the node of `device`: preferred-node memory policy where the container allows the syscall, CPU affinity + the
+// kernel's local-allocation default where it does not.  Best effort: a box without NUMA information is left alone.
+struct NumaNear {
+  cpu_set_t old_set;
+  bool moved = false, policy = false;
+  int node = -1;
+  static int node_of(int device) {
+    char bus[32] = {};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    int nd = -1;
+    if (FILE* fp = fopen(path.c_str(), "r")) { if (fscanf(fp, "%d", &nd) != 1) nd = -1; fclose(fp); }
+    return nd;
+  }
+  explicit NumaNear(int device) {
+    node = node_of(device);
+    if (node < 0 || node >= 64) return;
+    unsigned long mask = 1ul << node;
+#ifdef SYS_set_mempolicy
+    policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
+#endif
+    char path[96];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* fp = fopen(path, "r");
+    if (!fp) return;
+    char buf[4096] = {};
+    const bool got = fgets(buf, sizeof buf, fp) != nullptr;
+    fclose(fp);
+    if (!got || sched_getaffinity(0, sizeof old_set, &old_set) != 0) return;
+    cpu_set_t want;
+    CPU_ZERO(&want);
+    int any = 0;
+    for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+      int a = 0, b = 0;
+      const int k = sscanf(tok, "%d-%d", &a, &b);
+      if (k == 1) b = a;
+      if (k < 1) continue;
+      for (int c = a; c <= b && c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &old_set)) { CPU_SET(c, &want); ++any; }
+    }
+    if (any && sched_setaffinity(0, sizeof want, &want) == 0) moved = true;
+  }
+  ~NumaNear() {
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+#ifdef SYS_set_mempolicy
+    if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+  }
+};
+
 int setup_device(so_ctx* ctx, Device& d) {
   SO_CUDA(ctx, cudaSetDevice(d.id));
   cudaDeviceProp prop;
@@ -181,6 +236,7 @@ int setup_device(so_ctx* ctx, Device& d) {
   SO_CUDA(ctx, cudaMalloc(&d.mailbox, kMailBytes));
   SO_CUDA(ctx, cudaMemset(d.mailbox, 0, kMailBytes));
   void* hp = nullptr;
+  NumaNear near(d.id);
   SO_CUDA(ctx, cudaHostAlloc(&hp, sizeof(double) * (kMailCap + 4) + 128, cudaHostAllocMapped | cudaHostAllocPortable));
   memset(hp, 0, sizeof(double) * (kMailCap + 4) + 128);
   d.hres = static_cast<double*>(hp);
@@ -743,9 +799,13 @@ extern "C" int so_stats_reset(so_ctx* ctx) {
   return SO_OK;
 }
 
-// pinned host memory for callers that want full-speed H2D (e.g. a JNI direct buffer)
+// pinned host memory for callers that want full-speed H2D (e.g. a JNI direct buffer); placed on the NUMA node of the
+// calling thread's current device
 extern "C" int so_host_alloc(size_t bytes, void** out) {
   if (!out) return SO_EINVAL;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  NumaNear near(dev);
   cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
   if (e != cudaSuccess) return fail(nullptr, SO_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
   return SO_OK;
@@ -805,6 +865,7 @@ constexpr size_t kStageBytes = (size_t)64 << 20;      // per pinned staging buff
 
 int ensure_staging(so_ctx* ctx, Device& dv) {
   SO_CUDA(ctx, cudaSetDevice(dv.id));
+  NumaNear near(dv.id);
   for (int k = 0; k < 2; ++k) {
     if (!dv.stage[k]) SO_CUDA(ctx, cudaHostAlloc(&dv.stage[k], kStageBytes, cudaHostAllocDefault));
     if (!dv.stage_free[k]) SO_CUDA(ctx, cudaEventCreateWithFlags(&dv.stage_free[k], cudaEventDisableTiming));
