@@ -120,6 +120,12 @@ void so_host_free(void* p);
  * used for the 1/m normalisation is the sum over ranks. */
 int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out);
 
+/* The row range [*begin, *begin + *rows) of shard `g` when `m` observations of `f` inputs are split over `G` GPUs: contiguous
+ * blocks of ceil(m/G) rows, an even count for f == 1 (every shard then starts 16-byte aligned).  This is the split
+ * so_dataset_create makes in single-process mode and the one a rank-mode caller should give rank g; the analogue of the
+ * partitioner behind spark-apps/.../SparkDataSetConverter.scala:42-45.  Pure host arithmetic: callable without a GPU. */
+int so_shard_plan(int64_t m, int f, int G, int g, int64_t* begin, int64_t* rows);
+
 /* Append `rows` observations from host memory.  Pinned sources (so_host_alloc, cudaHostRegister) are copied directly;
  * pageable sources are staged through two pinned buffers so that the host-side memcpy overlaps the DMA.  `DataSet.++` (DataSet.scala:36) / Seq -> data-set conversion (SeqDataSetConverter.scala:28). */
 int so_dataset_append(so_dataset* ds, const double* X_rowmajor, const double* y, int64_t rows);
@@ -230,7 +236,7 @@ typedef struct so_call_stats {
   double  sum_finish_ms;
   double  min_kernel_ms;   /* fastest kernel_ms since so_init / so_stats_reset (0: none yet) */
   int64_t finished_on_device; /* last call: 1 = cross-GPU sum and host delivery done by the evaluation kernel itself (results up to
-                              4096 doubles), 0 = NCCL all-reduce + device-to-host copy */
+                              16384 doubles), 0 = NCCL all-reduce + device-to-host copy */
 } so_call_stats;
 /* Event times are collected lazily: so_stats waits for the last evaluation's events (microseconds), the evaluation calls do not. */
 int so_stats(so_ctx* ctx, so_call_stats* out);

@@ -815,6 +815,16 @@ extern "C" void so_host_free(void* p) { if (p) cudaFreeHost(p); }
 // =================================================================================================
 // Data set
 // =================================================================================================
+// contiguous row blocks of ceil(m/G) rows; pure host arithmetic, no GPU needed
+extern "C" int so_shard_plan(int64_t m, int f, int G, int g, int64_t* begin, int64_t* rows) {
+  if (m < 0 || f < 1 || G < 1 || g < 0 || g >= G || !begin || !rows) return SO_EINVAL;
+  int64_t mg = (m + G - 1) / G;
+  if (f == 1 && (mg & 1) && G > 1) ++mg;    // keep every shard's first row 16-byte aligned for 128-bit loads
+  const int64_t b = std::min<int64_t>((int64_t)g * mg, m), e = std::min<int64_t>((int64_t)(g + 1) * mg, m);
+  *begin = b; *rows = e - b;
+  return SO_OK;
+}
+
 extern "C" int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out) {
   if (!ctx || !out) return SO_EINVAL;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -823,12 +833,11 @@ extern "C" int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out
   ds->ctx = ctx; ds->m = m; ds->f = f;
   const int G = (int)ctx->devs.size();
   ds->shards.resize(G);
-  int64_t mg = (m + G - 1) / G;
-  if (f == 1 && (mg & 1) && G > 1) ++mg;    // keep every shard's first row 16-byte aligned for 128-bit loads
   for (int g = 0; g < G; ++g) {
-    const int64_t b = std::min<int64_t>((int64_t)g * mg, m), e = std::min<int64_t>((int64_t)(g + 1) * mg, m);
+    int64_t b = 0, cnt = 0;
+    so_shard_plan(m, f, G, g, &b, &cnt);
     ShardMem& sm = ds->shards[g];
-    sm.cap = e - b;
+    sm.cap = cnt;
     if (sm.cap > 0) {
       cudaError_t ce = cudaSetDevice(ctx->devs[g].id);
       if (ce == cudaSuccess) ce = cudaMalloc(&sm.X, sizeof(double) * (size_t)sm.cap * f);

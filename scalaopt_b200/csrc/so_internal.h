@@ -22,7 +22,7 @@ namespace so {
 // Mailboxes are double-buffered on the parity of the sequence number: a rank can be at most one call ahead of a peer
 // (it cannot finish call c+1 before every peer has posted its sums for c+1, i.e. has finished reading call c).
 constexpr int kMaxRanks = 8;
-constexpr int kMailCap = 4096;          // doubles per (parity, source rank) slot: results up to this size take mode 1
+constexpr int kMailCap = 16384;         // doubles per (parity, source rank) slot: results up to this size take mode 1
 struct Ctl {
   unsigned int ticket[4];
   int mode, world, rank, cap;

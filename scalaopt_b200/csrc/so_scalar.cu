@@ -478,7 +478,7 @@ __device__ __noinline__ void process1_cold(const typename Op::Args& args, double
 // registers and no issue slots in the compute warps, and 64-96 KB per block are in flight whatever the occupancy.
 // A stage is released (fence.proxy.async + block barrier) after its rows were processed and refilled by thread 0
 // right after that barrier (see "Releasing a stage" in the loop).
-// What ncu / A-B runs showed on the way here (profiles/, gpurun_out/ab*.log):
+// What ncu / A-B runs showed on the way here (profiles/r1_k2_*.json, profiles/r1_k2_ab*.log):
 //   direct LDG.128                     FP64 pipe 63% busy, top stall long_scoreboard        r1_k2_v1_direct_ldg.json
 //   ring + __syncthreads per chunk     FP64 pipe 70% busy, 9% of samples on the barrier     r1_k2_v2_block_ring.json
 //   warp-private rings (1 KB copies)   slower than the block ring (54% vs 64% of roofline)  DESIGN.md
@@ -733,7 +733,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       }
       if constexpr (std::is_same<Fam, FamGaussExpBkg>::value) {
         // the headline kernel (BASELINE config 3): 2 rows per range-checked group, 8 rows per thread per chunk,
-        // 2 blocks/SM.  A/B runs on one box (gpurun_out/call26-27): 4 rows per group -1 %, 4 rows per
+        // 2 blocks/SM.  A/B runs on one box (profiles/r1_k2_call26_groups.log, r1_k2_call27_groups.log): 4 rows per group -1 %, 4 rows per
         // chunk -3 %, 4096-entry exp table (degree-3 polynomial) +1.5 %, no range check at all +1.5 %, 20-24 warps/SM -8..-25 %.
 #ifndef SO_K2_G
 #define SO_K2_G 2
@@ -743,7 +743,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
 #define SO_K2_RPT 8
 #endif
         // every exp argument in range for this shard's inputs (known after launch_range): no per-row range check, and
-        // then 4 rows per group are the better grouping (gpurun_out/ab5-7.log: 3.22 vs 3.31 ms per 1e9 rows)
+        // then 4 rows per group are the better grouping (profiles/r1_k2_ab5_group4.log .. ab7: 3.22 vs 3.31 ms per 1e9 rows)
         if (s.has_range && Fam::args_in_range(pre, s.tmin, s.tmax)) {
 #ifndef SO_K2NC_G
 #define SO_K2NC_G 4
@@ -885,7 +885,7 @@ size_t scalar_partials_needed(Kind kind, int n, int k, int sm_count) {
 }
 
 #ifndef SO_NLL_G
-#define SO_NLL_G 2      // gpurun_out/ab11.log: 2 rows per checked group 2.36 ms vs 2.56 with 4; check-free with 4: 2.27 ms per 1e9 rows
+#define SO_NLL_G 2      // profiles/r1_nll_ab11_groups.log: 2 rows per checked group 2.36 ms vs 2.56 with 4; check-free with 4: 2.27 ms per 1e9 rows
 #define SO_NLL_MINB 3
 #define SO_NLL_RPT 4
 #define SO_NLL_NC_G 4

@@ -25,7 +25,7 @@ NCCL_UID_BYTES = 128
 EXPORTS = [
     "so_init", "so_nccl_unique_id", "so_init_rank", "so_shutdown", "so_last_error", "so_abi_version",
     "so_host_alloc", "so_host_free",
-    "so_dataset_create", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
+    "so_shard_plan", "so_dataset_create", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
     "so_dataset_size", "so_dataset_head", "so_dataset_slice", "so_dataset_free",
     "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_qr", "so_eval_line", "so_eval_hess_vec", "so_eval_nll", "so_stats", "so_stats_reset",
 ]
@@ -80,6 +80,7 @@ def load():
     L.so_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.so_host_free.argtypes = [vp]
     L.so_host_free.restype = None
+    L.so_shard_plan.argtypes = [i64, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.so_dataset_create.argtypes = [vp, i64, i32, C.POINTER(vp)]
     L.so_dataset_append.argtypes = [vp, vp, vp, i64]
     L.so_dataset_load_raw.argtypes = [vp, C.c_char_p, C.c_char_p, i64, i64]
@@ -109,6 +110,15 @@ def _vec(x):
 
 def _ptr(a):
     return a.ctypes.data_as(_dp)
+
+
+def shard_plan(m: int, f: int, G: int, g: int):
+    """(begin, rows) of shard g of G (so_shard_plan; needs no GPU)."""
+    b, r = C.c_int64(), C.c_int64()
+    rc = load().so_shard_plan(m, f, G, g, C.byref(b), C.byref(r))
+    if rc != 0:
+        raise NativeError(rc, "so_shard_plan: bad arguments")
+    return b.value, r.value
 
 
 class PinnedBuffer:
