@@ -6,14 +6,14 @@
 namespace so {
 namespace {
 
-__global__ void __launch_bounds__(256) k_finish(unsigned int* ticket, const double* __restrict__ out, int q) {
+__global__ void __launch_bounds__(1024) k_finish(unsigned int* ticket, const double* __restrict__ out, int q) {
   so_finish(ticket, out, q);
 }
 
 }  // namespace
 
 int launch_finish(const Shard& s, int q) {
-  k_finish<<<1, 256, 0, s.stream>>>(s.ticket, s.out, q);
+  k_finish<<<1, 1024, 0, s.stream>>>(s.ticket, s.out, q);
   return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
 }
 
