@@ -15,6 +15,7 @@
 //               (profiles/r1_fp64_peak.json), and one DMMA replaces 8 DFMA issue slots + their operand traffic.
 //   larger n    warp-specialised shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_ws below), f <= 512
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "so_wide.cuh"
@@ -832,10 +833,21 @@ int launch_ws(const Shard& s, const Params& P) {
 
 }  // namespace
 
+// so_gram_ph.cu
+size_t gram_ph_partials_needed(int f, int sm_count);
+int launch_gram_ph(const Shard& s, int fam, const Params& P);
+constexpr int kPhMaxF = 104;
+static bool gram_legacy() {          // A/B switch: SCALAOPT_GRAM_LEGACY=1 routes 8 < n through round 1's k_gram_tri / k_gram_ws
+  static const bool on = [] { const char* e = getenv("SCALAOPT_GRAM_LEGACY"); return e && *e && *e != '0'; }();
+  return on;
+}
+
 size_t gram_partials_needed(int n, int f, int sm_count) {
   if (n <= 8) return (size_t)sm_count * 8 * (size_t)(n * (n + 1) / 2 + n + 1);
   const int T = (n + 1 + 7) / 8;
-  if (n + 1 <= 48) return (size_t)sm_count * 4 * ((size_t)(T * (T + 1) / 2) * 64 + 16 * T + 4);
+  const size_t ph = f <= kPhMaxF ? gram_ph_partials_needed(f, sm_count) : 0;
+  if (n + 1 <= 48) return std::max(ph, (size_t)sm_count * 4 * ((size_t)(T * (T + 1) / 2) * 64 + 16 * T + 4));
+  if (ph) { const WsPlan b0 = ws_plan(f, sm_count); return std::max(ph, (size_t)b0.workers * b0.reps * b0.npatches * kPatchDoubles + (size_t)b0.workers * b0.QE); }
   const WsPlan b = ws_plan(f, sm_count);
   return (size_t)b.workers * b.reps * b.npatches * kPatchDoubles + (size_t)b.workers * b.QE;
 }
@@ -847,6 +859,7 @@ int launch_gram(const Shard& s, int fam, const Params& P) {
   return SO_EUNSUPPORTED;
 #else
   if (P.n <= 8) return fam == kLinear ? dispatch_small<kLinear>(s, P) : dispatch_small<kLogistic>(s, P);
+  if (P.f <= kPhMaxF && !gram_legacy()) return launch_gram_ph(s, fam, P);
   if (P.n + 1 <= 48) return fam == kLinear ? dispatch_tri<kLinear>(s, P) : dispatch_tri<kLogistic>(s, P);
   return fam == kLinear ? launch_ws<kLinear>(s, P) : launch_ws<kLogistic>(s, P);
 #endif
