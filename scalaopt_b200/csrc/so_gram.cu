@@ -8,11 +8,12 @@
 // 2n+1 passes of QR.apply (linalg/QR.scala:131-250) that only ever needed these sums.
 //
 //   n <= 8      one thread per observation, packed upper triangle in registers (FP64 FMA pipe, HBM-bound)
-//   n+1 <= 48   DMMA (mma.sync.m8n8k4.f64): a warp owns the whole upper triangle of 8x8 tiles and streams slabs
-//               of 4 rows.  The A and B fragments of tile (ta, tb) are the SAME registers — lane l holds
-//               Z[row0 + l%4][8t + l/4] — so a slab costs T 64-bit loads per lane, straight from global memory.
+//   f <= 104    k_gram_ph (so_gram_ph.cu): shared-memory staged DMMA SYRK in block-wide phases; DMMA = mma.sync.m8n8k4.f64,
+//               the A and B fragments of tile (ta, tb) are the SAME registers — lane l holds Z[row0 + l%4][8t + l/4].
 //               Measured on this pool's B200: DMMA 37.2 TFLOP/s vs 33.8 for register-resident DFMA
 //               (profiles/r1_fp64_peak.json), and one DMMA replaces 8 DFMA issue slots + their operand traffic.
+//               (Round 1's k_gram_tri — fragments straight from global memory, residual chain in the same warp — is gone:
+//               slower at every width, profiles/r2_gram_legacy.jsonl vs r2_gram_ph_final.jsonl.)
 //   larger n    warp-specialised shared-memory staged DMMA SYRK over 4x4-tile patches (k_gram_ws below), f <= 512
 #include <algorithm>
 #include <cstdlib>
@@ -98,252 +99,6 @@ int dispatch_small(const Shard& s, const Params& P) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 8 < n, n + 1 <= 8 T <= 48: DMMA over the upper triangle of 8x8 tiles
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-template <int T> __host__ __device__ constexpr int tri_tiles() { return T * (T + 1) / 2; }
-
-// EXTRA = true (f a multiple of 8): the tiles cover the f input columns only; the intercept's 1-column and the
-// residual column are NOT padded into a sixth tile column — their sums (sum x_c, sum x_c res, sum res, sum res^2,
-// row count) are accumulated with plain DADD/DFMA on the FP64 pipe, which is idle while the tensor pipe runs the
-// DMMAs.  For f = 32 that is 10 DMMAs per 4-row slab instead of 15.
-template <int FAM, int T, bool EXTRA>
-__global__ void __launch_bounds__(kThreads, 2)
-k_gram_tri(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
-           double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  constexpr int NT = tri_tiles<T>();
-  constexpr int QT = NT * 64 + (EXTRA ? 16 * T + 4 : 0);   // tiles, then [sum x_c] [sum x_c res] [cnt, sum res, sum res^2]
-  extern __shared__ double smem[];            // QT doubles: this block's tiles (lane-major) and extras
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rsel = lane & 3, csel = lane >> 2;
-  const int f = P.f, icpt = P.icpt, n = P.n;
-  const int col_one = (icpt && !EXTRA) ? f : -1, col_res = EXTRA ? -2 : f + icpt;
-  if (FAM == kLogistic) { exp_table_init(); __syncthreads(); }
-
-  double pz[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) pz[t] = (8 * t + csel < f) ? P.p[icpt + 8 * t + csel] : 0.0;
-  const double p0 = icpt ? P.p[0] : 0.0;
-  double acc[NT][2];
-#pragma unroll
-  for (int i = 0; i < NT; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
-  double s_one[EXTRA ? T : 1], s_res[EXTRA ? T : 1], cnt = 0.0, sr = 0.0, rr = 0.0;
-#pragma unroll
-  for (int t = 0; t < (EXTRA ? T : 1); ++t) { s_one[t] = 0.0; s_res[t] = 0.0; }
-
-  const int64_t nslabs = (rows + 3) >> 2;
-  const int64_t sstr = (int64_t)gridDim.x * kWarps;
-  int64_t slab = (int64_t)blockIdx.x * kWarps + warp;
-
-  double cur[T], nxt[T], ycur = 0.0, ynxt = 0.0;
-  bool vcur = false, vnxt = false;
-  auto load = [&](int64_t s, double (&fr)[T], double& yv, bool& valid) {
-    const int64_t row = 4 * s + rsel;
-    valid = row < rows;
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const int col = 8 * t + csel;
-      fr[t] = (valid && col < f) ? ld_stream(X + row * f + col) : 0.0;
-    }
-    yv = valid ? ld_stream(y + row) : 0.0;
-  };
-  if (slab < nslabs) load(slab, cur, ycur, vcur);
-  while (slab < nslabs) {
-    const int64_t ns = slab + sstr;
-    if (ns < nslabs) load(ns, nxt, ynxt, vnxt);
-    if (EXTRA) {       // the tiles depend on the loads only: issue them first, the residual chain overlaps with them
-#pragma unroll
-      for (int ta = 0; ta < T; ++ta)
-#pragma unroll
-        for (int tb = ta; tb < T; ++tb) {
-          const int idx = ta * T - ta * (ta - 1) / 2 + (tb - ta);
-          dmma(acc[idx][0], acc[idx][1], cur[ta], cur[tb]);
-        }
-    }
-    // linear predictor of the slab's 4 rows: lanes with equal lane%4 hold one row
-    double dot = 0.0;
-#pragma unroll
-    for (int t = 0; t < T; ++t) dot = fma(pz[t], cur[t], dot);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 8);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 16);
-    const double z = dot + p0;
-    double res;
-    if (FAM == kLinear) {
-      res = ycur - z;
-    } else {
-      const double e = so_exp(-fabs(z));
-      const double inv = so_rcp_fast(1.0 + e);
-      res = ((z >= 0.0) ? inv : e * inv) - ycur;
-    }
-    if (!vcur) res = 0.0;
-    if (EXTRA) {
-#pragma unroll
-      for (int t = 0; t < T; ++t) { s_one[t] += cur[t]; s_res[t] = fma(cur[t], res, s_res[t]); }
-      if (csel == 0) { cnt += vcur ? 1.0 : 0.0; sr += res; rr = fma(res, res, rr); }
-    } else {
-      const double one = vcur ? 1.0 : 0.0;
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int col = 8 * t + csel;
-        if (col == col_one) cur[t] = one;
-        if (col == col_res) cur[t] = res;
-      }
-    }
-    if (!EXTRA) {
-#pragma unroll
-      for (int ta = 0; ta < T; ++ta)
-#pragma unroll
-        for (int tb = ta; tb < T; ++tb) {
-          const int idx = ta * T - ta * (ta - 1) / 2 + (tb - ta);
-          dmma(acc[idx][0], acc[idx][1], cur[ta], cur[tb]);
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) cur[t] = nxt[t];
-    ycur = ynxt; vcur = vnxt;
-    slab = ns;
-  }
-
-  if (EXTRA) {      // fold the 4 row slots of a column (lanes csel*4 + 0..3), and the per-row scalars over the warp
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      s_one[t] += __shfl_xor_sync(0xffffffffu, s_one[t], 1); s_one[t] += __shfl_xor_sync(0xffffffffu, s_one[t], 2);
-      s_res[t] += __shfl_xor_sync(0xffffffffu, s_res[t], 1); s_res[t] += __shfl_xor_sync(0xffffffffu, s_res[t], 2);
-    }
-    cnt = warp_sum(cnt); sr = warp_sum(sr); rr = warp_sum(rr);
-  }
-  // block sum in warp order (deterministic), lane-major tile storage: tile[idx][lane*2 + reg]
-  for (int w = 0; w < kWarps; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int i = 0; i < NT; ++i) {
-        double* tile = smem + i * 64 + lane * 2;
-        if (w == 0) { tile[0] = acc[i][0]; tile[1] = acc[i][1]; }
-        else { tile[0] += acc[i][0]; tile[1] += acc[i][1]; }
-      }
-      if (EXTRA) {
-        double* ex = smem + NT * 64;
-        if (rsel == 0) {
-#pragma unroll
-          for (int t = 0; t < T; ++t) {
-            if (w == 0) { ex[8 * t + csel] = s_one[t]; ex[8 * T + 8 * t + csel] = s_res[t]; }
-            else { ex[8 * t + csel] += s_one[t]; ex[8 * T + 8 * t + csel] += s_res[t]; }
-          }
-        }
-        if (lane == 0) {
-          double* sc = ex + 16 * T;
-          if (w == 0) { sc[0] = cnt; sc[1] = sr; sc[2] = rr; sc[3] = 0.0; }
-          else { sc[0] += cnt; sc[1] += sr; sc[2] += rr; }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  for (int q = threadIdx.x; q < QT; q += kThreads) partials[(size_t)blockIdx.x * QT + q] = smem[q];
-  __threadfence();
-  __syncthreads();
-  __shared__ unsigned int s_last;
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    // emit the API layout: packed upper triangle over parameters (a <= b), then Jtr, then rtr.
-    // Z column of parameter a: (icpt ? (a == 0 ? ONE : a - 1) : a); ONE = the intercept's 1-column, RES = the residual.
-    constexpr int ONE = -1, RES = -2;
-    const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
-    const double jsgn = (FAM == kLinear) ? -1.0 : 1.0;         // J r = -x~ rho for least squares
-    for (int q = threadIdx.x; q < Qo; q += kThreads) {
-      int ca, cb;
-      double sgn = 1.0;
-      if (q < Tn) {
-        int a = 0, rem = q;                     // unpack (a, b) from the row-major packed index
-        while (rem >= n - a) { rem -= n - a; ++a; }
-        const int b = a + rem;
-        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
-        cb = icpt ? (b == 0 ? ONE : b - 1) : b;
-      } else if (q < Tn + n) {
-        const int a = q - Tn;
-        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
-        cb = RES;
-        sgn = jsgn;
-      } else {
-        ca = RES; cb = RES;
-      }
-      int off;
-      if (EXTRA) {
-        const int ex = NT * 64;
-        if (ca >= 0 && cb >= 0) {
-          if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }
-          const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
-          off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
-        } else if (ca == ONE && cb == ONE) off = ex + 16 * T;                 // row count
-        else if (ca == RES && cb == RES) off = ex + 16 * T + 2;               // sum res^2
-        else if ((ca == ONE && cb == RES) || (ca == RES && cb == ONE)) off = ex + 16 * T + 1;   // sum res
-        else if (ca == ONE || cb == ONE) off = ex + (ca == ONE ? cb : ca);    // sum x_c
-        else off = ex + 8 * T + (ca == RES ? cb : ca);                        // sum x_c res
-      } else {
-        if (ca == ONE) ca = f;
-        if (cb == ONE) cb = f;
-        if (ca == RES) ca = f + icpt;
-        if (cb == RES) cb = f + icpt;
-        if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }
-        const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
-        off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
-      }
-      double s = 0.0;
-      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += __ldcg(&partials[(size_t)b2 * QT + off]);
-      out[q] = s * sgn;
-    }
-    if (threadIdx.x == 0) *ticket = 0u;
-    so_finish(ticket, out, Qo);
-  }
-}
-
-template <int FAM, int T, bool EXTRA>
-int launch_tri(const Shard& s, const Params& P) {
-  auto kern = k_gram_tri<FAM, T, EXTRA>;
-  constexpr int QT = tri_tiles<T>() * 64 + (EXTRA ? 16 * T + 4 : 0);
-  const size_t smem = sizeof(double) * QT;
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
-  if (per_sm < 1) per_sm = 1;
-  const int64_t nslabs = (s.rows + 3) / 4;
-  const int64_t want = std::max<int64_t>(1, (nslabs + kWarps - 1) / kWarps);
-  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
-  const int Qo = P.n * (P.n + 1) / 2 + P.n + 1;
-  if ((size_t)grid * QT > s.partials_doubles || (size_t)Qo > s.out_doubles) return SO_ENOMEM;
-  kern<<<grid, kThreads, smem, s.stream>>>(s.X, s.y, s.rows, P, s.partials, s.out, s.ticket);
-  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
-}
-
-template <int FAM>
-int dispatch_tri(const Shard& s, const Params& P) {
-  if (P.f % 8 == 0) {                      // tiles over the inputs only, extras on the FP64 pipe
-    switch (P.f / 8) {
-      case 1: return launch_tri<FAM, 1, true>(s, P);
-      case 2: return launch_tri<FAM, 2, true>(s, P);
-      case 3: return launch_tri<FAM, 3, true>(s, P);
-      case 4: return launch_tri<FAM, 4, true>(s, P);
-      case 5: return launch_tri<FAM, 5, true>(s, P);
-    }
-  }
-  const int T = (P.n + 1 + 7) / 8;
-  switch (T) {
-    case 2: return launch_tri<FAM, 2, false>(s, P);
-    case 3: return launch_tri<FAM, 3, false>(s, P);
-    case 4: return launch_tri<FAM, 4, false>(s, P);
-    case 5: return launch_tri<FAM, 5, false>(s, P);
-    case 6: return launch_tri<FAM, 6, false>(s, P);
-  }
-  return SO_EUNSUPPORTED;
-}
-
-// ---------------------------------------------------------------------------------------------------
 // n + 1 > 48 (f up to 512 inputs): warp-specialised, shared-memory staged DMMA SYRK (k_gram_ws).
 //   * The DMMA tiles cover the f INPUT columns only (T = ceil(f/8) tile columns).  The upper triangle of tiles is
 //     cut into 4x4-tile patches (32x32 entries); a consumer warp owns one patch (16 DMMA accumulators = 64
@@ -368,6 +123,10 @@ int dispatch_tri(const Shard& s, const Params& P) {
 //     per 2 056-byte row).  Spare consumer warps share a patch with another warp and split the slabs of a chunk
 //     between them ("reps"); ws_plan() balances the DMMA count over the four SM sub-partitions.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 constexpr int kWsConsumers = 12, kWsProducers = 4, kWsThreads = 32 * (kWsConsumers + kWsProducers);
 constexpr int kPatch = 4, kWsMaxStages = 3, kWsMaxRows = 128;
 constexpr int kPatchDoubles = kPatch * kPatch * 64;
@@ -837,32 +596,18 @@ int launch_ws(const Shard& s, const Params& P) {
 size_t gram_ph_partials_needed(int f, int sm_count);
 int launch_gram_ph(const Shard& s, int fam, const Params& P);
 constexpr int kPhMaxF = 104;
-static bool gram_legacy() {          // A/B switch: SCALAOPT_GRAM_LEGACY=1 routes 8 < n through round 1's k_gram_tri / k_gram_ws
-  static const bool on = [] { const char* e = getenv("SCALAOPT_GRAM_LEGACY"); return e && *e && *e != '0'; }();
-  return on;
-}
 
 size_t gram_partials_needed(int n, int f, int sm_count) {
   if (n <= 8) return (size_t)sm_count * 8 * (size_t)(n * (n + 1) / 2 + n + 1);
-  const int T = (n + 1 + 7) / 8;
-  const size_t ph = f <= kPhMaxF ? gram_ph_partials_needed(f, sm_count) : 0;
-  if (n + 1 <= 48) return std::max(ph, (size_t)sm_count * 4 * ((size_t)(T * (T + 1) / 2) * 64 + 16 * T + 4));
-  if (ph) { const WsPlan b0 = ws_plan(f, sm_count); return std::max(ph, (size_t)b0.workers * b0.reps * b0.npatches * kPatchDoubles + (size_t)b0.workers * b0.QE); }
+  if (f <= kPhMaxF) return gram_ph_partials_needed(f, sm_count);
   const WsPlan b = ws_plan(f, sm_count);
   return (size_t)b.workers * b.reps * b.npatches * kPatchDoubles + (size_t)b.workers * b.QE;
 }
 
 int launch_gram(const Shard& s, int fam, const Params& P) {
-#ifdef SO_GRAM_MINIMAL      // tools/gram_ab.cu: only the shapes under test
-  if (P.f == 32) return fam == kLinear ? launch_tri<kLinear, 4, true>(s, P) : launch_tri<kLogistic, 4, true>(s, P);
-  if (P.f == 33) return launch_tri<kLinear, 5, false>(s, P);
-  return SO_EUNSUPPORTED;
-#else
   if (P.n <= 8) return fam == kLinear ? dispatch_small<kLinear>(s, P) : dispatch_small<kLogistic>(s, P);
-  if (P.f <= kPhMaxF && !gram_legacy()) return launch_gram_ph(s, fam, P);
-  if (P.n + 1 <= 48) return fam == kLinear ? dispatch_tri<kLinear>(s, P) : dispatch_tri<kLogistic>(s, P);
+  if (P.f <= kPhMaxF) return launch_gram_ph(s, fam, P);
   return fam == kLinear ? launch_ws<kLinear>(s, P) : launch_ws<kLogistic>(s, P);
-#endif
 }
 
 }  // namespace wide

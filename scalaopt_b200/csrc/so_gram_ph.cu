@@ -14,9 +14,10 @@
 //   phase B  all 16 warps run DMMAs (mma.sync.m8n8k4.f64) on that chunk: the fragments of a 4-row slab are T LDS.64
 //            per lane (A and B fragments of a tile pair are the same registers), the accumulations sum x_c and
 //            sum x_c res are independent DFMAs on the same fragments.  No dependent FP64 chain in this phase.
-// Rows travel global -> shared memory with cp.async (16 bytes per request when rows are 16-byte aligned, 8 otherwise)
-// into a two-stage ring, row pitch 8T+4 doubles (fragment reads and the interleaved LDS.128 of phase A are both
-// bank-conflict free); chunk c+1 is in flight during both phases of chunk c, no thread ever waits for a load it issued.
+// Rows travel global -> shared memory into a two-stage ring; chunk c+1 is in flight during both phases of chunk c and no
+// thread ever waits for a load it issued.  Even f, aligned base: ONE cp.async.bulk.tensor.2d (TMA, SASS UTMALDG) per 16
+// columns of the chunk, 128-byte swizzle (layout kTma below).  Otherwise cp.async (LDGSTS) into rows of pitch 8T+4 doubles.
+// Both layouts make the fragment reads of phase B and the LDS.128 of phase A bank-conflict free.
 // The upper triangle of 8x8 tiles is dealt round-robin to SPLIT warps (T <= 4: one warp holds all 10 tiles; T = 13: 91
 // tiles over 8 warps), the other 16/SPLIT-way parallelism is over slabs.  As in k_gram_tri's EXTRA mode the tiles cover
 // the f INPUT columns only; the intercept's 1-column and the residual column are sums on the FP64 pipe.
@@ -69,6 +70,102 @@ __host__ __device__ constexpr int ph_split(int T) { return T <= 4 ? 1 : T <= 6 ?
 // rows per chunk: as many as two stages of shared memory hold (kTma stages have no padding but whole 16-column boxes)
 __host__ __device__ constexpr int ph_rows(int T, int layout) { return layout == 1 ? (((T + 1) / 2) * 16 * 8 * 256 * 2 <= 200 * 1024 ? 256 : 128) : (T <= 6 ? 256 : 128); }
 __host__ __device__ constexpr int ph_qt(int T) { return ph_tiles(T) * 64 + 16 * T + 4; }   // tiles | sum x_c | sum x_c res | cnt, sum res, sum res^2
+
+// Block sums in a fixed order (deterministic: slab groups one after the other into shared memory), per-block partials, and
+// the block that draws the last ticket emits the API layout and runs so_finish.  Called by all threads after the row loop.
+template <int FAM, int T, int NTH>
+__device__ __forceinline__ void ph_epilogue(double (&acc)[(ph_tiles(T) + ph_split(T) - 1) / ph_split(T)][2],
+                                            double (&a_one)[(T + ph_split(T) - 1) / ph_split(T)],
+                                            double (&a_res)[(T + ph_split(T) - 1) / ph_split(T)], double cnt, double sr, double rr,
+                                            double* red, const Params& P, double* __restrict__ partials, double* __restrict__ out,
+                                            unsigned int* ticket) {
+  constexpr int kPhThreads = NTH, kPhWarps = NTH / 32;
+  constexpr int SPLIT = ph_split(T), NG = kPhWarps / SPLIT;
+  constexpr int NT = ph_tiles(T), NTS = (NT + SPLIT - 1) / SPLIT, TS = (T + SPLIT - 1) / SPLIT, QT = ph_qt(T);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rsel = lane & 3, csel = lane >> 2;
+  const int sub = warp % SPLIT, grp = warp / SPLIT;
+  const int icpt = P.icpt, n = P.n;
+  for (int i = tid; i < QT; i += kPhThreads) red[i] = 0.0;
+  __syncthreads();
+  // fold the 4 row slots of a column (lanes csel*4 + 0..3)
+#pragma unroll
+  for (int i = 0; i < TS; ++i) {
+    a_one[i] += __shfl_xor_sync(0xffffffffu, a_one[i], 1); a_one[i] += __shfl_xor_sync(0xffffffffu, a_one[i], 2);
+    a_res[i] += __shfl_xor_sync(0xffffffffu, a_res[i], 1); a_res[i] += __shfl_xor_sync(0xffffffffu, a_res[i], 2);
+  }
+  for (int g = 0; g < NG; ++g) {
+    if (grp == g) {
+#pragma unroll
+      for (int i = 0; i < NTS; ++i) {
+        const int idx = i * SPLIT + sub;
+        if (idx < NT) { double* tile = red + idx * 64 + lane * 2; tile[0] += acc[i][0]; tile[1] += acc[i][1]; }
+      }
+      if (rsel == 0) {
+#pragma unroll
+        for (int i = 0; i < TS; ++i) {
+          const int t = i * SPLIT + sub;
+          if (t < T) { red[NT * 64 + 8 * t + csel] += a_one[i]; red[NT * 64 + 8 * T + 8 * t + csel] += a_res[i]; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cnt = warp_sum(cnt); sr = warp_sum(sr); rr = warp_sum(rr);
+  for (int w = 0; w < kPhWarps; ++w) {
+    if (warp == w && lane == 0) { double* sc = red + NT * 64 + 16 * T; sc[0] += cnt; sc[1] += sr; sc[2] += rr; }
+    __syncthreads();
+  }
+  for (int q = tid; q < QT; q += kPhThreads) partials[(size_t)blockIdx.x * QT + q] = red[q];
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last_ph;
+  if (tid == 0) s_last_ph = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last_ph) {
+    __threadfence();
+    // emit the API layout: packed upper triangle over parameters (a <= b), then Jtr, then rtr.
+    // Z column of parameter a: (icpt ? (a == 0 ? ONE : a - 1) : a); ONE = the intercept's 1-column, RES = the residual.
+    constexpr int ONE = -1, RES = -2;
+    const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
+    const double jsgn = (FAM == kLinear) ? -1.0 : 1.0;         // J r = -x~ rho for least squares
+    for (int q = tid; q < Qo; q += kPhThreads) {
+      int ca, cb;
+      double sgn = 1.0;
+      if (q < Tn) {
+        int a = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * q)) * 0.5);   // packed index -> (a, b)
+        while (a > 0 && a * n - a * (a - 1) / 2 > q) --a;
+        while ((a + 1) * n - (a + 1) * a / 2 <= q) ++a;
+        const int b = a + (q - (a * n - a * (a - 1) / 2));
+        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
+        cb = icpt ? (b == 0 ? ONE : b - 1) : b;
+      } else if (q < Tn + n) {
+        const int a = q - Tn;
+        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
+        cb = RES;
+        sgn = jsgn;
+      } else {
+        ca = RES; cb = RES;
+      }
+      int off;
+      const int ex = NT * 64;
+      if (ca >= 0 && cb >= 0) {
+        if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }
+        const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
+        off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
+      } else if (ca == ONE && cb == ONE) off = ex + 16 * T;                 // row count
+      else if (ca == RES && cb == RES) off = ex + 16 * T + 2;               // sum res^2
+      else if ((ca == ONE && cb == RES) || (ca == RES && cb == ONE)) off = ex + 16 * T + 1;   // sum res
+      else if (ca == ONE || cb == ONE) off = ex + (ca == ONE ? cb : ca);    // sum x_c
+      else off = ex + 8 * T + (ca == RES ? cb : ca);                        // sum x_c res
+      double s = 0.0;
+      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += __ldcg(&partials[(size_t)b2 * QT + off]);
+      out[q] = s * sgn;
+    }
+    if (tid == 0) *ticket = 0u;
+    so_finish(ticket, out, Qo);
+  }
+}
 
 // Shared-memory layouts of a stage.
 //   kPadded  R rows at a pitch of 8T+4 doubles, filled by cp.async (LDGSTS, 16- or 8-byte requests): any f, any alignment.
@@ -314,87 +411,7 @@ k_gram_ph(const double* __restrict__ X, const double* __restrict__ y, int64_t ro
   ph_wait_all();
   __syncthreads();
 
-  // ---- block sums in a fixed order (deterministic): slab groups one after the other into shared memory ----
-  double* red = s_x;                                 // QT doubles: tiles lane-major, then the extras
-  for (int i = tid; i < QT; i += kPhThreads) red[i] = 0.0;
-  __syncthreads();
-  // fold the 4 row slots of a column (lanes csel*4 + 0..3)
-#pragma unroll
-  for (int i = 0; i < TS; ++i) {
-    a_one[i] += __shfl_xor_sync(0xffffffffu, a_one[i], 1); a_one[i] += __shfl_xor_sync(0xffffffffu, a_one[i], 2);
-    a_res[i] += __shfl_xor_sync(0xffffffffu, a_res[i], 1); a_res[i] += __shfl_xor_sync(0xffffffffu, a_res[i], 2);
-  }
-  for (int g = 0; g < NG; ++g) {
-    if (grp == g) {
-#pragma unroll
-      for (int i = 0; i < NTS; ++i) {
-        const int idx = i * SPLIT + sub;
-        if (idx < NT) { double* tile = red + idx * 64 + lane * 2; tile[0] += acc[i][0]; tile[1] += acc[i][1]; }
-      }
-      if (rsel == 0) {
-#pragma unroll
-        for (int i = 0; i < TS; ++i) {
-          const int t = i * SPLIT + sub;
-          if (t < T) { red[NT * 64 + 8 * t + csel] += a_one[i]; red[NT * 64 + 8 * T + 8 * t + csel] += a_res[i]; }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  cnt = warp_sum(cnt); sr = warp_sum(sr); rr = warp_sum(rr);
-  for (int w = 0; w < kPhWarps; ++w) {
-    if (warp == w && lane == 0) { double* sc = red + NT * 64 + 16 * T; sc[0] += cnt; sc[1] += sr; sc[2] += rr; }
-    __syncthreads();
-  }
-  for (int q = tid; q < QT; q += kPhThreads) partials[(size_t)blockIdx.x * QT + q] = red[q];
-  __threadfence();
-  __syncthreads();
-  __shared__ unsigned int s_last_ph;
-  if (tid == 0) s_last_ph = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last_ph) {
-    __threadfence();
-    // emit the API layout: packed upper triangle over parameters (a <= b), then Jtr, then rtr.
-    // Z column of parameter a: (icpt ? (a == 0 ? ONE : a - 1) : a); ONE = the intercept's 1-column, RES = the residual.
-    constexpr int ONE = -1, RES = -2;
-    const int Tn = n * (n + 1) / 2, Qo = Tn + n + 1;
-    const double jsgn = (FAM == kLinear) ? -1.0 : 1.0;         // J r = -x~ rho for least squares
-    for (int q = tid; q < Qo; q += kPhThreads) {
-      int ca, cb;
-      double sgn = 1.0;
-      if (q < Tn) {
-        int a = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * q)) * 0.5);   // packed index -> (a, b)
-        while (a > 0 && a * n - a * (a - 1) / 2 > q) --a;
-        while ((a + 1) * n - (a + 1) * a / 2 <= q) ++a;
-        const int b = a + (q - (a * n - a * (a - 1) / 2));
-        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
-        cb = icpt ? (b == 0 ? ONE : b - 1) : b;
-      } else if (q < Tn + n) {
-        const int a = q - Tn;
-        ca = icpt ? (a == 0 ? ONE : a - 1) : a;
-        cb = RES;
-        sgn = jsgn;
-      } else {
-        ca = RES; cb = RES;
-      }
-      int off;
-      const int ex = NT * 64;
-      if (ca >= 0 && cb >= 0) {
-        if ((ca >> 3) > (cb >> 3)) { const int tmp = ca; ca = cb; cb = tmp; }
-        const int ta = ca >> 3, tb = cb >> 3, i = ca & 7, j = cb & 7;
-        off = (ta * T - ta * (ta - 1) / 2 + (tb - ta)) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1);
-      } else if (ca == ONE && cb == ONE) off = ex + 16 * T;                 // row count
-      else if (ca == RES && cb == RES) off = ex + 16 * T + 2;               // sum res^2
-      else if ((ca == ONE && cb == RES) || (ca == RES && cb == ONE)) off = ex + 16 * T + 1;   // sum res
-      else if (ca == ONE || cb == ONE) off = ex + (ca == ONE ? cb : ca);    // sum x_c
-      else off = ex + 8 * T + (ca == RES ? cb : ca);                        // sum x_c res
-      double s = 0.0;
-      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += __ldcg(&partials[(size_t)b2 * QT + off]);
-      out[q] = s * sgn;
-    }
-    if (tid == 0) *ticket = 0u;
-    so_finish(ticket, out, Qo);
-  }
+  ph_epilogue<FAM, T, NTH>(acc, a_one, a_res, cnt, sr, rr, s_x, P, partials, out, ticket);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
@@ -433,36 +450,35 @@ int launch_ph_layout(const Shard& s, const Params& P, const CUtensorMap& tmap, i
   return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
 }
 
+// Threads per block: two blocks of 8 warps per SM up to 64 inputs (four of 4 warps up to 24) — their phases interleave,
+// n = 32: 5.96 -> 5.70 ms, n = 16: 5.82 -> 4.80 ms per 1e8 / 2e8 rows — one block of 16 warps beyond, where the tile
+// triangle is split over up to 8 warps (profiles/r2_gram_ph_v6_half.jsonl, r2_gram_ph_v7_nth.txt).
+// Also measured and not kept: accumulating the next chunk's linear predictor inside the DMMA loop (three stages, one
+// barrier per chunk, no separate phase A): n = 32 5.64 vs 5.48 ms, n = 40 7.47 vs 6.89 ms (profiles/r2_gram_ph_v8_fused.txt).
+__host__ __device__ constexpr int ph_threads(int T) { return T <= 3 ? 128 : T <= 8 ? 256 : 512; }
+
 template <int FAM, int T>
 int launch_ph(const Shard& s, const Params& P) {
   // 16-byte requests need 16-byte aligned rows: even f and an aligned first row (a view may start at an odd row)
   const bool aligned = (P.f % 2 == 0) && (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (reinterpret_cast<uintptr_t>(s.y) % 16 == 0);
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof tmap);
-  // two blocks of 8 warps per SM instead of one of 16: their phases interleave (experiment switch until the A/B is in)
-  static const int nth_env = [] { const char* e = getenv("SCALAOPT_GRAM_NTH"); return e && *e ? atoi(e) : 0; }();
-  int nth = T <= 8 ? 256 : 512;           // measured: profiles/r2_gram_ph_v6_half.jsonl
-  if (nth_env == 128 || nth_env == 256 || nth_env == 512) nth = nth_env;
-  if (T > 8 && nth == 128) nth = 256;
-  static const bool no_tma = [] { const char* e = getenv("SCALAOPT_GRAM_NO_TMA"); return e && *e && *e != '0'; }();
+  static const bool no_tma = [] { const char* e = getenv("SCALAOPT_GRAM_NO_TMA"); return e && *e && *e != '0'; }();   // A/B switch
+  constexpr int NTH = ph_threads(T);
   if constexpr (T <= 12) {
     if (aligned && !no_tma && s.rows < ((int64_t)1 << 31) && encode_tiled()) {
-      const int R = ph_rows(T, kTma) * nth / 512;
+      constexpr int R = ph_rows(T, kTma) * NTH / 512;
       const cuuint64_t dims[2] = {(cuuint64_t)P.f, (cuuint64_t)s.rows};
       const cuuint64_t strides[1] = {(cuuint64_t)P.f * 8};
       const cuuint32_t box[2] = {16, (cuuint32_t)R};
       const cuuint32_t estr[2] = {1, 1};
-      const CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(s.X), dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r == CUDA_SUCCESS) {
-        if constexpr (T <= 8) if (nth == 128) return launch_ph_layout<FAM, T, kTma, 128>(s, P, tmap, 1);
-        return nth == 256 ? launch_ph_layout<FAM, T, kTma, 256>(s, P, tmap, 1) : launch_ph_layout<FAM, T, kTma, 512>(s, P, tmap, 1);
-      }
+      if (encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(s.X), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        return launch_ph_layout<FAM, T, kTma, NTH>(s, P, tmap, 1);
     }
   }
-  if constexpr (T <= 8) if (nth == 128) return launch_ph_layout<FAM, T, kPadded, 128>(s, P, tmap, aligned ? 1 : 0);
-  return nth == 256 ? launch_ph_layout<FAM, T, kPadded, 256>(s, P, tmap, aligned ? 1 : 0) : launch_ph_layout<FAM, T, kPadded, 512>(s, P, tmap, aligned ? 1 : 0);
+  return launch_ph_layout<FAM, T, kPadded, NTH>(s, P, tmap, aligned ? 1 : 0);
 }
 
 template <int FAM>
