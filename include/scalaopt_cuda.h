@@ -194,7 +194,9 @@ int so_eval_normal_eq(so_dataset* ds, int family, const double* p, int n,
  *   R^T R = [ JtJ  Jtr ; Jtr^T  rtr ]   (same conventions and scaling as so_eval_normal_eq),
  * i.e. rows i < n are (R_J[i,:] | (Q^T r)_i) and R[n][n] = +-||r - J J^+ r||: exactly the (n+1)-row system
  * MSEFunction.jacobianAndResidualsMatrix hands to QR.apply in the drop-in (row signs are arbitrary, as with any QR).
- * Single-input families, and the linear / logistic families with n <= 8 (SO_EUNSUPPORTED otherwise). */
+ * Single-input families, and the linear / logistic families with n <= 63: per-thread triangles up to n = 8 (HBM- to
+ * FP64-bound), one triangle per warp in shared memory beyond (issue-bound: the robust route, not the fast one).
+ * SO_EUNSUPPORTED otherwise. */
 int so_eval_qr(so_dataset* ds, int family, const double* p, int n, double* R /* (n+1)*(n+1) */);
 
 /* K3. k step sizes scored in one pass:  phi[j] = loss(p + alpha[j] d),  dphi[j] = grad(p + alpha[j] d) . d

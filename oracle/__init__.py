@@ -67,6 +67,7 @@ def lib():
         L.orc_jacobian_matrix.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_int,
                                           C.c_double, _dp]
         L.orc_normal_eq.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, C.c_int, _Fold, _dp, _dp, _dp]
+        L.orc_normal_eq_comp.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp]
         L.orc_qr.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _ip, _dp, _dp]
         L.orc_qr.restype = C.c_int
         L.orc_qr_solution.argtypes = [_dp, _dp, _dp, _ip, C.c_int, _dp]
@@ -171,6 +172,18 @@ def normal_eq(family, X, y, p, parts=1, threads=1):
     lib().orc_normal_eq(family, _p(X), _p(y), m, f, _p(p), n, _Fold(parts, threads), _p(JtJ), _p(Jtr),
                         C.byref(rtr))
     return JtJ, Jtr, rtr.value
+
+
+def normal_eq_comp(family, X, y, p, threads=1):
+    """compensated sums (hi, lo), each n*n + n + 1 doubles laid out [JtJ row-major | Jtr | rtr]: the yardstick for
+    summation error at scale, not a restatement of the reference"""
+    X, y, m, f = _xy(X, y)
+    p = _a(p)
+    n = p.size
+    hi = np.empty(n * n + n + 1)
+    lo = np.empty(n * n + n + 1)
+    lib().orc_normal_eq_comp(family, _p(X), _p(y), m, f, _p(p), n, threads, _p(hi), _p(lo))
+    return hi, lo
 
 
 class QRResult:

@@ -457,6 +457,59 @@ void orc_normal_eq(int family, const double* X, const double* y, int64_t m, int 
   free(acc);
 }
 
+/* The same sums, COMPENSATED: exact products (TwoProduct through fma) added with Neumaier's running error term, per
+ * partition and again across partitions; hi + lo is the sum of the m exactly-formed per-row terms to ~1e-32 relative.
+ * Not a restatement of anything in the reference — the yardstick that both the reference's left fold and the GPU's tree
+ * are measured against at m = 1e9 ("parity at scale").  out_hi / out_lo: n*n + n + 1 doubles. */
+static inline void comp_add(double* s, double* c, double v) {
+  double t = *s + v;
+  if (fabs(*s) >= fabs(v)) *c += (*s - t) + v; else *c += (v - t) + *s;
+  *s = t;
+}
+static inline void comp_add_prod(double* s, double* c, double a, double b) {
+  double pr = a * b, er = fma(a, b, -pr);
+  comp_add(s, c, pr);
+  *c += er;
+}
+typedef struct comp_job { int family; const double* X; const double* y; int f; const double* p; int n; int64_t b, e; double* s; double* c; } comp_job;
+static void* comp_worker(void* arg) {
+  comp_job* jb = (comp_job*)arg;
+  int n = jb->n, Q = n * n + n + 1;
+  for (int q = 0; q < Q; ++q) { jb->s[q] = 0.0; jb->c[q] = 0.0; }
+  double J[ORC_MAXN];
+  for (int64_t i = jb->b; i < jb->e; ++i) {
+    double r = orc_jacobian_row(jb->family, jb->p, n, jb->X + (size_t)i * jb->f, jb->f, jb->y[i], J);
+    for (int a = 0; a < n; ++a)
+      for (int b = a; b < n; ++b) comp_add_prod(&jb->s[a * n + b], &jb->c[a * n + b], J[a], J[b]);
+    for (int a = 0; a < n; ++a) comp_add_prod(&jb->s[n * n + a], &jb->c[n * n + a], J[a], r);
+    comp_add_prod(&jb->s[n * n + n], &jb->c[n * n + n], r, r);
+  }
+  return NULL;
+}
+void orc_normal_eq_comp(int family, const double* X, const double* y, int64_t m, int f, const double* p, int n, int threads,
+                        double* out_hi, double* out_lo) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  int Q = n * n + n + 1;
+  pthread_t th[256]; comp_job jobs[256];
+  double* buf = (double*)malloc(sizeof(double) * 2 * (size_t)threads * Q);
+  for (int t = 0; t < threads; ++t) {
+    comp_job jb = { family, X, y, f, p, n, (int64_t)(((__int128)t * m) / threads), (int64_t)(((__int128)(t + 1) * m) / threads),
+                    buf + (size_t)(2 * t) * Q, buf + (size_t)(2 * t + 1) * Q };
+    jobs[t] = jb;
+    if (threads > 1) pthread_create(&th[t], NULL, comp_worker, &jobs[t]); else comp_worker(&jobs[t]);
+  }
+  if (threads > 1) for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+  for (int q = 0; q < Q; ++q) {
+    double s = 0.0, c = 0.0;
+    for (int t = 0; t < threads; ++t) { comp_add(&s, &c, jobs[t].s[q]); comp_add(&s, &c, jobs[t].c[q]); }
+    out_hi[q] = s; out_lo[q] = c;
+  }
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < a; ++b) { out_hi[a * n + b] = out_hi[b * n + a]; out_lo[a * n + b] = out_lo[b * n + a]; }
+  free(buf);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * line search scores
  * ------------------------------------------------------------------------------------------- */

@@ -76,6 +76,9 @@ void orc_jacobian_matrix(int family, const double* X, const double* y, int64_t m
                          int fd, double eps, double* rows);
 
 /* sums that QR.apply extracts from that matrix: JtJ[n*n], Jtr[n], rtr (folded row by row in `fold` order). */
+/* compensated (Neumaier + exact products) version of the same sums: hi + lo, n*n + n + 1 doubles each; test yardstick only */
+void orc_normal_eq_comp(int family, const double* X, const double* y, int64_t m, int f, const double* p, int n, int threads,
+                        double* out_hi, double* out_lo);
 void orc_normal_eq(int family, const double* X, const double* y, int64_t m, int f, const double* p, int n,
                    orc_fold fold, double* JtJ, double* Jtr, double* rtr);
 

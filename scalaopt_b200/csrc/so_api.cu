@@ -1202,9 +1202,9 @@ extern "C" int so_eval_qr(so_dataset* ds, int family, const double* p, int n, do
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_family(ctx, family, ds->f, n);
   if (rc) return rc;
-  const bool narrow = (family == SO_FAMILY_LINEAR || family == SO_FAMILY_LINEAR_NOINT || family == SO_FAMILY_LOGISTIC) && n <= SO_QR_WIDE_MAX_N;
+  const bool narrow = (family == SO_FAMILY_LINEAR || family == SO_FAMILY_LINEAR_NOINT || family == SO_FAMILY_LOGISTIC) && n <= SO_QR_COLS_MAX_N;
   if (!family_is_scalar_t(family) && !narrow)
-    return fail(ctx, SO_EUNSUPPORTED, "so_eval_qr: family %d with n=%d is outside the TSQR catalogue (single-input families; linear / logistic with n <= %d)", family, n, SO_QR_WIDE_MAX_N);
+    return fail(ctx, SO_EUNSUPPORTED, "so_eval_qr: family %d with n=%d is outside the TSQR catalogue (single-input families; linear / logistic with n <= %d)", family, n, SO_QR_COLS_MAX_N);
   const int C = n + 1, per = C * C;
   const int slots = ctx->rank_mode ? ctx->world : (int)ctx->devs.size();
   std::vector<double> res;

@@ -56,7 +56,8 @@ struct Shard {
   double tmin = 0.0, tmax = 0.0;
 };
 
-constexpr int SO_QR_WIDE_MAX_N = 8;     // TSQR of the linear-predictor families: n + 1 <= 9 columns per thread
+constexpr int SO_QR_WIDE_MAX_N = 8;     // TSQR of the linear-predictor families: n + 1 <= 9 columns per thread (so_wide_qr.cu)
+constexpr int SO_QR_COLS_MAX_N = 63;    // ... and up to 64 columns with one triangle per warp in shared memory (so_wide_qrw.cu)
 
 enum Kind { kLossGrad = 1, kNormalEq = 2, kLine = 3, kHessVec = 4, kNll = 5, kQr = 6 };
 

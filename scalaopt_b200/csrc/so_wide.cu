@@ -248,6 +248,8 @@ int launch_mapped(const Shard& s, const Params& P, int want_grad) {
 int launch_line(const Shard& s, int fam, const Params& P);                      // so_wide_line.cu
 int launch_gram(const Shard& s, int fam, const Params& P);                      // so_gram.cu
 int launch_qr(const Shard& s, int fam, const Params& P);                        // so_wide_qr.cu (n <= 8)
+int launch_qr_wide(const Shard& s, int fam, const Params& P);                   // so_wide_qrw.cu (8 < n <= 47)
+size_t qrw_partials_needed(int n, int sm_count);
 size_t gram_partials_needed(int n, int f, int sm_count);                        // so_gram.cu
 
 }  // namespace wide
@@ -255,6 +257,7 @@ size_t gram_partials_needed(int n, int f, int sm_count);                        
 size_t wide_partials_needed(Kind kind, int family, int n, int f, int k, int sm_count) {
   (void)family;
   if (kind == kNormalEq) return wide::gram_partials_needed(n, f, sm_count);
+  if (kind == kQr && n > SO_QR_WIDE_MAX_N) return wide::qrw_partials_needed(n, sm_count);
   const size_t Q = (size_t)std::max(n + 1, 2 * std::max(k, 1));
   return (size_t)sm_count * 8 * Q;    // at most 8 resident blocks per SM
 }
@@ -288,7 +291,7 @@ int launch_wide(Kind kind, const Shard& s, int family, const double* p, const do
     case kNormalEq:
       return launch_gram(s, fam, P);
     case kQr:
-      return n <= SO_QR_WIDE_MAX_N ? launch_qr(s, fam, P) : SO_EUNSUPPORTED;
+      return n <= SO_QR_WIDE_MAX_N ? launch_qr(s, fam, P) : (n <= SO_QR_COLS_MAX_N ? launch_qr_wide(s, fam, P) : SO_EUNSUPPORTED);
     case kNll: break;      // single-input pdfs only (launch_nll)
   }
   return SO_EINVAL;

@@ -60,6 +60,25 @@ def test_config3_gaussian_peak_1e9_rows(native, oracle, host, gpu_ctx):
         JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p, parts=8, threads=8)
         assert_gram(JtJ_w, JtJ_o); assert_vec(Jtr_w, Jtr_o, what="Jtr window"); assert_loss(rtr_w, rtr_o)
         v.free()
+    # summation error at m = 1e9 ("parity at scale"): all 1e9 rows read back in windows and summed
+    # on the host with exact products and Neumaier compensation (oracle.normal_eq_comp; the windows' hi/lo parts are
+    # added exactly with math.fsum) — the GPU's block/warp tree is held to the north_star tolerances against THAT
+    import math
+    import os
+    n, Q = 5, 5 * 5 + 5 + 1
+    pieces = [[] for _ in range(Q)]
+    W = 1 << 26
+    threads = max(1, len(os.sched_getaffinity(0)))
+    for b in range(0, m, W):
+        X, y = ds.read(b, min(W, m - b))
+        hi, lo = oracle.normal_eq_comp(fam, X, y, p, threads=threads)
+        for q in range(Q):
+            pieces[q] += [float(hi[q]), float(lo[q])]
+    ref = np.array([math.fsum(v) for v in pieces])
+    assert_gram(JtJ, ref[: n * n].reshape(n, n))
+    assert_vec(Jtr, ref[n * n: n * n + n], rtol=1e-11, what="Jtr vs compensated sum of 1e9 rows")
+    assert_loss(rtr, ref[-1])
+    assert_loss(loss, ref[-1] / (2.0 * m))
     # run-to-run reproducibility at full size, every kernel that streams through the shared-memory ring (a refill that
     # races with the loads of the stage it overwrites shows up here and nowhere at small sizes: ~1600 chunks per block)
     def bits(*arrays):

@@ -56,8 +56,6 @@ def test_levenberg_marquardt_trajectory_matches_oracle(native, oracle, host, gpu
     """k2: K2 + Cholesky, trial-point losses from K1; k2-speculative (the default): trial-point losses from K2 passes whose
     sums serve the next Jacobian request; tsqr: the (n+1)-row system is the R factor from so_eval_qr."""
     tsqr, speculate = mode == "tsqr", mode != "k2"
-    if tsqr and case == "lm_spec_linear":
-        pytest.skip("TSQR covers the single-input families and linear / logistic rows with n <= 8 (this case has n = 11)")
     if case == "gauss_expbkg":         # BASELINE config 3 at oracle-sized m
         fam, n = oracle.GAUSS_EXPBKG, 5
         truth = np.array([2.0, 0.5, 0.05, 1.0, 3.0])

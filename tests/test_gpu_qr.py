@@ -94,10 +94,56 @@ def test_tsqr_of_the_narrow_linear_predictor_families(native, oracle, gpu_ctx, n
     ds.free()
 
 
+COLS_CASES = [("LINEAR_NOINT", 9), ("LINEAR", 10), ("LINEAR", 16), ("LINEAR_NOINT", 31), ("LINEAR", 31), ("LINEAR_NOINT", 32),
+              ("LOGISTIC", 32), ("LINEAR_NOINT", 47), ("LINEAR", 46), ("LOGISTIC", 12), ("LINEAR_NOINT", 63)]
+
+
+@pytest.mark.parametrize("name,f", COLS_CASES)
+@pytest.mark.parametrize("m", [20_003, 70, 5])
+def test_tsqr_of_the_wide_linear_predictor_families(native, oracle, gpu_ctx, name, f, m):
+    """so_eval_qr with 8 < n <= 63 (one triangle per warp, lanes are columns — so_wide_qrw.cu): LM spec case 1 is n = 11,
+    BASELINE config 2 is n = 33, config 5 has n = 32.  Same three references as the narrow cases."""
+    fam = getattr(oracle, name)
+    if name == "LINEAR":
+        truth = np.concatenate([[80.0], np.arange(f, dtype=float)])
+    elif name == "LINEAR_NOINT":
+        truth = np.arange(1, f + 1, dtype=float) / f
+    else:
+        truth = np.array([(((j % 7) - 3) / 4.0) for j in range(f + 1)])
+    X, y = oracle.generate(fam, m, f, truth)
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    p = truth * 0.9 + 0.05
+    n = p.size
+    R = ds.qr(fam, p)
+    assert gpu_ctx.stats().launches == 1
+    assert R.shape == (n + 1, n + 1) and np.all(np.tril(R, -1) == 0.0) and np.all(np.isfinite(R))
+    JtJ, Jtr, rtr = oracle.normal_eq(fam, X, y, p)
+    G = np.block([[JtJ, Jtr[:, None]], [Jtr[None, :], np.array([[rtr]])]])
+    scale = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
+    assert np.max(np.abs(R.T @ R - G) / scale) < 1e-11
+    if m <= n:
+        ds.free()
+        return                                               # fewer rows than columns: R is not unique
+    ab = oracle.jacobian_matrix(fam, X, y, p)
+    Rn = _normalise(R)
+    colnorm = np.sqrt(np.diag(JtJ))
+    Rl = _normalise(np.linalg.qr(ab, mode="r"))
+    np.testing.assert_allclose(Rn / np.append(colnorm, np.sqrt(rtr)), Rl / np.append(colnorm, np.sqrt(rtr)), rtol=0, atol=1e-9)
+    if n <= 16:                                              # the restated 2n+1-pass QR.apply on the same rows
+        q = oracle.qr(ab, n, pivoting=False)
+        Rref = q.Rmat()
+        sref = np.where(np.diag(Rref) < 0, -1.0, 1.0)
+        np.testing.assert_allclose(Rn[:n, :n] / colnorm, (Rref * sref[:, None]) / colnorm, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(Rn[:n, n], q.qtb[:n] * sref, rtol=0, atol=1e-9 * np.sqrt(rtr))
+    # bit-reproducible
+    assert np.array_equal(ds.qr(fam, p), R)
+    ds.free()
+
+
 def test_tsqr_beyond_the_catalogue_is_an_error(native, gpu_ctx):
-    ds = native.Dataset(gpu_ctx, 32, 9).append(np.ones((32, 9)), np.ones(32))
+    ds = native.Dataset(gpu_ctx, 32, 64).append(np.ones((32, 64)), np.ones(32))
     with pytest.raises(native.NativeError):
-        ds.qr(native.LINEAR_NOINT, np.ones(9))            # n = 9 > 8: no per-thread triangle of that size
+        ds.qr(native.LINEAR_NOINT, np.ones(64))           # n = 64 > 63: a row no longer fits two columns per lane
     ds.free()
 
 

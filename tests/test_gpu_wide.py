@@ -150,3 +150,59 @@ def test_linear_predictor_families_at_random_scales(native, oracle, gpu_ctx, nam
         sc = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
         assert np.max(np.abs(R.T @ R - G) / sc) < 1e-10
     ds.free()
+
+
+@pytest.mark.parametrize("f", [2, 7, 32])
+def test_logistic_saturated_predictors_match_a_50_digit_reference(native, oracle, gpu_ctx, f):
+    """Where the oracle stops (it forms o = 1/(1+exp(-z)) like Neuron.scala and overflows its own log for |z| >~ 36,
+    so the k > 4 line-search cases above are skipped for this family): loss, gradient, phi/dphi at every step size and
+    the Hessian-vector product against 50-digit mpmath arithmetic on the same rows, predictors out to |z| ~ 300."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    fam = oracle.LOGISTIC
+    truth = _truth("LOGISTIC", f)
+    m = 1500
+    X, y = oracle.generate(fam, m, f, truth)
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    p = truth * 30.0 + 0.5                                 # |z| up to ~100 at alpha = 0, several hundred along the ray
+    d = np.cos(np.arange(f + 1) + 0.3) * 2.0
+    alphas = [0.0, 0.5, 1.0, 2.0, 4.0, 8.0, 16.0, 0.37, 3.0]
+
+    def reference(w):
+        w = [mp.mpf(float(v)) for v in w]
+        loss = mp.mpf(0)
+        grad = [mp.mpf(0)] * (f + 1)
+        zs = []
+        for i in range(m):
+            xt = [mp.mpf(1)] + [mp.mpf(float(v)) for v in X[i]]
+            z = sum(a * b for a, b in zip(w, xt))
+            zs.append(z)
+            yi = mp.mpf(float(y[i]))
+            # CE(o, y) with o = 1/(1+exp(-z)): -y log o - (1-y) log(1-o) = log(1+exp(-z)) + (1-y) z
+            loss += mp.log1p(mp.exp(-z)) + (1 - yi) * z
+            o = 1 / (1 + mp.exp(-z))
+            grad = [g + (o - yi) * xv for g, xv in zip(grad, xt)]
+        return loss / m, [g / m for g in grad], zs
+
+    loss, grad = ds.loss_grad(fam, p)
+    l_ref, g_ref, zs = reference(p)
+    assert max(abs(float(z)) for z in zs) > 36.0           # the regime the oracle cannot do
+    assert abs(loss - float(l_ref)) <= 1e-12 * abs(float(l_ref))
+    g_ref_f = np.array([float(g) for g in g_ref])
+    assert_vec(grad, g_ref_f, rtol=1e-12, what="gradient vs mpmath")
+    phi, dphi = ds.line(fam, p, d, alphas)
+    for j, a in enumerate(alphas):
+        l_a, g_a, zs_a = reference(p + a * d)
+        dphi_ref = float(sum(g * mp.mpf(float(dv)) for g, dv in zip(g_a, d)))
+        assert abs(phi[j] - float(l_a)) <= 1e-12 * abs(float(l_a)), (a, phi[j], float(l_a))
+        assert abs(dphi[j] - dphi_ref) <= 1e-11 * max(abs(dphi_ref), 1e-300), (a, dphi[j], dphi_ref)
+    # H d = (1/m) sum o (1 - o) (x~ . d) x~
+    Hd = ds.hess_vec(fam, p, d)
+    H_ref = [mp.mpf(0)] * (f + 1)
+    for i in range(m):
+        xt = [mp.mpf(1)] + [mp.mpf(float(v)) for v in X[i]]
+        o = 1 / (1 + mp.exp(-zs[i]))
+        xd = sum(a * mp.mpf(float(b)) for a, b in zip(xt, d))
+        H_ref = [h + o * (1 - o) * xd * xv for h, xv in zip(H_ref, xt)]
+    assert_vec(Hd, np.array([float(h / m) for h in H_ref]), rtol=1e-11, what="Hd vs mpmath")
+    ds.free()

@@ -161,3 +161,27 @@ def test_mlp_restatement_reproduces_the_trainer_spec_properties(oracle):
     e = w[:6].reshape(2, 3)
     o = 1.0 / (1.0 + np.exp(-(e[:, 0] + X[0] @ e[:, 1:].T)))
     assert oracle.model(oracle.MLP_MSE, w, X[0]) == pytest.approx(w[6] + o @ w[7:], rel=1e-14)
+
+
+def test_compensated_normal_equations_agree_with_the_fold_and_beat_it(oracle):
+    """oracle.normal_eq_comp (exact products + Neumaier; the yardstick of the 1e9-row GPU test) against the restated left
+    fold on a size where both run, and against an exactly representable case."""
+    fam = oracle.GAUSS_EXPBKG
+    truth = np.array([2.0, 0.5, 0.05, 1.0, 3.0])
+    X, y = oracle.generate(fam, 200_001, 1, truth, noise_sigma=0.05)
+    p = truth * 1.1
+    JtJ, Jtr, rtr = oracle.normal_eq(fam, X, y, p)
+    for threads in (1, 3):
+        hi, lo = oracle.normal_eq_comp(fam, X, y, p, threads=threads)
+        ref = hi + lo
+        np.testing.assert_allclose(ref[:25].reshape(5, 5), JtJ, rtol=1e-12, atol=1e-12 * np.abs(JtJ).max())
+        np.testing.assert_allclose(ref[25:30], Jtr, rtol=1e-10, atol=1e-12 * np.abs(Jtr).max())
+        assert ref[30] == pytest.approx(rtr, rel=1e-13)
+    # linear family, integer data: every product and sum is exact, so hi is the exact answer and lo is zero
+    Xi = np.arange(1.0, 2001.0).reshape(-1, 1)
+    yi = 3.0 * Xi[:, 0] + 7.0
+    hi, lo = oracle.normal_eq_comp(oracle.LINEAR, Xi, yi, np.array([1.0, 1.0]), threads=2)
+    r = yi - (1.0 + Xi[:, 0])
+    assert np.all(lo == 0.0)
+    assert hi[-1] == float(np.sum(r.astype(object) ** 2))
+    assert hi[0] == 2000.0 and hi[1] == float(np.sum(Xi)) and hi[3] == float(np.sum(Xi[:, 0].astype(object) ** 2))

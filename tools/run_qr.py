@@ -1,25 +1,23 @@
-"""timing of so_eval_qr against so_eval_normal_eq: python tools/run_qr.py <family> <rows>"""
-import os, sys
+"""TSQR timing: python tools/run_qr.py  -> one JSON line per shape (so_eval_qr next to so_eval_normal_eq on the same rows)"""
+import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from scalaopt_b200 import native
-name, m = sys.argv[1], int(sys.argv[2])
-fam = getattr(native, name)
-truth = {"GAUSS_EXPBKG": [2.0, 0.5, 0.05, 1.0, 3.0], "GAUSS": [2.0, 0.5, 0.05], "EXPDECAY": [2.0, -1.3],
-         "POLY": [1.0, -2.0, 0.5, 3.0]}[name]
-truth = np.array(truth)
+shapes = [("linear_noint", 4, 400_000_000), ("linear", 10, 100_000_000), ("linear_noint", 16, 100_000_000),
+          ("linear_noint", 32, 50_000_000), ("logistic", 32, 50_000_000), ("linear_noint", 47, 20_000_000)]
 with native.Context(1) as ctx:
-    ds = native.Dataset(ctx, m, 1).generate(fam, truth)
-    p = truth * 1.1 + 0.01
-    for _ in range(3):
-        ds.normal_eq(fam, p)
-    k2 = ctx.stats().kernel_ms
-    for _ in range(3):
-        R = ds.qr(fam, p)
-    qr = ctx.stats().kernel_ms
-    JtJ, Jtr, rtr = ds.normal_eq(fam, p)
-    n = truth.size
-    G = np.block([[JtJ, Jtr[:, None]], [Jtr[None, :], np.array([[rtr]])]])
-    err = np.max(np.abs(R.T @ R - G) / np.sqrt(np.outer(np.diag(G), np.diag(G))))
-    print(f"{name} rows={m}: K2 {k2:.3f} ms, TSQR {qr:.3f} ms ({16e-6 * m / qr:.0f} GB/s), |R^T R - G| rel {err:.2e}")
-    ds.free()
+    for name, f, m in shapes:
+        fam = {"linear_noint": native.LINEAR_NOINT, "linear": native.LINEAR, "logistic": native.LOGISTIC}[name]
+        n = f + (0 if name == "linear_noint" else 1)
+        truth = np.arange(1, n + 1) / n
+        ds = native.Dataset(ctx, m, f).generate(fam, truth)
+        out = {"family": name, "f": f, "n": n, "rows": m}
+        for what, fn in (("tsqr_ms", lambda: ds.qr(fam, truth * 0.9)), ("k2_ms", lambda: ds.normal_eq(fam, truth * 0.9))):
+            ks = []
+            for _ in range(5):
+                fn()
+                ks.append(ctx.stats().kernel_ms)
+            out[what] = float(np.median(ks[1:]))
+        out["tsqr_over_k2"] = out["tsqr_ms"] / out["k2_ms"]
+        print(json.dumps(out), flush=True)
+        ds.free()

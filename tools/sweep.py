@@ -113,7 +113,25 @@ def main():
                    iterations_per_s=res.iterations / dt, max_abs_err_vs_truth=float(np.abs(x - truth).max()),
                    counters=fobj.counters())
             fobj.free()
-            lm = host.bench_lm(ctx, ds, native.LINEAR_NOINT, np.zeros(f), repeats=1)
+            # Steihaug trust region (gradient/SteihaugCG.scala:51-148), delta0 = 1 as SURVEY.md 8d cfg4 asks
+            fobj = host.Objective.gpu(ctx, ds, native.LINEAR_NOINT, f)
+            cfg = host.default_config(host.STEIHAUG_CG)
+            cfg.delta0 = 1.0
+            t0 = time.perf_counter()
+            try:
+                x, res = host.minimize(host.STEIHAUG_CG, fobj, np.zeros(f), cfg)
+                outcome = "converged"
+            except host.MaxIterException as e:      # thrown, not returned, like the reference
+                x, res, outcome = None, None, f"MaxIterException: {e}"
+            dt = time.perf_counter() - t0
+            c = fobj.counters()
+            report(config="cfg4 Steihaug-CG linear 1e7x256 (delta0=1)", outcome=outcome, seconds=dt,
+                   iterations=int(res.iterations) if res is not None else None,
+                   iterations_per_s=(res.iterations / dt) if res is not None else None,
+                   max_abs_err_vs_truth=float(np.abs(x - truth).max()) if x is not None else None,
+                   passes_per_s=(c["k1_passes"] + c["k4_passes"]) / dt, counters=c)
+            fobj.free()
+            lm = host.bench_lm(ctx, ds, native.LINEAR_NOINT, np.zeros(f), repeats=1, runs=1)
             report(config="cfg4 LevenbergMarquardt linear 1e7x256 (compute-bound Gram)", **{k: v for k, v in lm.items() if k != "minimiser"})
             ds.free()
         if "cfg5" in which:
