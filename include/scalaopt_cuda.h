@@ -72,12 +72,25 @@ typedef enum so_family {
    * reference composes them (dirHessian = forward difference of gradients, eps = 1e-8, Trainer.scala:76-80). */
   SO_FAMILY_MLP_MSE = 7,
   SO_FAMILY_MLP_CE = 8,
-  SO_FAMILY_COUNT = 9
+  /* Round 2: the network families also take K = ny > 1 outputs per observation (so_dataset_create_multi), which is what the
+   * reference's own spec trains — FFNeuralNetwork(Vector(Iris.nInputs, 5, Iris.nClasses)), FFNeuralNetworkTrainerSpec.scala:353-376:
+   *   n = h (f + 1) + K (h + 1) weights, reference order (hidden neurons, then output neurons; bias first)
+   *   MLP_MSE, K > 1: SO_EUNSUPPORTED — the reference has `???` there (FFNeuralNetwork.scala:157)
+   *   MLP_CE,  K > 1: SoftMaxFunction outputs o_k = exp(z_k - max) / sum (:143-158), loss = -sum_k y_k log(o_k / sum o)
+   *                   (:89-103), residual_k = (sum y) o_k - y_k (:168-173)
+   *   LM convention (Neuron.jacobian, Neuron.scala:67-73): network residual = ||residual||_2, Jacobian row = gradient /
+   *   residual of the neuron (hidden neurons: of the FIRST output neuron), as the reference has it.
+   * SOFTMAX: no hidden layer — FFNeuralNetwork(Vector(f, K)) with CrossEntropy + SoftMaxFunction (spec :222-260), n = K (f + 1), K >= 2.
+   * Shapes: f <= 16, h <= 16, K <= SO_MAX_OUTPUTS.  Weight decay (FFNeuralNetworkTrainer.scala:59-69,147-153) is data-independent
+   * and is applied by the caller's objective (GpuMSEFunction::decay). */
+  SO_FAMILY_SOFTMAX = 9,
+  SO_FAMILY_COUNT = 10
 } so_family;
 
 #define SO_MAX_POLY_N   8      /* polynomial family: at most 8 coefficients */
 #define SO_MAX_FEATURES 512    /* linear-predictor families: f <= 512 */
 #define SO_MAX_ALPHAS   32     /* so_eval_line: k <= 32 step sizes per pass */
+#define SO_MAX_OUTPUTS  8      /* outputs per observation (network families) */
 
 typedef struct so_ctx so_ctx;
 typedef struct so_dataset so_dataset;
@@ -119,6 +132,9 @@ void so_host_free(void* p);
  * set (sharded evenly, contiguous row blocks); in rank mode m is THIS rank's shard and the data-set size
  * used for the 1/m normalisation is the sum over ranks. */
 int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out);
+/* ... with `ny` outputs per observation: y is row-major [m x ny] in append / read / head / load_raw (DataPoint.y is a vector in
+ * the reference, variable/Point.scala:29; every family but the network ones needs ny = 1). */
+int so_dataset_create_multi(so_ctx* ctx, int64_t m, int f, int ny, so_dataset** out);
 
 /* The row range [*begin, *begin + *rows) of shard `g` when `m` observations of `f` inputs are split over `G` GPUs: contiguous
  * blocks of ceil(m/G) rows, an even count for f == 1 (every shard then starts 16-byte aligned).  This is the split

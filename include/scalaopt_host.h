@@ -87,6 +87,8 @@ int soh_objective_use_tsqr(soh_objective* objective, int on);
 
 /* Levenberg-Marquardt trial-point losses from a K2 pass whose sums are kept for the Jacobian request that follows an
  * accepted step (default on; off = one K1 loss pass per trial point + one K2 pass per outer iteration). */
+/* FFNeuralNetworkTrainer.withDecay (std-apps/.../nnet/FFNeuralNetworkTrainer.scala:57): weight decay of a GPU network objective */
+int soh_objective_set_decay(soh_objective* objective, double decay);
 int soh_objective_speculate(soh_objective* objective, int on);
 
 /* negLogLikelihood(pdf, GpuDataSet(ds)) _ (std-apps/.../stats/package.scala:97-103) with finite-difference derivatives

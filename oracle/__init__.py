@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 LINEAR, LINEAR_NOINT, LOGISTIC, EXPDECAY, GAUSS, GAUSS_EXPBKG, POLY, MLP_MSE, MLP_CE = range(9)
+SOFTMAX = 9        # FFNeuralNetwork(Vector(f, K)), cross-entropy + soft-max: evaluated by the net_* functions below
 
 
 def build(force: bool = False) -> str:
@@ -67,6 +68,9 @@ def lib():
         L.orc_jacobian_matrix.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_int,
                                           C.c_double, _dp]
         L.orc_normal_eq.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, C.c_int, _Fold, _dp, _dp, _dp]
+        L.orc_net_row.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_net_loss_grad.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp, C.c_int64, _dp, C.c_double, _dp, _dp]
+        L.orc_net_jacobian_matrix.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp, C.c_int64, _dp, C.c_double, _dp]
         L.orc_normal_eq_comp.argtypes = [C.c_int, _dp, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp]
         L.orc_qr.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _ip, _dp, _dp]
         L.orc_qr.restype = C.c_int
@@ -184,6 +188,43 @@ def normal_eq_comp(family, X, y, p, threads=1):
     lo = np.empty(n * n + n + 1)
     lib().orc_normal_eq_comp(family, _p(X), _p(y), m, f, _p(p), n, threads, _p(hi), _p(lo))
     return hi, lo
+
+
+def _net_args(sizes, X, Y):
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, int(sizes[0]))
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(X.shape[0], int(sizes[-1]))
+    return sizes, X, Y
+
+
+def net_nweights(sizes):
+    return int(sum(sizes[l] * (sizes[l - 1] + 1) for l in range(1, len(sizes))))
+
+
+def net_loss_grad(sizes, cross_entropy, X, Y, w, decay=0.0, want_grad=True):
+    """FFNeuralNetworkTrainer(FFNeuralNetwork(Vector(sizes...)), data, decay).apply(w) / .gradient(w) with vector targets"""
+    sizes, X, Y = _net_args(sizes, X, Y)
+    w = _a(w)
+    loss = C.c_double()
+    g = np.empty(w.size) if want_grad else None
+    rc = lib().orc_net_loss_grad(sizes.ctypes.data_as(_ip), sizes.size, int(cross_entropy), _p(X), _p(Y), X.shape[0], _p(w),
+                                 float(decay), C.byref(loss), _p(g) if want_grad else None)
+    if rc != 0:
+        raise NotImplementedError("the reference has `???` for this network (mean squared error with several outputs)")
+    return loss.value, g
+
+
+def net_jacobian_matrix(sizes, cross_entropy, X, Y, w, decay=0.0):
+    """trainer.jacobianAndResidualsMatrix(w): (m [+ n]) x (n + 1) rows (jacobian | residual)"""
+    sizes, X, Y = _net_args(sizes, X, Y)
+    w = _a(w)
+    n = w.size
+    rows = np.empty((X.shape[0] + (n if decay > 0.0 else 0), n + 1))
+    rc = lib().orc_net_jacobian_matrix(sizes.ctypes.data_as(_ip), sizes.size, int(cross_entropy), _p(X), _p(Y), X.shape[0],
+                                       _p(w), float(decay), _p(rows))
+    if rc != 0:
+        raise NotImplementedError("the reference has `???` for this network")
+    return rows
 
 
 class QRResult:

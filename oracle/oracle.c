@@ -300,6 +300,136 @@ static void mlp_backprop(int family, const double* p, int n, const double* x, in
   if (loss) *loss = (family == ORC_MLP_CE) ? logistic_ce(out, y) : res * res;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * The general network: FFNeuralNetwork(Vector(sizes...)) with vector targets, LossType.MeanSquaredError + LinearFunction
+ * output or LossType.CrossEntropy + LogisticFunction (one output) / SoftMaxFunction (several), inner neurons
+ * LogisticFunction — what FFNeuralNetworkTrainerSpec.scala:222-260 (Vector(2, 3)) and :353-376 (Vector(4, 5, 3)) train.
+ * Weights in the reference's order: layer by layer, neuron by neuron, bias first (FFNeuralNetwork.scala:66-68,252-263).
+ *   forward  FFNeuralNetwork.forward / activateLayer (:112-158): soft-max with the maximum excitation subtracted
+ *   backward propagateErrorsOuterLayer (:161-187), Neuron.propagateError (Neuron.scala:51-63)
+ *   loss     :76-104 (the multi-class fold returns 0.0 when it meets an output that is exactly 0 — restated as is)
+ *   residual :105-110; gradient Neuron.scala:65; jacobian Neuron.scala:67-73
+ * Mean squared error with several outputs is `???` in the reference (:157): refused here too (returns -1).
+ * ------------------------------------------------------------------------------------------- */
+#define ORC_NET_MAXL 8
+#define ORC_NET_MAXW 64
+int orc_net_row(const int* sizes, int nlayers, int cross_entropy, const double* w, const double* x, const double* y,
+                double* loss, double* grad, double* jac, double* residual) {
+  double out[ORC_NET_MAXL][ORC_NET_MAXW], err[ORC_NET_MAXL][ORC_NET_MAXW], res[ORC_NET_MAXL][ORC_NET_MAXW];
+  const double* wl[ORC_NET_MAXL];
+  int K = sizes[nlayers - 1];
+  if (!cross_entropy && K > 1) return -1;
+  const double* wp = w;
+  for (int l = 1; l < nlayers; ++l) { wl[l] = wp; wp += (size_t)sizes[l] * (sizes[l - 1] + 1); }
+  for (int i = 0; i < sizes[0]; ++i) out[0][i] = x[i];
+  for (int l = 1; l < nlayers; ++l) {
+    int nin = sizes[l - 1], last = (l == nlayers - 1);
+    double exc[ORC_NET_MAXW];
+    for (int j = 0; j < sizes[l]; ++j) {
+      const double* wj = wl[l] + (size_t)j * (nin + 1);
+      exc[j] = wj[0] + inner(out[l - 1], wj + 1, nin);                       /* Neuron.activate */
+    }
+    if (last && K > 1) {                                                      /* activateLayer, CrossEntropy, several outputs */
+      double mx = exc[0], sum = 0.0, probs[ORC_NET_MAXW];
+      for (int j = 1; j < K; ++j) if (exc[j] > mx) mx = exc[j];
+      for (int j = 0; j < K; ++j) { probs[j] = exp(exc[j] - mx); sum = sum + probs[j]; }
+      for (int j = 0; j < K; ++j) out[l][j] = probs[j] / sum;
+    } else {
+      for (int j = 0; j < sizes[l]; ++j)
+        out[l][j] = (last && !cross_entropy) ? exc[j] : 1.0 / (1.0 + exp(-exc[j]));
+    }
+  }
+  int L = nlayers - 1;
+  /* outer layer */
+  double targets_sum = 0.0;
+  for (int k = 0; k < K; ++k) targets_sum = targets_sum + y[k];
+  for (int k = 0; k < K; ++k) {
+    if (!cross_entropy) { res[L][k] = out[L][k] - y[k]; err[L][k] = res[L][k] * 1.0; }
+    else if (K > 1) { res[L][k] = targets_sum * out[L][k] - y[k]; err[L][k] = res[L][k]; }
+    else { res[L][k] = out[L][k] - y[k]; err[L][k] = res[L][k]; }
+  }
+  /* inner layers, last to first */
+  for (int l = L - 1; l >= 1; --l)
+    for (int j = 0; j < sizes[l]; ++j) {
+      double ld = 0.0;
+      for (int k = 0; k < sizes[l + 1]; ++k) ld = ld + err[l + 1][k] * wl[l + 1][(size_t)k * (sizes[l] + 1) + 1 + j];
+      err[l][j] = ld * (out[l][j] * (1.0 - out[l][j]));
+      res[l][j] = res[l + 1][0];                                              /* residual = neurons.head.residual */
+    }
+  if (loss) {
+    if (!cross_entropy) { double s2 = 0.0; for (int k = 0; k < K; ++k) s2 = s2 + res[L][k] * res[L][k]; *loss = s2; }
+    else if (K == 1) *loss = logistic_ce(out[L][0], y[0]);
+    else {
+      double osum = 0.0, entropy = 0.0;
+      for (int k = 0; k < K; ++k) osum = osum + out[L][k];
+      if (osum > 0.0) {
+        for (int k = 0; k < K; ++k) entropy = (out[L][k] > 0.0) ? entropy - y[k] * log(out[L][k] / osum) : 0.0;
+        *loss = entropy;
+      } else *loss = 0.0;
+    }
+  }
+  if (residual) {
+    if (K == 1) *residual = res[L][0];
+    else { double s2 = 0.0; for (int k = 0; k < K; ++k) s2 = s2 + res[L][k] * res[L][k]; *residual = sqrt(s2); }
+  }
+  if (grad || jac) {
+    size_t q = 0;
+    for (int l = 1; l < nlayers; ++l)
+      for (int j = 0; j < sizes[l]; ++j)
+        for (int i = 0; i <= sizes[l - 1]; ++i) {
+          double g = (i == 0 ? 1.0 : out[l - 1][i - 1]) * err[l][j];
+          if (grad) grad[q] = g;
+          if (jac) jac[q] = (res[l][j] != res[l][j] || res[l][j] == 0.0) ? g : g / res[l][j];
+          ++q;
+        }
+  }
+  return 0;
+}
+
+static int net_nweights(const int* sizes, int nlayers) {
+  int n = 0;
+  for (int l = 1; l < nlayers; ++l) n += sizes[l] * (sizes[l - 1] + 1);
+  return n;
+}
+
+/* FFNeuralNetworkTrainer.apply / gradient (Trainer.scala:59-69): the fold starts from the weight-decay term and is divided
+ * by data.size; Y is m x K row-major */
+int orc_net_loss_grad(const int* sizes, int nlayers, int cross_entropy, const double* X, const double* Y, int64_t m,
+                      const double* w, double decay, double* loss, double* grad) {
+  int n = net_nweights(sizes, nlayers), f = sizes[0], K = sizes[nlayers - 1];
+  double w2 = 0.0;
+  for (int i = 0; i < n; ++i) w2 = w2 + w[i] * w[i];
+  double acc = w2 / 2.0 * decay, g[ORC_NET_MAXL * ORC_NET_MAXW * 4];
+  if (n > (int)(sizeof g / sizeof g[0])) return -1;
+  if (grad) for (int i = 0; i < n; ++i) grad[i] = w[i] * decay;
+  for (int64_t r = 0; r < m; ++r) {
+    double l;
+    if (orc_net_row(sizes, nlayers, cross_entropy, w, X + (size_t)r * f, Y + (size_t)r * K, &l, grad ? g : NULL, NULL, NULL)) return -1;
+    acc = acc + l;
+    if (grad) for (int i = 0; i < n; ++i) grad[i] = grad[i] + g[i];
+  }
+  *loss = acc / (double)m;
+  if (grad) for (int i = 0; i < n; ++i) grad[i] = grad[i] / (double)m;
+  return 0;
+}
+
+/* jacobianAndResidualsMatrix (Trainer.scala:100-108,147-153): m rows (jacobian | residual), then, with decay > 0, n penalty rows
+ * sqrt(decay) e_i | 0.  rows: (m [+ n]) x (n + 1) */
+int orc_net_jacobian_matrix(const int* sizes, int nlayers, int cross_entropy, const double* X, const double* Y, int64_t m,
+                            const double* w, double decay, double* rows) {
+  int n = net_nweights(sizes, nlayers), f = sizes[0], K = sizes[nlayers - 1];
+  for (int64_t r = 0; r < m; ++r)
+    if (orc_net_row(sizes, nlayers, cross_entropy, w, X + (size_t)r * f, Y + (size_t)r * K, NULL, NULL, rows + (size_t)r * (n + 1),
+                    rows + (size_t)r * (n + 1) + n)) return -1;
+  if (decay > 0.0)
+    for (int i = 0; i < n; ++i) {
+      double* row = rows + (size_t)(m + i) * (n + 1);
+      for (int k = 0; k <= n; ++k) row[k] = 0.0;
+      row[i] = sqrt(decay);
+    }
+  return 0;
+}
+
 typedef struct eval_ctx { int family; const double* p; int n; int f; const double* d; double eps; } eval_ctx;
 
 /* ---------------------------------------------------------------------------------------------

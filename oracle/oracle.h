@@ -76,6 +76,15 @@ void orc_jacobian_matrix(int family, const double* X, const double* y, int64_t m
                          int fd, double eps, double* rows);
 
 /* sums that QR.apply extracts from that matrix: JtJ[n*n], Jtr[n], rtr (folded row by row in `fold` order). */
+/* FFNeuralNetwork(Vector(sizes...)) with vector targets (Y is m x sizes[nlayers-1], row-major): one row, the trainer's loss /
+ * gradient with weight decay, and its Jacobian/residual rows incl. the decay penalty rows.  -1: a shape the reference itself
+ * refuses (mean squared error with several outputs is `???` there). */
+int orc_net_row(const int* sizes, int nlayers, int cross_entropy, const double* w, const double* x, const double* y,
+                double* loss, double* grad, double* jac, double* residual);
+int orc_net_loss_grad(const int* sizes, int nlayers, int cross_entropy, const double* X, const double* Y, int64_t m,
+                      const double* w, double decay, double* loss, double* grad);
+int orc_net_jacobian_matrix(const int* sizes, int nlayers, int cross_entropy, const double* X, const double* Y, int64_t m,
+                            const double* w, double decay, double* rows);
 /* compensated (Neumaier + exact products) version of the same sums: hi + lo, n*n + n + 1 doubles each; test yardstick only */
 void orc_normal_eq_comp(int family, const double* X, const double* y, int64_t m, int f, const double* p, int n, int threads,
                         double* out_hi, double* out_lo);

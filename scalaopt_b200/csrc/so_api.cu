@@ -138,6 +138,7 @@ struct so_dataset {
   so_ctx* ctx = nullptr;
   int64_t m = 0;        // rows reserved in this process
   int f = 0;
+  int ny = 1;           // outputs per observation (row-major y[m x ny]); > 1 only for the network families
   std::vector<ShardMem> shards;   // one per device of the context
   bool view = false;
   int64_t global_m = -1;          // rank mode: sum of filled rows over ranks (cached)
@@ -423,8 +424,15 @@ void teardown(so_ctx* ctx) {
   }
 }
 
-int check_family(so_ctx* ctx, int family, int f, int n) {
+int check_family(so_ctx* ctx, int family, int f, int n, int ny = 1) {
   if (family < 0 || family >= SO_FAMILY_COUNT) return fail(ctx, SO_EINVAL, "unknown family %d", family);
+  if (ny != 1 && !family_is_net(family))
+    return fail(ctx, SO_EINVAL, "family %d takes one output per observation, data set has %d", family, ny);
+  if (family_is_net(family)) {
+    if (net_hidden_units(family, f, ny, n) < 0)
+      return fail(ctx, SO_EINVAL, "network family %d on f=%d inputs and %d outputs: n=%d is not h (f + 1) + K (h + 1) (softmax: K (f + 1), K >= 2)", family, f, ny, n);
+    return SO_OK;
+  }
   if (family_is_scalar_t(family) && f != 1) return fail(ctx, SO_EINVAL, "family %d takes one input per observation, data set has f=%d", family, f);
   if (family == SO_FAMILY_POLY) {
     if (n < 1 || n > SO_MAX_POLY_N) return fail(ctx, SO_EUNSUPPORTED, "polynomial family supports 1..%d coefficients, got %d", SO_MAX_POLY_N, n);
@@ -432,8 +440,6 @@ int check_family(so_ctx* ctx, int family, int f, int n) {
   }
   if (f > SO_MAX_FEATURES) return fail(ctx, SO_EUNSUPPORTED, "f=%d exceeds SO_MAX_FEATURES=%d", f, SO_MAX_FEATURES);
   const int want = family_nparams(family, f, n);
-  if (family_is_mlp(family) && want < 0)
-    return fail(ctx, SO_EINVAL, "MLP family on f=%d inputs takes n = h (f + 2) + 1 weights for h >= 1 hidden neurons, got %d", f, n);
   if (n != want) return fail(ctx, SO_EINVAL, "family %d on f=%d inputs takes n=%d parameters, got %d", family, f, want, n);
   return SO_OK;
 }
@@ -584,7 +590,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
   for (int g = 0; g < G; ++g) {
     Device& dv = ctx->devs[g];
     const ShardMem& sm = ds->shards[g];
-    const size_t need_partials = family_is_mlp(family) && !nll ? mlp_partials_needed(kind, n, dv.sm_count)
+    const size_t need_partials = family_is_net(family) && !nll ? mlp_partials_needed(kind, n, dv.sm_count)
                                  : scalar ? scalar_partials_needed(kind, n, k, dv.sm_count)
                                           : wide_partials_needed(kind, family, n, ds->f, k, dv.sm_count);
     int rc = ensure_workspace(ctx, dv, need_partials, (size_t)Q + 2);
@@ -593,7 +599,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
     if (cudaSetDevice(dv.id) != cudaSuccess || cudaEventRecord(es.e0, dv.stream) != cudaSuccess)
       return bail(fail(ctx, SO_ECUDA, "device %d: %s", dv.id, cudaGetErrorString(cudaGetLastError())));
     Shard sh;
-    sh.X = sm.X; sh.y = sm.y; sh.rows = sm.filled; sh.f = ds->f;
+    sh.X = sm.X; sh.y = sm.y; sh.rows = sm.filled; sh.f = ds->f; sh.ny = ds->ny;
     sh.partials = dv.partials; sh.partials_doubles = dv.partials_cap;
     sh.out = dv.out; sh.out_doubles = dv.out_cap;
     sh.ticket = reinterpret_cast<unsigned int*>(fin ? dv.ctl1 : dv.ctl0);
@@ -609,7 +615,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
         sh.out_doubles = (size_t)per;
       }
       rc = nll ? launch_nll(sh, nll->pdf, p, n, nll->consts, nll->nconsts)
-               : family_is_mlp(family) ? launch_mlp(kind, sh, family, p, n, want_grad)
+               : family_is_net(family) ? launch_mlp(kind, sh, family, p, n, want_grad)
                : scalar ? launch_scalar(kind, sh, family, p, d, n, alpha, k, want_grad)
                         : launch_wide(kind, sh, family, p, d, n, alpha, k, want_grad);
       if (rc < 0) {
@@ -684,7 +690,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
   for (Device& dv : ctx->devs) dv.ev_turn = turn ^ 1;
   res.push_back((double)m_global);
   ctx->stats.rows = rows_local;
-  ctx->stats.bytes = rows_local * 8 * (int64_t)(nll ? 1 : ds->f + 1);
+  ctx->stats.bytes = rows_local * 8 * (int64_t)(nll ? 1 : ds->f + ds->ny);
   ctx->stats.launches = launches;
   ctx->stats.total_launches += launches;
   ctx->stats.total_evals += 1;
@@ -825,12 +831,14 @@ extern "C" int so_shard_plan(int64_t m, int f, int G, int g, int64_t* begin, int
   return SO_OK;
 }
 
-extern "C" int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out) {
+extern "C" int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out) { return so_dataset_create_multi(ctx, m, f, 1, out); }
+
+extern "C" int so_dataset_create_multi(so_ctx* ctx, int64_t m, int f, int ny, so_dataset** out) {
   if (!ctx || !out) return SO_EINVAL;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (m < 0 || f < 1) return fail(ctx, SO_EINVAL, "so_dataset_create: m=%lld f=%d", (long long)m, f);
+  if (m < 0 || f < 1 || ny < 1 || ny > SO_MAX_OUTPUTS) return fail(ctx, SO_EINVAL, "so_dataset_create: m=%lld f=%d ny=%d", (long long)m, f, ny);
   so_dataset* ds = new so_dataset();
-  ds->ctx = ctx; ds->m = m; ds->f = f;
+  ds->ctx = ctx; ds->m = m; ds->f = f; ds->ny = ny;
   const int G = (int)ctx->devs.size();
   ds->shards.resize(G);
   for (int g = 0; g < G; ++g) {
@@ -841,7 +849,7 @@ extern "C" int so_dataset_create(so_ctx* ctx, int64_t m, int f, so_dataset** out
     if (sm.cap > 0) {
       cudaError_t ce = cudaSetDevice(ctx->devs[g].id);
       if (ce == cudaSuccess) ce = cudaMalloc(&sm.X, sizeof(double) * (size_t)sm.cap * f);
-      if (ce == cudaSuccess) ce = cudaMalloc(&sm.y, sizeof(double) * (size_t)sm.cap);
+      if (ce == cudaSuccess) ce = cudaMalloc(&sm.y, sizeof(double) * (size_t)sm.cap * ny);
       if (ce != cudaSuccess) {
         int rc = fail(ctx, ce == cudaErrorMemoryAllocation ? SO_ENOMEM : SO_ECUDA,
                       "so_dataset_create: %lld rows x %d on device %d: %s", (long long)sm.cap, f, ctx->devs[g].id, cudaGetErrorString(ce));
@@ -923,11 +931,11 @@ struct MemSource : RowSource {
   const double* direct(bool is_y, int64_t off) override { return pinned ? (is_y ? y : X) + off : nullptr; }
 };
 struct FileSource : RowSource {
-  int fdx = -1, fdy = -1; int64_t base_rows = 0; int f = 1;
+  int fdx = -1, fdy = -1; int64_t base_rows = 0; int f = 1, ny = 1;
   ~FileSource() override { if (fdx >= 0) close(fdx); if (fdy >= 0) close(fdy); }
   int fetch(bool is_y, int64_t off, int64_t count, double* dst) override {
     const int fd = is_y ? fdy : fdx;
-    const int64_t base = (int64_t)sizeof(double) * ((is_y ? base_rows : base_rows * f) + off);
+    const int64_t base = (int64_t)sizeof(double) * ((is_y ? base_rows * ny : base_rows * f) + off);
     return parallel_chunks(count, [&](int64_t b, int64_t e) {
       char* out = reinterpret_cast<char*>(dst + b);
       int64_t pos = base + (int64_t)sizeof(double) * b, left = (int64_t)sizeof(double) * (e - b);
@@ -948,7 +956,7 @@ int ingest(so_dataset* ds, RowSource& src, int64_t rows) {
   int64_t filled = 0;
   for (const ShardMem& sm : ds->shards) filled += sm.filled;
   if (filled + rows > ds->m) return fail(ctx, SO_EINVAL, "ingest: %lld rows do not fit (%lld of %lld used)", (long long)rows, (long long)filled, (long long)ds->m);
-  const int f = ds->f;
+  const int f = ds->f, ny = ds->ny;
   int64_t done = 0;
   int turn = 0;
   for (size_t g = 0; g < ds->shards.size() && done < rows; ++g) {
@@ -959,8 +967,8 @@ int ingest(so_dataset* ds, RowSource& src, int64_t rows) {
     SO_CUDA(ctx, cudaSetDevice(dv.id));
     for (int pass = 0; pass < 2; ++pass) {               // X stream, then y stream
       const bool is_y = pass == 1;
-      const int64_t width = is_y ? 1 : f;
-      double* dst = is_y ? sm.y + sm.filled : sm.X + (size_t)sm.filled * f;
+      const int64_t width = is_y ? ny : f;
+      double* dst = is_y ? sm.y + (size_t)sm.filled * ny : sm.X + (size_t)sm.filled * f;
       const int64_t total = take * width, src_off = done * width;
       if (const double* direct = src.direct(is_y, src_off)) {
         SO_CUDA(ctx, cudaMemcpyAsync(dst, direct, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, dv.stream));
@@ -1009,7 +1017,7 @@ extern "C" int so_dataset_load_raw(so_dataset* ds, const char* path_X, const cha
   FileSource src;
   src.fdx = open(path_X, O_RDONLY);
   src.fdy = open(path_y, O_RDONLY);
-  src.base_rows = file_row_offset; src.f = ds->f;
+  src.base_rows = file_row_offset; src.f = ds->f; src.ny = ds->ny;
   if (src.fdx < 0 || src.fdy < 0) return fail(ctx, SO_EINVAL, "so_dataset_load_raw: cannot open %s / %s", path_X, path_y);
   return ingest(ds, src, rows);
 }
@@ -1032,6 +1040,7 @@ extern "C" int so_dataset_generate(so_dataset* ds, int family, const double* p_t
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (ds->view) return fail(ctx, SO_EINVAL, "so_dataset_generate: cannot fill a view");
   ++ctx->data_epoch;
+  if (ds->ny != 1) return fail(ctx, SO_EUNSUPPORTED, "so_dataset_generate: synthetic data exist for one output per observation only");
   int rc = check_family(ctx, family, ds->f, n);
   if (rc) return rc;
   // the t grid of the scalar families spans the global data set: in rank mode every rank holds m rows
@@ -1067,7 +1076,7 @@ extern "C" int so_dataset_read(so_dataset* ds, int64_t row_begin, int64_t rows, 
     if (hi > lo) {
       SO_CUDA(ctx, cudaSetDevice(ctx->devs[g].id));
       if (X) SO_CUDA(ctx, cudaMemcpy(X + (size_t)done * ds->f, sm.X + (size_t)(lo - base) * ds->f, sizeof(double) * (size_t)(hi - lo) * ds->f, cudaMemcpyDeviceToHost));
-      if (y) SO_CUDA(ctx, cudaMemcpy(y + done, sm.y + (lo - base), sizeof(double) * (size_t)(hi - lo), cudaMemcpyDeviceToHost));
+      if (y) SO_CUDA(ctx, cudaMemcpy(y + (size_t)done * ds->ny, sm.y + (size_t)(lo - base) * ds->ny, sizeof(double) * (size_t)(hi - lo) * ds->ny, cudaMemcpyDeviceToHost));
       done += hi - lo;
     }
     base += sm.filled;
@@ -1098,7 +1107,7 @@ extern "C" int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_d
   for (const ShardMem& sm : ds->shards) filled += sm.filled;
   if (begin < 0 || end < begin || end > filled) return fail(ctx, SO_EINVAL, "so_dataset_slice: [%lld, %lld) outside [0, %lld)", (long long)begin, (long long)end, (long long)filled);
   so_dataset* v = new so_dataset();
-  v->ctx = ctx; v->f = ds->f; v->view = true; v->m = end - begin;
+  v->ctx = ctx; v->f = ds->f; v->ny = ds->ny; v->view = true; v->m = end - begin;
   v->shards.resize(ds->shards.size());
   int64_t base = 0;
   for (size_t g = 0; g < ds->shards.size(); ++g) {
@@ -1106,7 +1115,7 @@ extern "C" int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_d
     const int64_t lo = std::max<int64_t>(begin, base), hi = std::min<int64_t>(end, base + sm.filled);
     if (hi > lo) {
       v->shards[g].X = sm.X + (size_t)(lo - base) * ds->f;
-      v->shards[g].y = sm.y + (lo - base);
+      v->shards[g].y = sm.y + (size_t)(lo - base) * ds->ny;
       v->shards[g].cap = v->shards[g].filled = hi - lo;
     }
     base += sm.filled;
@@ -1140,7 +1149,7 @@ extern "C" int so_eval_loss_grad(so_dataset* ds, int family, const double* p, in
   if (!ds || !p || !loss) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  int rc = check_family(ctx, family, ds->f, n);
+  int rc = check_family(ctx, family, ds->f, n, ds->ny);
   if (rc) return rc;
   const int Q = grad ? 1 + n : 1;
   std::vector<double> res;
@@ -1156,7 +1165,7 @@ extern "C" int so_eval_normal_eq(so_dataset* ds, int family, const double* p, in
   if (!ds || !p || !JtJ || !Jtr || !rtr) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  int rc = check_family(ctx, family, ds->f, n);
+  int rc = check_family(ctx, family, ds->f, n, ds->ny);
   if (rc) return rc;
   const int T = n * (n + 1) / 2, Q = T + n + 1;
   std::vector<double> res;
@@ -1200,7 +1209,7 @@ extern "C" int so_eval_qr(so_dataset* ds, int family, const double* p, int n, do
   if (!ds || !p || !R) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  int rc = check_family(ctx, family, ds->f, n);
+  int rc = check_family(ctx, family, ds->f, n, ds->ny);
   if (rc) return rc;
   const bool narrow = (family == SO_FAMILY_LINEAR || family == SO_FAMILY_LINEAR_NOINT || family == SO_FAMILY_LOGISTIC) && n <= SO_QR_COLS_MAX_N;
   if (!family_is_scalar_t(family) && !narrow)
@@ -1220,10 +1229,10 @@ extern "C" int so_eval_line(so_dataset* ds, int family, const double* p, const d
   if (!ds || !p || !d || !alpha || !phi || !dphi) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  int rc = check_family(ctx, family, ds->f, n);
+  int rc = check_family(ctx, family, ds->f, n, ds->ny);
   if (rc) return rc;
   if (k < 1 || k > SO_MAX_ALPHAS) return fail(ctx, SO_EINVAL, "so_eval_line: k=%d outside [1, %d]", k, SO_MAX_ALPHAS);
-  if (family_is_mlp(family)) {
+  if (family_is_net(family)) {
     // LineSearchPoint.fx / dfx as the reference evaluates them: f(x + a d) and gradient(x + a d) . d (Point.scala:54-57),
     // one fused loss+gradient launch per step size
     so_call_stats acc{};
@@ -1281,9 +1290,9 @@ extern "C" int so_eval_hess_vec(so_dataset* ds, int family, const double* p, con
   if (!ds || !p || !d || !Hd) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  int rc = check_family(ctx, family, ds->f, n);
+  int rc = check_family(ctx, family, ds->f, n, ds->ny);
   if (rc) return rc;
-  if (family_is_mlp(family)) {
+  if (family_is_net(family)) {
     // FFNeuralNetworkTrainer.dirHessian: (gradient(w + d * eps) - gradient(w)) / eps, eps = 1e-8 (Trainer.scala:46,76-80)
     const double eps = 1.0e-8;
     so_call_stats acc{};

@@ -41,6 +41,7 @@ struct Shard {
   const double* y = nullptr;   // rows
   int64_t rows = 0;
   int f = 0;
+  int ny = 1;                  // outputs per row (y is rows x ny, row-major); > 1 only for the network families
   // workspace owned by the context (per device)
   double* partials = nullptr;  // per-block partial sums
   size_t partials_doubles = 0;
@@ -93,7 +94,7 @@ int launch_wide(Kind kind, const Shard& s, int family, const double* p, const do
 
 // FFNeuralNetwork(Vector(f, h, 1)) families (so_mlp.cu): kLossGrad and kNormalEq
 int launch_mlp(Kind kind, const Shard& s, int family, const double* p, int n, int want_grad);
-int mlp_hidden_units(int f, int n);      // h from n = h (f + 2) + 1, or -1
+int launch_net(Kind kind, const Shard& s, int family, int h, const double* p, int n, int want_grad);   // so_net.cu: any (f, h, K)
 size_t mlp_partials_needed(Kind kind, int n, int sm_count);
 
 // min / max / non-finite count of the X stream of an f == 1 shard -> buf3 (device, order-preserving integer keys; the
@@ -126,10 +127,19 @@ inline int family_nparams(int family, int f, int n_hint) {
     case SO_FAMILY_GAUSS: return 3;
     case SO_FAMILY_GAUSS_EXPBKG: return 5;
     case SO_FAMILY_POLY: return n_hint;
-    case SO_FAMILY_MLP_MSE: case SO_FAMILY_MLP_CE: return (n_hint >= f + 3 && (n_hint - 1) % (f + 2) == 0) ? n_hint : -1;
+    case SO_FAMILY_MLP_MSE: case SO_FAMILY_MLP_CE: case SO_FAMILY_SOFTMAX: return n_hint;     // checked by net_hidden_units
   }
   return -1;
 }
 inline bool family_is_mlp(int family) { return family == SO_FAMILY_MLP_MSE || family == SO_FAMILY_MLP_CE; }
+// the FFNeuralNetwork families (so_mlp.cu, so_net.cu): one hidden layer of h >= 1 logistic neurons, or none (SOFTMAX)
+inline bool family_is_net(int family) { return family_is_mlp(family) || family == SO_FAMILY_SOFTMAX; }
+// hidden neurons from the weight count: n = h (f + 1) + K (h + 1); SOFTMAX: n = K (f + 1) and h = 0.  -1: no such network
+inline int net_hidden_units(int family, int f, int K, int n) {
+  if (family == SO_FAMILY_SOFTMAX) return (K >= 2 && n == K * (f + 1)) ? 0 : -1;
+  if (n <= K || (n - K) % (f + 1 + K) != 0) return -1;
+  const int h = (n - K) / (f + 1 + K);
+  return h >= 1 ? h : -1;
+}
 
 }  // namespace so

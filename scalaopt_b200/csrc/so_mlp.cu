@@ -156,16 +156,19 @@ int dispatch(Kind kind, const Shard& s, int h, const double* p, int want_grad) {
 
 }  // namespace
 
-int mlp_hidden_units(int f, int n) { return (n >= f + 3 && (n - 1) % (f + 2) == 0) ? (n - 1) / (f + 2) : -1; }
-
 size_t mlp_partials_needed(Kind kind, int n, int sm_count) {
   return (size_t)sm_count * 8 * (size_t)std::max(out_doubles(kind, n, 1), 16);
 }
 
+// scalar output and f, h <= 4: the register-resident template kernels above; any other catalogue shape (several outputs,
+// soft-max, wider layers, no hidden layer): so_net.cu
 int launch_mlp(Kind kind, const Shard& s, int family, const double* p, int n, int want_grad) {
-  const int h = mlp_hidden_units(s.f, n);
-  if (h < 1) return SO_EINVAL;
-  return family == SO_FAMILY_MLP_CE ? dispatch<true>(kind, s, h, p, want_grad) : dispatch<false>(kind, s, h, p, want_grad);
+  const int h = net_hidden_units(family, s.f, s.ny, n);
+  if (h < 0) return SO_EINVAL;
+  const bool small_k2 = kind != kNormalEq || n <= 9;
+  if (s.ny == 1 && family != SO_FAMILY_SOFTMAX && s.f <= 4 && h >= 1 && h <= 4 && small_k2)
+    return family == SO_FAMILY_MLP_CE ? dispatch<true>(kind, s, h, p, want_grad) : dispatch<false>(kind, s, h, p, want_grad);
+  return launch_net(kind, s, family, h, p, n, want_grad);
 }
 
 }  // namespace so

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libscalaopt_host.so")
 LEVENBERG_MARQUARDT, BFGS, CONJUGATE_GRADIENT, NEWTON_CG, STEIHAUG_CG, NELDER_MEAD = range(6)
 OK, MAX_ITER, ILLEGAL_ARG, GPU_ERROR, ERROR = range(5)
 
-EXPORTS = ["soh_default_config", "soh_objective_from_callbacks", "soh_objective_gpu", "soh_objective_use_tsqr", "soh_objective_speculate", "soh_objective_gpu_nll", "soh_objective_free",
+EXPORTS = ["soh_default_config", "soh_objective_from_callbacks", "soh_objective_gpu", "soh_objective_use_tsqr", "soh_objective_set_decay", "soh_objective_speculate", "soh_objective_gpu_nll", "soh_objective_free",
            "soh_objective_counters", "soh_objective_apply", "soh_objective_gradient", "soh_objective_dirder",
            "soh_objective_dir_hessian", "soh_objective_jacobian_rows", "soh_minimize", "soh_zoom_step_length",
            "soh_qr", "soh_last_error"]
@@ -86,6 +86,7 @@ def load():
     L.soh_objective_gpu.restype = vp
     L.soh_objective_use_tsqr.argtypes = [vp, C.c_int]
     L.soh_objective_speculate.argtypes = [vp, C.c_int]
+    L.soh_objective_set_decay.argtypes = [vp, C.c_double]
     L.soh_objective_gpu_nll.argtypes = [vp, vp, C.c_int, C.c_int, _dp, C.c_int]
     L.soh_objective_gpu_nll.restype = vp
     L.soh_objective_free.argtypes = [vp]
@@ -163,12 +164,15 @@ class Objective:
         return cls(h, n, keepalive=cbs)
 
     @classmethod
-    def gpu(cls, ctx: native.Context, ds: native.Dataset, family: int, n: int, tsqr: bool = False, speculate: bool = True):
+    def gpu(cls, ctx: native.Context, ds: native.Dataset, family: int, n: int, tsqr: bool = False, speculate: bool = True,
+            decay: float = 0.0):
         """GpuMSEFunction(family, GpuDataSet(ds)); tsqr=True: Jacobian system from so_eval_qr instead of K2 + Cholesky;
         speculate=False: LM trial-point losses from K1 loss passes instead of speculative K2 passes"""
         h = load().soh_objective_gpu(ctx._h, ds._h, ds.f, family, n)
         if not speculate:
             load().soh_objective_speculate(h, 0)
+        if decay and load().soh_objective_set_decay(h, float(decay)) != 0:
+            raise IllegalArgumentException(load().soh_last_error().decode())
         if tsqr and load().soh_objective_use_tsqr(h, 1) != 0:
             raise RuntimeError(load().soh_last_error().decode())
         return cls(h, n, keepalive=(ctx, ds))

@@ -109,6 +109,10 @@ class GpuMSEFunction : public MSEFunction {
   // rejected again), and only where a K2 pass costs about what a K1 pass costs (n <= 16: the Gram is HBM-bound).
   bool speculate = true;
   static constexpr int kSpeculateMaxN = 16;
+  // FFNeuralNetworkTrainer's weight decay (std-apps/.../nnet/FFNeuralNetworkTrainer.scala:59-69,100-108,147-153): the loss fold
+  // starts from |w|^2 / 2 * decay, the gradient fold from w * decay (both divided by data.size), and the Jacobian/residual
+  // matrix gains n rows sqrt(decay) e_i | 0.  Data-independent, O(n): applied here, around the device sums.
+  double decay = 0.0;
   mutable GpuCounters counters;
   GpuMSEFunction(std::shared_ptr<GpuDataSet> d, int family_, int n_) : data(std::move(d)), family(family_), n(n_) {}
 
@@ -127,7 +131,7 @@ class GpuMSEFunction : public MSEFunction {
       counters.k2_passes++; counters.spec_passes++;
       double rtr = 0.0;
       for (int i = 0; i <= n; ++i) rtr += spec.R[(size_t)i * (n + 1) + n] * spec.R[(size_t)i * (n + 1) + n];
-      const double loss = rtr * loss_scale() / (double)data->size();
+      const double loss = rtr * loss_scale() / (double)data->size() + decay_loss(x);
       remember(x, loss, nullptr);
       return loss;
     }
@@ -136,7 +140,7 @@ class GpuMSEFunction : public MSEFunction {
       check(so_eval_normal_eq(data->ds, family, x.data(), n, spec.JtJ.data(), spec.Jtr.data(), &spec.rtr));
       spec.x = x; spec.valid = true;
       counters.k2_passes++; counters.spec_passes++;
-      const double loss = spec.rtr * loss_scale() / (double)data->size();
+      const double loss = spec.rtr * loss_scale() / (double)data->size() + decay_loss(x);
       remember(x, loss, nullptr);
       return loss;
     }
@@ -144,6 +148,7 @@ class GpuMSEFunction : public MSEFunction {
       double loss = 0.0;
       check(so_eval_loss_grad(data->ds, family, x.data(), n, &loss, nullptr));
       counters.k1_passes++;
+      loss += decay_loss(x);
       remember(x, loss, nullptr);
       return loss;
     }
@@ -190,10 +195,11 @@ class GpuMSEFunction : public MSEFunction {
       double rtr = 0.0;
       for (int i = 0; i <= n; ++i) rtr += Rf[(size_t)i * (n + 1) + n] * Rf[(size_t)i * (n + 1) + n];
       // the loss at p is a function of r^T r only for the MSE families (cross-entropy: K1 computes it when LM asks)
-      if (loss_scale() > 0.0) { int64_t m = data->size(); remember(p, rtr * loss_scale() / (double)m, nullptr); }
+      if (loss_scale() > 0.0) { int64_t m = data->size(); remember(p, rtr * loss_scale() / (double)m + decay_loss(p), nullptr); }
       std::vector<AugmentedRow> rows;
       for (int i = 0; i <= n; ++i)
         rows.emplace_back(Vec(Rf.begin() + (size_t)i * (n + 1), Rf.begin() + (size_t)i * (n + 1) + n), Rf[(size_t)i * (n + 1) + n], (int64_t)i);
+      append_penalty_rows(rows);
       return std::make_shared<SeqDataSet<AugmentedRow>>(std::move(rows));
     }
     std::vector<double> JtJ((size_t)n * n), Jtr(n);
@@ -207,7 +213,11 @@ class GpuMSEFunction : public MSEFunction {
     }
     // the loss at p comes for free: sum r^2 / (2m) for the MSE families; FFNeuralNetwork's MSE loss is not halved
     // (FFNeuralNetwork.scala:70-72); the cross-entropy families' loss is not a function of r^T r
-    if (loss_scale() > 0.0) { int64_t m = data->size(); remember(p, rtr * loss_scale() / (double)m, nullptr); }
+    if (loss_scale() > 0.0) { int64_t m = data->size(); remember(p, rtr * loss_scale() / (double)m + decay_loss(p), nullptr); }
+    // weight decay: the penalty rows sqrt(decay) e_i | 0 of the trainer's matrix (Trainer.scala:147-153) add decay to the
+    // diagonal of the Gram; folding them in BEFORE the factorisation matters — J alone is often rank-deficient for a
+    // network (soft-max redundancy: cond(J) ~ 1e35 on the Iris-shaped spec case) while [J; sqrt(decay) I] never is
+    if (decay > 0.0) for (int i = 0; i < n; ++i) JtJ[(size_t)i * n + i] += decay;
     // Cholesky JtJ = R^T R (upper R), q = R^-T Jtr, rho = sqrt(max(0, rtr - q.q)); O(n^3) on the host
     std::vector<Vec> R(n, Vec(n, 0.0));
     Vec q(n, 0.0);
@@ -241,8 +251,15 @@ class GpuMSEFunction : public MSEFunction {
   // loss = loss_scale * r^T r / m where the loss is a function of r^T r (0: it is not)
   double loss_scale() const {
     if (family == SO_FAMILY_MLP_MSE) return 1.0;                  // FFNeuralNetwork.scala:70-72, not halved
-    if (family == SO_FAMILY_LOGISTIC || family == SO_FAMILY_MLP_CE) return 0.0;
+    if (family == SO_FAMILY_LOGISTIC || family == SO_FAMILY_MLP_CE || family == SO_FAMILY_SOFTMAX) return 0.0;
     return 0.5;                                                   // MSEFunction.scala:34
+  }
+  double decay_loss(const Vec& x) const { return decay > 0.0 ? 0.5 * decay * dot(x, x) / (double)data->size() : 0.0; }
+  void append_penalty_rows(std::vector<AugmentedRow>& rows) const {      // penaltyMatrix, Trainer.scala:147-153
+    if (!(decay > 0.0)) return;
+    const double pen = std::sqrt(decay);
+    const int64_t base = (int64_t)rows.size();
+    for (int i = 0; i < n; ++i) { Vec e(n, 0.0); e[i] = pen; rows.emplace_back(std::move(e), 0.0, base + i); }
   }
   struct LineEntry { double beta, phi, dphi; };
   mutable std::list<Entry> cache;                 // most recent first; keyed on the bit pattern of x
@@ -264,6 +281,11 @@ class GpuMSEFunction : public MSEFunction {
     double loss = 0.0; Vec g(n);
     check(so_eval_loss_grad(data->ds, family, x.data(), n, &loss, g.data()));
     counters.k1_passes++;
+    if (decay > 0.0) {
+      const double m = (double)data->size();
+      loss += decay_loss(x);
+      for (int i = 0; i < n; ++i) g[i] += x[i] * decay / m;
+    }
     remember(x, loss, &g);
     if (on_ray_beta(x)) ray_trials++;
     return *find(x);

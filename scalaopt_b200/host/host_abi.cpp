@@ -114,6 +114,13 @@ extern "C" int soh_objective_use_tsqr(soh_objective* o, int on) {
   return SOH_OK;
 }
 
+extern "C" int soh_objective_set_decay(soh_objective* o, double decay) {
+  auto* g = o ? dynamic_cast<GpuMSEFunction*>(o->fn.get()) : nullptr;
+  if (!g || !(decay >= 0.0)) { g_err = "soh_objective_set_decay: not a GPU least-squares objective, or decay < 0"; return SOH_ILLEGAL_ARG; }
+  g->decay = decay;
+  return SOH_OK;
+}
+
 extern "C" int soh_objective_speculate(soh_objective* o, int on) {
   auto* g = o ? dynamic_cast<GpuMSEFunction*>(o->fn.get()) : nullptr;
   if (!g) { g_err = "soh_objective_speculate: not a GPU least-squares objective"; return SOH_ILLEGAL_ARG; }

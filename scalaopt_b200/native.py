@@ -14,9 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscalaopt_cuda.so")
 
-LINEAR, LINEAR_NOINT, LOGISTIC, EXPDECAY, GAUSS, GAUSS_EXPBKG, POLY, MLP_MSE, MLP_CE = range(9)
+LINEAR, LINEAR_NOINT, LOGISTIC, EXPDECAY, GAUSS, GAUSS_EXPBKG, POLY, MLP_MSE, MLP_CE, SOFTMAX = range(10)
 FAMILY_NAMES = {LINEAR: "linear", LINEAR_NOINT: "linear_noint", LOGISTIC: "logistic", EXPDECAY: "expdecay",
-                GAUSS: "gauss", GAUSS_EXPBKG: "gauss_expbkg", POLY: "poly", MLP_MSE: "mlp_mse", MLP_CE: "mlp_ce"}
+                GAUSS: "gauss", GAUSS_EXPBKG: "gauss_expbkg", POLY: "poly", MLP_MSE: "mlp_mse", MLP_CE: "mlp_ce", SOFTMAX: "softmax"}
 PDF_GAUSS_EXPBKG = 0
 MAX_ALPHAS = 32
 NCCL_UID_BYTES = 128
@@ -25,7 +25,7 @@ NCCL_UID_BYTES = 128
 EXPORTS = [
     "so_init", "so_nccl_unique_id", "so_init_rank", "so_shutdown", "so_last_error", "so_abi_version",
     "so_host_alloc", "so_host_free",
-    "so_shard_plan", "so_dataset_create", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
+    "so_shard_plan", "so_dataset_create", "so_dataset_create_multi", "so_dataset_append", "so_dataset_load_raw", "so_dataset_clear", "so_dataset_generate", "so_dataset_read",
     "so_dataset_size", "so_dataset_head", "so_dataset_slice", "so_dataset_free",
     "so_eval_loss_grad", "so_eval_normal_eq", "so_eval_qr", "so_eval_line", "so_eval_hess_vec", "so_eval_nll", "so_stats", "so_stats_reset",
 ]
@@ -82,6 +82,7 @@ def load():
     L.so_host_free.restype = None
     L.so_shard_plan.argtypes = [i64, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.so_dataset_create.argtypes = [vp, i64, i32, C.POINTER(vp)]
+    L.so_dataset_create_multi.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]
     L.so_dataset_append.argtypes = [vp, vp, vp, i64]
     L.so_dataset_load_raw.argtypes = [vp, C.c_char_p, C.c_char_p, i64, i64]
     L.so_dataset_clear.argtypes = [vp]
@@ -203,22 +204,22 @@ class Context:
 class Dataset:
     """``so_dataset``: observations resident in HBM."""
 
-    def __init__(self, ctx: Context, m: int, f: int, _handle=None, _parent=None):
-        self.ctx, self.f = ctx, f
+    def __init__(self, ctx: Context, m: int, f: int, _handle=None, _parent=None, ny: int = 1):
+        self.ctx, self.f, self.ny = ctx, f, ny
         self._parent = _parent
         if _handle is not None:
             self._h = _handle
         else:
             self._h = C.c_void_p()
-            ctx.check(load().so_dataset_create(ctx._h, m, f, C.byref(self._h)))
+            ctx.check(load().so_dataset_create_multi(ctx._h, m, f, ny, C.byref(self._h)))
         import weakref
         ctx._datasets.append(weakref.ref(self))
 
     def append(self, X, y):
         X = np.ascontiguousarray(X, dtype=np.float64)
         y = _vec(y)
-        rows = y.size
-        assert X.size == rows * self.f, "X must be rows x f"
+        rows = y.size // self.ny
+        assert X.size == rows * self.f and y.size == rows * self.ny, "X must be rows x f, y rows x ny"
         self.ctx.check(load().so_dataset_append(self._h, X.ctypes.data, y.ctypes.data, rows))
         return self
 
@@ -242,7 +243,7 @@ class Dataset:
 
     def read(self, row_begin, rows):
         X = np.empty((rows, self.f))
-        y = np.empty(rows)
+        y = np.empty(rows) if self.ny == 1 else np.empty((rows, self.ny))
         self.ctx.check(load().so_dataset_read(self._h, row_begin, rows, X.ctypes.data, y.ctypes.data))
         return X, y
 
@@ -260,7 +261,7 @@ class Dataset:
     def slice(self, begin, end) -> "Dataset":
         h = C.c_void_p()
         self.ctx.check(load().so_dataset_slice(self._h, begin, end, C.byref(h)))
-        return Dataset(self.ctx, end - begin, self.f, _handle=h, _parent=self)
+        return Dataset(self.ctx, end - begin, self.f, _handle=h, _parent=self, ny=self.ny)
 
     # ---- the four evaluations ----
     def loss_grad(self, family, p, want_grad=True):

@@ -185,3 +185,35 @@ def test_compensated_normal_equations_agree_with_the_fold_and_beat_it(oracle):
     assert np.all(lo == 0.0)
     assert hi[-1] == float(np.sum(r.astype(object) ** 2))
     assert hi[0] == 2000.0 and hi[1] == float(np.sum(Xi)) and hi[3] == float(np.sum(Xi[:, 0].astype(object) ** 2))
+
+
+def test_network_restatement_with_vector_targets(oracle):
+    """The general FFNeuralNetwork restatement (oracle.net_*): what FFNeuralNetworkTrainerSpec.scala:38-117 asserts of the
+    reference — back-propagated gradient = finite-difference gradient to 1e-5 — for the multi-class shapes of :222-260 and
+    :353-376, with and without weight decay; equality with the one-output restatement; the penalty rows; and the refusal
+    of mean squared error with several outputs (`???` in the reference)."""
+    rng = np.random.default_rng(1)
+    for sizes in ((4, 5, 3), (2, 3), (3, 2, 2, 2)):
+        n = oracle.net_nweights(sizes)
+        X = rng.standard_normal((60, sizes[0]))
+        Y = np.eye(sizes[-1])[rng.integers(0, sizes[-1], 60)]
+        w = rng.uniform(-0.5, 0.5, n)
+        for decay in (0.0, 0.01):
+            l, g = oracle.net_loss_grad(sizes, True, X, Y, w, decay=decay)
+            eps = 1e-7
+            gfd = np.array([(oracle.net_loss_grad(sizes, True, X, Y, w + eps * np.eye(n)[i], decay=decay, want_grad=False)[0] - l) / eps
+                            for i in range(n)])
+            np.testing.assert_allclose(g, gfd, rtol=0, atol=1e-5)
+    w2 = rng.uniform(-0.5, 0.5, 9)
+    X2 = rng.standard_normal((40, 2)); y2 = rng.integers(0, 2, 40).astype(float)
+    for fam, ce in ((oracle.MLP_CE, True), (oracle.MLP_MSE, False)):
+        l_new, g_new = oracle.net_loss_grad([2, 2, 1], ce, X2, y2.reshape(-1, 1), w2)
+        assert l_new == oracle.apply(fam, X2, y2, w2)
+        np.testing.assert_array_equal(g_new, oracle.gradient(fam, X2, y2, w2))
+        np.testing.assert_array_equal(oracle.net_jacobian_matrix([2, 2, 1], ce, X2, y2.reshape(-1, 1), w2),
+                                      oracle.jacobian_matrix(fam, X2, y2, w2))
+    rows = oracle.net_jacobian_matrix([2, 2, 1], True, X2, y2.reshape(-1, 1), w2, decay=0.04)
+    assert rows.shape == (49, 10)
+    np.testing.assert_array_equal(rows[40:, :9], 0.2 * np.eye(9)); assert np.all(rows[40:, 9] == 0.0)
+    with pytest.raises(NotImplementedError):
+        oracle.net_loss_grad([2, 2, 3], False, X2, np.zeros((40, 3)), rng.uniform(-1, 1, 15))
