@@ -206,3 +206,27 @@ def test_logistic_saturated_predictors_match_a_50_digit_reference(native, oracle
         H_ref = [h + o * (1 - o) * xd * xv for h, xv in zip(H_ref, xt)]
     assert_vec(Hd, np.array([float(h / m) for h in H_ref]), rtol=1e-11, what="Hd vs mpmath")
     ds.free()
+
+
+@pytest.mark.parametrize("name,f", [("LINEAR", 31), ("LOGISTIC", 33), ("LINEAR_NOINT", 9), ("LINEAR", 127), ("LINEAR_NOINT", 511)])
+@pytest.mark.parametrize("m", [20_000, 20_001, 1, 2])
+def test_odd_row_lengths_row_pair_path(native, oracle, gpu_ctx, name, f, m):
+    """odd f streams row PAIRS with 128-bit loads (k_wide_pair): even and odd row counts, a single row, and views that
+    start on an odd row (8-byte aligned only: the 64-bit mapping takes those) must all give the oracle's sums"""
+    fam = getattr(oracle, name)
+    truth = _truth(name, f)
+    if f > 200 and m > 1000:
+        m = 3_000 + (m & 1)
+    X, y = oracle.generate(fam, m, f, truth)
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    p = truth * 0.9 + 0.05
+    d = np.cos(np.arange(p.size)) * 0.1
+    views = [(0, m)] + ([(1, m), (2, m - 1)] if m > 4 else [])
+    for b, e in views:
+        v = ds.slice(b, e)
+        loss, grad = v.loss_grad(fam, p)
+        assert_loss(loss, oracle.apply(fam, X[b:e], y[b:e], p))
+        assert_vec(grad, oracle.gradient(fam, X[b:e], y[b:e], p))
+        assert_vec(v.hess_vec(fam, p, d), oracle.hess_vec(fam, X[b:e], y[b:e], p, d), rtol=1e-11, what="Hd")
+        v.free()
+    ds.free()

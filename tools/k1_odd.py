@@ -1,0 +1,20 @@
+"""K1 / K4 on odd and even row lengths: python tools/k1_odd.py"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from scalaopt_b200 import native
+HBM = 6554.2
+with native.Context(1) as ctx:
+    for name, f, m in (("linear", 31, 100_000_000), ("linear_noint", 32, 100_000_000), ("linear", 127, 20_000_000), ("linear_noint", 128, 20_000_000), ("logistic", 33, 80_000_000), ("linear", 9, 200_000_000), ("linear", 15, 200_000_000)):
+        fam = {"linear_noint": native.LINEAR_NOINT, "linear": native.LINEAR, "logistic": native.LOGISTIC}[name]
+        n = f + (0 if name == "linear_noint" else 1)
+        truth = np.arange(1, n + 1) / n
+        ds = native.Dataset(ctx, m, f).generate(fam, truth)
+        out = {"family": name, "f": f, "rows": m}
+        for what, fn in (("k1_ms", lambda: ds.loss_grad(fam, truth * 0.9)), ("k4_ms", lambda: ds.hess_vec(fam, truth * 0.9, truth))):
+            ks = []
+            for _ in range(6):
+                fn(); ks.append(ctx.stats().kernel_ms)
+            out[what] = float(np.median(ks[1:])); out[what.replace("_ms", "_hbm_frac")] = m * 8.0 * (f + 1) / 1e9 / (out[what] * 1e-3) / HBM
+        print(json.dumps(out), flush=True)
+        ds.free()
