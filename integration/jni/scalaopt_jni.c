@@ -26,20 +26,33 @@ JNIEXPORT jlong JNICALL JFN(datasetCreate)(JNIEnv* e, jobject o, jlong ctx, jlon
   so_dataset* ds = 0;
   return so_dataset_create((so_ctx*)(intptr_t)ctx, m, f, &ds) == SO_OK ? (jlong)(intptr_t)ds : 0;
 }
+/* Bulk transfers do NOT hold a JNI critical section: a multi-GB host-to-device copy inside GetPrimitiveArrayCritical would
+ * stall the JVM's garbage collector for its whole duration.  Get/ReleaseDoubleArrayElements may copy; callers that ingest
+ * at PCIe speed use datasetAppendDirect with direct ByteBuffers over so_host_alloc'ed (pinned) memory. */
 JNIEXPORT jint JNICALL JFN(datasetAppend)(JNIEnv* e, jobject o, jlong ds, jdoubleArray x, jdoubleArray y, jlong rows) {
-  double* px = (*e)->GetPrimitiveArrayCritical(e, x, 0);
-  double* py = (*e)->GetPrimitiveArrayCritical(e, y, 0);
+  jdouble* px = (*e)->GetDoubleArrayElements(e, x, 0);
+  jdouble* py = (*e)->GetDoubleArrayElements(e, y, 0);
   int rc = so_dataset_append((so_dataset*)(intptr_t)ds, px, py, rows);
-  (*e)->ReleasePrimitiveArrayCritical(e, y, py, JNI_ABORT);
-  (*e)->ReleasePrimitiveArrayCritical(e, x, px, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, y, py, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, x, px, JNI_ABORT);
   return rc;
 }
+JNIEXPORT jint JNICALL JFN(datasetAppendDirect)(JNIEnv* e, jobject o, jlong ds, jobject xBuf, jobject yBuf, jlong rows) {
+  const double* px = (const double*)(*e)->GetDirectBufferAddress(e, xBuf);
+  const double* py = (const double*)(*e)->GetDirectBufferAddress(e, yBuf);
+  if (!px || !py) return SO_EINVAL;
+  return so_dataset_append((so_dataset*)(intptr_t)ds, px, py, rows);
+}
+JNIEXPORT jlong JNICALL JFN(datasetCreateMulti)(JNIEnv* e, jobject o, jlong ctx, jlong m, jint f, jint ny) {
+  so_dataset* ds = 0;
+  return so_dataset_create_multi((so_ctx*)(intptr_t)ctx, m, f, ny, &ds) == SO_OK ? (jlong)(intptr_t)ds : 0;
+}
 JNIEXPORT jint JNICALL JFN(datasetRead)(JNIEnv* e, jobject o, jlong ds, jlong b, jlong rows, jdoubleArray x, jdoubleArray y) {
-  double* px = (*e)->GetPrimitiveArrayCritical(e, x, 0);
-  double* py = (*e)->GetPrimitiveArrayCritical(e, y, 0);
+  jdouble* px = (*e)->GetDoubleArrayElements(e, x, 0);
+  jdouble* py = (*e)->GetDoubleArrayElements(e, y, 0);
   int rc = so_dataset_read((so_dataset*)(intptr_t)ds, b, rows, px, py);
-  (*e)->ReleasePrimitiveArrayCritical(e, y, py, 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, x, px, 0);
+  (*e)->ReleaseDoubleArrayElements(e, y, py, 0);
+  (*e)->ReleaseDoubleArrayElements(e, x, px, 0);
   return rc;
 }
 JNIEXPORT jlong JNICALL JFN(datasetSize)(JNIEnv* e, jobject o, jlong ds) {

@@ -12,7 +12,11 @@ object NativeLib {
   @native def shutdown(ctx: Long): Unit
   @native def lastError(ctx: Long): String
   @native def datasetCreate(ctx: Long, m: Long, f: Int): Long
+  /** y has ny outputs per observation, row-major (so_dataset_create_multi; network families only) */
+  @native def datasetCreateMulti(ctx: Long, m: Long, f: Int, ny: Int): Long
   @native def datasetAppend(ds: Long, x: Array[Double], y: Array[Double], rows: Long): Int
+  /** direct ByteBuffers over pinned memory: full PCIe speed, no JVM-side copy, no GC pause */
+  @native def datasetAppendDirect(ds: Long, x: java.nio.ByteBuffer, y: java.nio.ByteBuffer, rows: Long): Int
   @native def datasetGenerate(ds: Long, family: Int, pTrue: Array[Double], seed: Long, sigma: Double, rowOffset: Long): Int
   @native def datasetRead(ds: Long, rowBegin: Long, rows: Long, x: Array[Double], y: Array[Double]): Int
   @native def datasetSize(ds: Long): Long
@@ -31,6 +35,6 @@ object NativeLib {
   @native def datasetLoadRaw(ds: Long, xPath: String, yPath: String, rows: Long, fileRowOffset: Long): Int
 
   val Linear = 0; val LinearNoIntercept = 1; val Logistic = 2; val ExpDecay = 3
-  val Gauss = 4; val GaussExpBkg = 5; val Poly = 6; val MlpMse = 7; val MlpCe = 8
+  val Gauss = 4; val GaussExpBkg = 5; val Poly = 6; val MlpMse = 7; val MlpCe = 8; val SoftMax = 9
   val PdfGaussExpBkg = 0
 }
