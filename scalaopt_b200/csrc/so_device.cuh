@@ -76,6 +76,42 @@ __device__ __forceinline__ double so_exp_fast(double x) {
 // rare path (|x| >= 708, inf, NaN): a real call keeps the ~60 libdevice instructions out of the hot loop body
 static __device__ __noinline__ double exp_slow(double x) { return exp(x); }
 
+// ---- exp of a PRODUCT, argument given in units of ln2/256: so_exps(p, q) = exp(p q ln2/256) ----------------------
+// The kernels' exp arguments are products (rate * t, -(zz * zz)); with the 256/ln2 folded into one factor on the host
+// the product itself never has to be formed: k = round(p q) and r = p q - k both come out of one FMA each, so an
+// exponential costs 8 FP64-pipe instructions INCLUDING its argument (so_exp_fast: 8 + the multiplication that forms
+// x).  r is exact up to one rounding (no ln2 constant in the reduction any more); the polynomial is the same degree-4
+// series in c r, c = ln2/256, with the powers of c folded into the coefficients (c3 rounded to a 32-bit immediate:
+// 1.5e-7 relative on a term <= 4.1e-10, i.e. 6e-17 on the result).  Error vs libm of the exact product: <= 1.5 ulp; the
+// rounding of the scaled factor perturbs the ARGUMENT by <= 1 ulp, as forming x = rate * t did before.
+struct ExpSConsts { double shift, c1, c2, c4, unscale; };
+static __constant__ ExpSConsts kExpS = {
+    6755399441055744.0,        // 1.5 * 2^52
+    0x1.62e42fefa39efp-9,      // c      = ln 2 / 256
+    0x1.ebfbdff82c58fp-19,     // c^2 / 2
+    0x1.3b2ab6fba4e77p-39,     // c^4 / 24
+    0x1.62e42fefa39efp-9,      // scaled argument -> natural argument (slow path)
+};
+#define SO_EXPS_C3 __longlong_as_double(0x3E2C6B0900000000LL)      // c^3 / 6 = 0x1.c6b08d704a0c0p-29 to 32 bits
+constexpr double kExpScale = 0x1.71547652b82fep+8;                 // 256 / ln 2: host-side factor of the scaled arguments
+constexpr double kExpScaleSqrt = 0x1.337cc2183b050p+4;             // its square root (for arguments of the form -(zz)^2)
+constexpr double kExpScaledLimit = 700.0 * 0x1.71547652b82fep+8;   // |p q| below this: so_exps is valid (708 less 1 % margin)
+// valid for |p q| < kExpScaledLimit; the checked kernels test that on the factors (so_scalar.cu: hi_below)
+__device__ __forceinline__ double so_exps(double p, double q) {
+  double kd = fma(p, q, kExpS.shift);
+  const int ki = __double2loint(kd);
+  kd -= kExpS.shift;
+  const double r = fma(p, q, -kd);                                 // |r| <= 1/2 (units of ln2/256)
+  double s = fma(r, kExpS.c4, SO_EXPS_C3);
+  s = fma(s, r, kExpS.c2);
+  s = fma(s, r, kExpS.c1);
+  const double pm1 = s * r;
+  const double Tb = s_exp_tab[ki & (kExpTableSize - 1)];
+  const double T = __hiloint2double(__double2hiint(Tb) + (ki << 12), __double2loint(Tb));
+  return fma(T, pm1, T);
+}
+static __device__ __noinline__ double exps_slow(double p, double q) { return exp(p * q * kExpS.unscale); }
+
 // Variant with a 4096-entry table (32 KB, in dynamic shared memory) and a degree-3 polynomial: 8 FP64-pipe
 // instructions.  |r| <= ln2/8192, truncation error r^4/24 < 3e-18.  Worth its shared memory only where the kernel
 // is FP64-issue-bound (every FP64 instruction costs >= 2 issue cycles and nothing else hides under it).

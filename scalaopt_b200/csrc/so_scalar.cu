@@ -35,19 +35,33 @@ constexpr int kThreads = 256;
 constexpr double kSqrt2 = 1.4142135623730951;
 constexpr double kInvSqrt2 = 0.70710678118654752;
 
+// Range check of the checked kernels, on the FP32 pipe and on values the row has anyway: every exp argument is either
+// -(v^2) or v * const, so "|argument| < 700" is |v| < limit with a per-evaluation limit.  Limits travel as the HIGH WORD
+// of the double (read as a float it orders like the double's magnitude; an inf/NaN v has an inf/NaN high word, which
+// compares false): one FSETP with a free |.| per exponential, no FP64 instruction, no dependence on the exp's own chain.
+inline int hi_word(double v) { long long b; std::memcpy(&b, &v, sizeof b); return (int)(b >> 32); }
+inline int lim_linear(double scaled_rate) { return hi_word(kExpScaledLimit / std::fabs(scaled_rate)); }     // rate 0 -> inf: any finite v passes
+inline int lim_square() { return hi_word(std::sqrt(kExpScaledLimit)); }
+__device__ __forceinline__ bool hi_below(double v, int limit_hi) { return fabsf(__int_as_float(__double2hiint(v))) < __int_as_float(limit_hi); }
+
 // ---------------------------------------------------------------------------------------------------
 // Families.  Pre = per-evaluation constants (kernel parameter space), u = derivative basis.
 // Evaluation is split in two so that the kernel can range-check all exp arguments of a group of rows with
-// one branch and then run the branch-free so_exp_fast on all of them (cross-row ILP on the FP64 pipe):
-//   args(pre, t, a)              -> the NE exp arguments of this row
+// one branch and then run the branch-free exponential on all of them (cross-row ILP on the FP64 pipe):
+//   sargs(pre, t, p, q)          -> the NE exp arguments of this row as PRODUCTS p q in units of ln2/256 (so_exps in
+//                                   so_device.cuh: the 256/ln2 is folded into the per-evaluation constants, the
+//                                   product is never formed: one FP64 instruction less per exponential)
 //   finish(pre, t, ex, f, u)     -> model value and derivative basis from the NE exponentials
+// The Gaussian's argument is -(zz')^2 with zz' = sqrt(256/ln2) z/sqrt2, and zz' is also what the derivative basis is
+// built from (u1 = g zz', u2 = g zz'^2): the powers of sqrt(256/ln2) go into D.
 // ---------------------------------------------------------------------------------------------------
 struct FamExpDecay {   // f = p0 exp(p1 t)                       LevenbergMarquardtSpec.scala:62-63
   static constexpr int N = 2, NE = 1;
   __host__ __device__ static constexpr bool gram_alias(int, int, int&, int&) { return false; }
-  struct Pre { double p0, p1; double D[N]; };
-  static Pre prepare(const double* p) { Pre c; c.p0 = p[0]; c.p1 = p[1]; c.D[0] = 1.0; c.D[1] = p[0]; return c; }
-  __device__ static __forceinline__ void args(const Pre& c, double t, double* a) { a[0] = c.p1 * t; }
+  struct Pre { double p0, p1s; double D[N]; int tlim; };          // p1s = p1 * 256/ln2
+  static Pre prepare(const double* p) { Pre c; c.p0 = p[0]; c.p1s = p[1] * kExpScale; c.D[0] = 1.0; c.D[1] = p[0]; c.tlim = lim_linear(c.p1s); return c; }
+  __device__ static __forceinline__ void sargs(const Pre& c, double t, double* p, double* q) { p[0] = t; q[0] = c.p1s; }
+  __device__ static __forceinline__ bool in_range(const Pre& c, double t, const double*, const double*) { return hi_below(t, c.tlim); }
   __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
     u[0] = ex[0];          // df/dp0 = e
     u[1] = t * ex[0];      // df/dp1 = p0 t e
@@ -70,21 +84,23 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
   static constexpr int N = 3, NE = 1;
   // u1*u1 = (g zz)^2 = g * (g zz^2) = u0*u2: the (1,1) sum is the (0,2) sum, accumulate it once
   __host__ __device__ static constexpr bool gram_alias(int i, int j, int& si, int& sj) { if (i == 1 && j == 1) { si = 0; sj = 2; return true; } return false; }
-  struct Pre { double A, mu, s, sr2, nmsr2; double D[N]; };   // s = 1/sigma, sr2 = s/sqrt(2), nmsr2 = -mu sr2
+  struct Pre { double A, mu, s, sr2, nmsr2; double D[N]; int zlim; };   // s = 1/sigma, sr2 = sqrt(256/ln2) s/sqrt(2), nmsr2 = -mu sr2
   static Pre prepare(const double* p) {
-    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.nmsr2 = -c.mu * c.sr2;
-    c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2; c.D[2] = 2.0 * p[0] * c.s;
+    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2 * kExpScaleSqrt; c.nmsr2 = -c.mu * c.sr2;
+    c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2 / kExpScaleSqrt; c.D[2] = 2.0 * p[0] * c.s / kExpScale;
+    c.zlim = lim_square();
     return c;
   }
-  __device__ static __forceinline__ void args(const Pre& c, double t, double* a) {
-    const double zz = fma(t, c.sr2, c.nmsr2);      // z / sqrt(2),  z = (t - mu)/sigma, one FMA
-    a[0] = -zz * zz;
+  __device__ static __forceinline__ void sargs(const Pre& c, double t, double* p, double* q) {
+    const double zz = fma(t, c.sr2, c.nmsr2);      // zz' = sqrt(256/ln2) z / sqrt(2),  z = (t - mu)/sigma, one FMA
+    p[0] = -zz; q[0] = zz;
   }
+  __device__ static __forceinline__ bool in_range(const Pre& c, double, const double*, const double* q) { return hi_below(q[0], c.zlim); }
   __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
     const double zz = fma(t, c.sr2, c.nmsr2);
     u[0] = ex[0];          // df/dA     = g
-    u[1] = ex[0] * zz;     // df/dmu    = A g z / sigma      = (A s sqrt2) g zz
-    u[2] = u[1] * zz;      // df/dsigma = A g z^2 / sigma    = (2 A s) g zz^2
+    u[1] = ex[0] * zz;     // df/dmu    = A g z / sigma      = (A s sqrt2 / S) g zz',   S = sqrt(256/ln2)
+    u[2] = u[1] * zz;      // df/dsigma = A g z^2 / sigma    = (2 A s / S^2) g zz'^2
     f = c.A * ex[0];
   }
   __device__ static __forceinline__ double residual(const Pre& c, double y, const double* ex, double) { return fma(-c.A, ex[0], y); }
@@ -92,7 +108,7 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
     const double zz = fma(t, c.sr2, c.nmsr2);
     return ex[0] * fma(zz, fma(zz, dd[2], dd[1]), dd[0]);          // g (dd0 + zz dd1 + zz^2 dd2)
   }
-  // B_i += rho * (d2f/dp2 . d)_i in Horner form in v = zz = z/sqrt2 with host-side coefficients (see hprepare):
+  // B_i += rho * (d2f/dp2 . d)_i in Horner form in v = zz' = S z/sqrt2 with host-side coefficients (see hgauss):
   //   h0 = g v (a0 + a1 v),  h1 = g (b0 + v (b1 + v (b2 + v b3))),  h2 = g v (c0 + v (c1 + v (c2 + v c3)))
   struct HGauss { double a0, a1, b0, b1, b2, b3, c0, c1, c2, c3; };
   static HGauss hgauss(const double* p, const double* d) {
@@ -103,6 +119,11 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
     h.b2 = As2 * d[1] * 2.0;         h.b3 = As2 * d[2] * 2.0 * r2;
     h.c0 = -2.0 * As2 * d[1] * r2;   h.c1 = (s * d[0] - 3.0 * As2 * d[2]) * 2.0;
     h.c2 = As2 * d[1] * 2.0 * r2;    h.c3 = As2 * d[2] * 4.0;
+    // the kernels' v is S z/sqrt2: every power of v (incl. the one in "g v") takes a factor 1/S
+    const double iS = 1.0 / kExpScaleSqrt, iL = 1.0 / kExpScale;
+    h.a0 *= iS; h.a1 *= iL;
+    h.b1 *= iS; h.b2 *= iL; h.b3 *= iL * iS;
+    h.c0 *= iS; h.c1 *= iL; h.c2 *= iL * iS; h.c3 *= iL * iL;
     return h;
   }
   __device__ static __forceinline__ void hess_gauss(const HGauss& h, double v, double g, double gv, double rho, double* B) {
@@ -121,17 +142,19 @@ struct FamGauss {      // f = A exp(-(t-mu)^2 / (2 sigma^2)),  p = (A, mu, sigma
 struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),  p = (A, mu, sigma, B, lambda)
   static constexpr int N = 5, NE = 2;   // functional form of stats/example/ExSignalPlusBackgroundFit.scala:78-114
   __host__ __device__ static constexpr bool gram_alias(int i, int j, int& si, int& sj) { if (i == 1 && j == 1) { si = 0; sj = 2; return true; } return false; }
-  struct Pre { double A, mu, s, sr2, nmsr2, B, nlam; double D[N]; };
+  struct Pre { double A, mu, s, sr2, nmsr2, B, nlam; double D[N]; int zlim, tlim; };    // sr2, nmsr2 as in FamGauss; nlam = -lambda 256/ln2
   static Pre prepare(const double* p) {
-    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2; c.nmsr2 = -c.mu * c.sr2; c.B = p[3]; c.nlam = -p[4];
-    c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2; c.D[2] = 2.0 * p[0] * c.s; c.D[3] = 1.0; c.D[4] = -p[3];
+    Pre c; c.A = p[0]; c.mu = p[1]; c.s = 1.0 / p[2]; c.sr2 = c.s * kInvSqrt2 * kExpScaleSqrt; c.nmsr2 = -c.mu * c.sr2; c.B = p[3]; c.nlam = -p[4] * kExpScale;
+    c.D[0] = 1.0; c.D[1] = p[0] * c.s * kSqrt2 / kExpScaleSqrt; c.D[2] = 2.0 * p[0] * c.s / kExpScale; c.D[3] = 1.0; c.D[4] = -p[3];
+    c.zlim = lim_square(); c.tlim = lim_linear(c.nlam);
     return c;
   }
-  __device__ static __forceinline__ void args(const Pre& c, double t, double* a) {
+  __device__ static __forceinline__ void sargs(const Pre& c, double t, double* p, double* q) {
     const double zz = fma(t, c.sr2, c.nmsr2);
-    a[0] = -zz * zz;
-    a[1] = c.nlam * t;
+    p[0] = -zz; q[0] = zz;
+    p[1] = t; q[1] = c.nlam;
   }
+  __device__ static __forceinline__ bool in_range(const Pre& c, double t, const double*, const double* q) { return hi_below(q[0], c.zlim) && hi_below(t, c.tlim); }
   __device__ static __forceinline__ void finish(const Pre& c, double t, const double* ex, double& f, double (&u)[N]) {
     const double zz = fma(t, c.sr2, c.nmsr2);
     u[0] = ex[0];
@@ -151,11 +174,11 @@ struct FamGaussExpBkg {  // f = A exp(-(t-mu)^2/(2 sigma^2)) + B exp(-lambda t),
     return fma(ex[0], h1, ex[1] * h2);                             // g (dd0 + zz dd1 + zz^2 dd2) + e (dd3 + t dd4): 5 instead of 3 + 5
   }
   // true when both exp arguments stay inside (-700, 700) for every t in [tmin, tmax] (they are monotone or convex in t,
-  // so the end points decide); NaN anywhere compares false.  708 is the limit of so_exp_fast: 1 % of margin for rounding.
+  // so the end points decide); NaN anywhere compares false.  708 is the limit of so_exps: 1 % of margin for rounding.
   static bool args_in_range(const Pre& c, double tmin, double tmax) {
     const double z0 = std::fabs(tmin * c.sr2 + c.nmsr2), z1 = std::fabs(tmax * c.sr2 + c.nmsr2);
     const double zm = z0 > z1 ? z0 : z1, tm = std::fabs(tmin) > std::fabs(tmax) ? std::fabs(tmin) : std::fabs(tmax);
-    return zm * zm < 700.0 && std::fabs(c.nlam) * tm < 700.0;
+    return zm * zm < kExpScaledLimit && std::fabs(c.nlam) * tm < kExpScaledLimit;
   }
   // Gaussian part as in FamGauss; exponential part: h3 = -t e d4, h4 = -t e d3 + B t^2 e d4
   struct HPre { FamGauss::HGauss g; double nd4, nd3, Bd4; };
@@ -180,7 +203,8 @@ struct FamPoly {       // f = sum_k p_k t^k
   }
   struct Pre { double p[N]; double D[N]; };
   static Pre prepare(const double* p) { Pre c; for (int k = 0; k < N; ++k) { c.p[k] = p[k]; c.D[k] = 1.0; } return c; }
-  __device__ static __forceinline__ void args(const Pre&, double, double*) {}
+  __device__ static __forceinline__ void sargs(const Pre&, double, double*, double*) {}
+  __device__ static __forceinline__ bool in_range(const Pre&, double, const double*, const double*) { return true; }
   __device__ static __forceinline__ void finish(const Pre& c, double t, const double*, double& f, double (&u)[N]) {
     u[0] = 1.0;
     double s = c.p[0];
@@ -203,7 +227,8 @@ struct OpLossGrad {
   static constexpr bool kHasSrc = false;
   static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre; double scale[Q]; };
-  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void sargs(const Args& a, double t, double* p, double* q) { Fam::sargs(a.pre, t, p, q); }
+  __device__ static __forceinline__ bool in_range(const Args& a, double t, const double* p, const double* q) { return Fam::in_range(a.pre, t, p, q); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
     Fam::finish(a.pre, t, ex, f, u);
@@ -223,7 +248,8 @@ struct OpNormalEq {
   static constexpr bool kHasSrc = true;
   static constexpr bool kNeedsY = true;
   __host__ __device__ static constexpr int packed(int i, int j) { return i * N - i * (i - 1) / 2 + (j - i); }
-  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void sargs(const Args& a, double t, double* p, double* q) { Fam::sargs(a.pre, t, p, q); }
+  __device__ static __forceinline__ bool in_range(const Args& a, double t, const double* p, const double* q) { return Fam::in_range(a.pre, t, p, q); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
     Fam::finish(a.pre, t, ex, f, u);
@@ -249,9 +275,15 @@ struct OpLine {
   static constexpr bool kHasSrc = false;
   static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre[KB]; double dd[KB][N]; double scale[Q]; };   // dd = D(p + alpha d) o d
-  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) {
+  __device__ static __forceinline__ void sargs(const Args& a, double t, double* p, double* q) {
 #pragma unroll
-    for (int k = 0; k < KB; ++k) Fam::args(a.pre[k], t, ea + k * Fam::NE);
+    for (int k = 0; k < KB; ++k) Fam::sargs(a.pre[k], t, p + k * Fam::NE, q + k * Fam::NE);
+  }
+  __device__ static __forceinline__ bool in_range(const Args& a, double t, const double* p, const double* q) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) ok = ok && Fam::in_range(a.pre[k], t, p + k * Fam::NE, q + k * Fam::NE);
+    return ok;
   }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
 #pragma unroll
@@ -283,7 +315,8 @@ struct OpHessVec {
   static constexpr bool kHasSrc = false;
   static constexpr bool kNeedsY = true;
   struct Args { typename Fam::Pre pre; typename Fam::HPre h; double dd[N]; double scale[N]; double scale2[N]; };
-  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void sargs(const Args& a, double t, double* p, double* q) { Fam::sargs(a.pre, t, p, q); }
+  __device__ static __forceinline__ bool in_range(const Args& a, double t, const double* p, const double* q) { return Fam::in_range(a.pre, t, p, q); }
   __device__ static __forceinline__ void accum(const Args& a, double t, double y, const double* ex, double (&acc)[Q]) {
     double f, u[N];
     Fam::finish(a.pre, t, ex, f, u);
@@ -307,28 +340,30 @@ struct OpHessVec {
 // ---------------------------------------------------------------------------------------------------
 struct PdfGaussExpBkg {
   static constexpr int NE = 2;
-  struct Pre { double sr2, nmsr2, nlam, lamx, cS, cB; };
+  struct Pre { double sr2, nmsr2, nlam, xmin, cS, cB; int zlim, xlim; };   // sr2, nmsr2, nlam scaled as in FamGaussExpBkg
   static Pre prepare(const double* p, const double* consts) {
     Pre c;
     const double fSig = p[0], mu = p[1], sigma = p[2], lambda = p[3], xMin = consts[0];
     const double s = 1.0 / sigma;
-    c.sr2 = s * kInvSqrt2; c.nmsr2 = -mu * c.sr2;
-    c.nlam = -lambda; c.lamx = lambda * xMin;
+    c.sr2 = s * kInvSqrt2 * kExpScaleSqrt; c.nmsr2 = -mu * c.sr2;
+    c.nlam = -lambda * kExpScale; c.xmin = xMin;
+    c.zlim = lim_square(); c.xlim = lim_linear(c.nlam);
     c.cS = fSig * s * 0.3989422804014327;        // fSig / (sqrt(2 pi) sigma)
     c.cB = (1.0 - fSig) * lambda;
     return c;
   }
-  __device__ static __forceinline__ void args(const Pre& c, double x, double* a) {
+  __device__ static __forceinline__ void sargs(const Pre& c, double x, double* p, double* q) {
     const double zz = fma(x, c.sr2, c.nmsr2);
-    a[0] = -zz * zz;                             // -z^2/2
-    a[1] = fma(x, c.nlam, c.lamx);               // -lambda (x - xMin)
+    p[0] = -zz; q[0] = zz;                       // -z^2/2
+    p[1] = x - c.xmin; q[1] = c.nlam;            // -lambda (x - xMin)
   }
+  __device__ static __forceinline__ bool in_range(const Pre& c, double, const double* p, const double* q) { return hi_below(q[0], c.zlim) && hi_below(p[1], c.xlim); }
   __device__ static __forceinline__ double value(const Pre& c, const double* ex) { return fma(c.cS, ex[0], c.cB * ex[1]); }
   // both exp arguments inside (-700, 700) for every x in [xmin, xmax] (end points decide); NaN compares false
   static bool args_in_range(const Pre& c, double xmin, double xmax) {
     const double z0 = std::fabs(xmin * c.sr2 + c.nmsr2), z1 = std::fabs(xmax * c.sr2 + c.nmsr2), zm = z0 > z1 ? z0 : z1;
-    const double b0 = std::fabs(xmin * c.nlam + c.lamx), b1 = std::fabs(xmax * c.nlam + c.lamx);
-    return zm * zm < 700.0 && b0 < 700.0 && b1 < 700.0;
+    const double b0 = std::fabs((xmin - c.xmin) * c.nlam), b1 = std::fabs((xmax - c.xmin) * c.nlam);
+    return zm * zm < kExpScaledLimit && b0 < kExpScaledLimit && b1 < kExpScaledLimit;
   }
 };
 
@@ -340,7 +375,8 @@ struct OpNll {
   static constexpr bool kHasSrc = false, kNeedsY = false;
   struct Args { typename Pdf::Pre pre; double scale[Q]; };
   __device__ static __forceinline__ void init(double (&acc)[Q]) { acc[0] = 1.0; acc[1] = 0.0; acc[2] = 0.0; }
-  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Pdf::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void sargs(const Args& a, double t, double* p, double* q) { Pdf::sargs(a.pre, t, p, q); }
+  __device__ static __forceinline__ bool in_range(const Args& a, double t, const double* p, const double* q) { return Pdf::in_range(a.pre, t, p, q); }
   __device__ static __forceinline__ void accum(const Args& a, double, double, const double* ex, double (&acc)[Q]) {
     const double v = Pdf::value(a.pre, ex);
     const int hi = __double2hiint(v);
@@ -382,7 +418,8 @@ struct OpQr {
   static constexpr int N = Fam::N, C = N + 1, Q = C * (C + 1) / 2, NEXP = Fam::NE, G = C <= 6 ? 8 : 4;   // rows per fold
   struct Args { typename Fam::Pre pre; double scale[C]; };
   static constexpr bool kHasSrc = false, kNeedsY = true, kGroupFold = true;
-  __device__ static __forceinline__ void args(const Args& a, double t, double* ea) { Fam::args(a.pre, t, ea); }
+  __device__ static __forceinline__ void sargs(const Args& a, double t, double* p, double* q) { Fam::sargs(a.pre, t, p, q); }
+  __device__ static __forceinline__ bool in_range(const Args& a, double t, const double* p, const double* q) { return Fam::in_range(a.pre, t, p, q); }
   __device__ static __forceinline__ void row(const Args& a, double t, double y, const double* ex, double (&r)[C]) {
     double f, u[N];
     Fam::finish(a.pre, t, ex, f, u);
@@ -415,26 +452,23 @@ __device__ __forceinline__ void process_rows(const typename Op::Args& args, cons
       for (int r = 0; r < G; ++r) Op::accum(args, t[r], y[r], nullptr, acc);
     }
   } else {
-    double ea[G][NE];
+    double ea[G][NE], pp[G][NE], qq[G][NE];
     bool ok = true;
 #pragma unroll
     for (int r = 0; r < G; ++r) {
-      Op::args(args, t[r], ea[r]);
-      if (CHECK) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) ok = ok && exp_in_range(ea[r][e]);
-      }
+      Op::sargs(args, t[r], pp[r], qq[r]);
+      if (CHECK) ok = ok && Op::in_range(args, t[r], pp[r], qq[r]);
     }
     if (!CHECK || ok) {
 #pragma unroll
       for (int r = 0; r < G; ++r)
 #pragma unroll
-        for (int e = 0; e < NE; ++e) ea[r][e] = BIG ? so_exp_fast_big(ea[r][e], big_tab) : so_exp_fast(ea[r][e]);
-    } else {      // some |arg| >= 708, inf or NaN in this group: full-range libdevice exp for the whole group
+        for (int e = 0; e < NE; ++e) ea[r][e] = so_exps(pp[r][e], qq[r][e]);
+    } else {      // some |arg| >= 700, inf or NaN in this group: full-range libdevice exp for the whole group
 #pragma unroll
       for (int r = 0; r < G; ++r)
 #pragma unroll
-        for (int e = 0; e < NE; ++e) ea[r][e] = exp_slow(ea[r][e]);
+        for (int e = 0; e < NE; ++e) ea[r][e] = exps_slow(pp[r][e], qq[r][e]);
     }
     if constexpr (requires { Op::kGroupFold; }) Op::template accum_group<G>(args, t, y, &ea[0][0], acc);
     else {
@@ -556,7 +590,7 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
     // the generic proxy; the two must be ordered, and a block barrier alone does not do that: LDS instructions may still
     // be in flight when their warp passes BAR.SYNC.  (Seen for real: a variant of this kernel whose accumulators lived in
     // local memory returned run-to-run different sums at 1e9 rows with the barrier right after the loads; with the
-    // proxy fence it was reproducible again.  tools/k2_ab.sh, gpurun_out/ab3.log.)
+    // proxy fence it was reproducible again.  tools/k2_ab.sh, profiles/r1_k2_ab_release_modes.log.)
     //   MODE 0 (default): process the rows, then fence.proxy.async + __syncthreads, then thread 0 refills the stage:
     //           the loads have long completed (their values were consumed), so the fence costs nothing.
     //   MODE 1: as MODE 0 with an `empty` mbarrier instead of the block barrier: only thread 0 waits for the other warps.
