@@ -848,7 +848,8 @@ extern "C" int so_dataset_create_multi(so_ctx* ctx, int64_t m, int f, int ny, so
     sm.cap = cnt;
     if (sm.cap > 0) {
       cudaError_t ce = cudaSetDevice(ctx->devs[g].id);
-      if (ce == cudaSuccess) ce = cudaMalloc(&sm.X, sizeof(double) * (size_t)sm.cap * f);
+      // + 16 bytes: the odd-f kernels stream rows as aligned 16-byte units and may touch one element past the last row
+      if (ce == cudaSuccess) ce = cudaMalloc(&sm.X, sizeof(double) * ((size_t)sm.cap * f + 2));
       if (ce == cudaSuccess) ce = cudaMalloc(&sm.y, sizeof(double) * (size_t)sm.cap * ny);
       if (ce != cudaSuccess) {
         int rc = fail(ctx, ce == cudaErrorMemoryAllocation ? SO_ENOMEM : SO_ECUDA,

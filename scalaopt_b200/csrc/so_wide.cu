@@ -14,26 +14,33 @@ namespace {
 
 enum { kModeLossGrad = 0, kModeHessVec = 1 };
 
-template <int FAM, int MODE, int L, int C, int V, bool PF>
+// ODD: f odd streamed as (f + 1)/2 aligned 16-byte units per row, see so_wide.cuh.  The two row parities hold a column in
+// different registers; they meet in the block reduction.
+template <int FAM, int MODE, int L, int C, int V, bool PF, bool ODD = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
        int want_grad, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   extern __shared__ double smem[];
   constexpr int RW = 32 / L, CV = C * V;
+  static_assert(!ODD || V == 2, "ODD streams 16-byte units");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & (L - 1), r = lane / L;
   const int f = P.f, icpt = P.icpt;
   const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
   if (FAM == kLogistic) { exp_table_init(); log_table_init(); __syncthreads(); }
+  // parity of every row this lane will ever hold (0: the row starts 16-byte aligned)
+  const int odd = ODD ? lane_row_parity<L>(X, warp, r) : 0;
+  const double* Xs = X - odd;
 
   double pj[CV], dj[CV], g[CV];
 #pragma unroll
   for (int c = 0; c < C; ++c)
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const int col = (c * L + q) * V + v;
-      pj[c * V + v] = (col < f) ? P.p[icpt + col] : 0.0;
-      dj[c * V + v] = (MODE == kModeHessVec && col < f) ? P.d[icpt + col] : 0.0;
+      const int col = (c * L + q) * V + v - odd;
+      const bool live = col >= 0 && col < f;
+      pj[c * V + v] = live ? P.p[icpt + col] : 0.0;
+      dj[c * V + v] = (MODE == kModeHessVec && live) ? P.d[icpt + col] : 0.0;
       g[c * V + v] = 0.0;
     }
   const double p0 = icpt ? P.p[0] : 0.0, d0 = (icpt && MODE == kModeHessVec) ? P.d[0] : 0.0;
@@ -84,7 +91,7 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
     if (grp < ngroups) {
       const int64_t row = grp * RW + r;
       vcur = row < rows;
-      load_frag<L, C, V>(cur, X, row, vcur, f, q);
+      load_row<L, C, V, ODD>(cur, Xs, row, rows, vcur, f, q, odd);
       ycur = vcur ? ld_stream(y + row) : 0.0;
     }
     while (grp < ngroups) {
@@ -92,7 +99,7 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
       if (ng < ngroups) {
         const int64_t row = ng * RW + r;
         vnxt = row < rows;
-        load_frag<L, C, V>(nxt, X, row, vnxt, f, q);
+        load_row<L, C, V, ODD>(nxt, Xs, row, rows, vnxt, f, q, odd);
         ynxt = vnxt ? ld_stream(y + row) : 0.0;
       }
       step(cur, ycur, vcur);
@@ -104,7 +111,7 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
       Frag<C, V> cur;
       const int64_t row = grp * RW + r;
       const bool valid = row < rows;
-      load_frag<L, C, V>(cur, X, row, valid, f, q);
+      load_row<L, C, V, ODD>(cur, Xs, row, rows, valid, f, q, odd);
       const double yv = valid ? ld_stream(y + row) : 0.0;
       step(cur, yv, valid);
     }
@@ -114,186 +121,41 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
   double* wsum = smem;                 // [kWarps][Q]
   double* vals = smem + kWarps * Q;    // [Q]
   const int base = (MODE == kModeLossGrad) ? 1 : 0;
+  if constexpr (!ODD) {
 #pragma unroll
-  for (int c = 0; c < C; ++c)
+    for (int c = 0; c < C; ++c)
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const double s = col_sum<L>(g[c * V + v]);
-      const int col = (c * L + q) * V + v;
-      if (r == 0 && col < f) wsum[warp * Q + base + icpt + col] = s;
-    }
-  {
-    const double s0 = col_sum<L>(g0), sl = col_sum<L>(loss);
-    if (lane == 0) {
-      if (MODE == kModeLossGrad) wsum[warp * Q] = sl;
-      if (icpt) wsum[warp * Q + base] = s0;
-    }
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < Q; j += kThreads) {
-    double s = 0.0;
-    for (int w2 = 0; w2 < kWarps; ++w2) s += wsum[w2 * Q + j];
-    vals[j] = s;
-  }
-  __syncthreads();
-  finish_grid(vals, Q, (MODE == kModeLossGrad) ? 1 : 0, P.scale0, partials, out, ticket);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Odd f.  A row of an odd number of doubles starts 16-byte aligned only every other row, so the mapping above falls
-// back to 64-bit loads (V = 1) and loses a third of the bandwidth (cfg5 as specified has f = n - 1 = 31 and 127: 0.58 and
-// 0.62 of HBM in round 1).  TWO consecutive rows, however, are 2f doubles that do start aligned: this kernel streams row
-// PAIRS with 128-bit loads exactly like k_wide<V = 2> streams rows of 2f inputs, and every register element knows which
-// of the two rows it belongs to: two dot products (weights zero on the other row's elements), two link evaluations, and
-// the rank-1 update takes the residual of the element's own row.  The two halves of the accumulators meet in the block
-// reduction.  A trailing unpaired row is loaded element-wise.
-// ---------------------------------------------------------------------------------------------------
-template <int C>
-struct PairFrag { double x[C * 2]; };
-
-template <int L, int C>
-__device__ __forceinline__ void load_pair(PairFrag<C>& fr, const double* __restrict__ X, int64_t pair, bool va, bool vb, int f, int q) {
-  const double* base = X + pair * 2 * f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const int e = (c * L + q) * 2;                  // element index inside the pair: [0, f) row A, [f, 2f) row B
-    double2 v = make_double2(0.0, 0.0);
-    if (va && (e + 1 < f || (vb && e + 1 < 2 * f))) v = ld_stream2(reinterpret_cast<const double2*>(base + e));
-    else if (va && e < f) v.x = ld_stream(base + e);            // last element of a trailing unpaired row A
-    fr.x[c * 2] = v.x;
-    fr.x[c * 2 + 1] = v.y;
-  }
-}
-
-template <int FAM, int MODE, int L, int C>
-__global__ void __launch_bounds__(kThreads, 2)
-k_wide_pair(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
-            int want_grad, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  extern __shared__ double smem[];
-  constexpr int RW = 32 / L, CV = C * 2;
-  constexpr bool PF = C <= 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = lane & (L - 1), r = lane / L;
-  const int f = P.f, icpt = P.icpt;
-  const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
-  if (FAM == kLogistic) { exp_table_init(); log_table_init(); __syncthreads(); }
-
-  // one weight per register element (that of the element's own row) and one bit saying which row that is
-  double pw[CV], dw[CV], g[CV];
-  unsigned isb = 0;
-#pragma unroll
-  for (int c = 0; c < C; ++c)
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int e = (c * L + q) * 2 + v, i = c * 2 + v;
-      if (e >= f) isb |= 1u << i;
-      const int col = e >= f ? e - f : e;
-      const bool live = e < 2 * f;
-      pw[i] = live ? P.p[icpt + col] : 0.0;
-      dw[i] = (MODE == kModeHessVec && live) ? P.d[icpt + col] : 0.0;
-      g[i] = 0.0;
-    }
-  const double p0 = icpt ? P.p[0] : 0.0, d0 = (icpt && MODE == kModeHessVec) ? P.d[0] : 0.0;
-  double g0 = 0.0, loss = 0.0;
-
-  const int64_t npairs = (rows + 1) / 2;
-  const int64_t ngroups = (npairs + RW - 1) / RW;
-  const int64_t gstr = (int64_t)gridDim.x * kWarps;
-
-  auto dots = [&](const double (&w)[CV], const PairFrag<C>& fr, double& sa, double& sb) {
-    sa = 0.0; sb = 0.0;
-#pragma unroll
-    for (int i = 0; i < CV; ++i) { if (isb >> i & 1u) sb = fma(w[i], fr.x[i], sb); else sa = fma(w[i], fr.x[i], sa); }
-    sa = row_sum<L>(sa); sb = row_sum<L>(sb);
-  };
-  auto step = [&](const PairFrag<C>& fr, double ya, double yb, bool va, bool vb) {
-    double wa, wb;
-    if (MODE == kModeLossGrad) {
-      double za, zb;
-      dots(pw, fr, za, zb);
-      double la, lb;
-      link<FAM>(za + p0, ya, la, wa);
-      link<FAM>(zb + p0, yb, lb, wb);
-      if (!va) { wa = 0.0; la = 0.0; }
-      if (!vb) { wb = 0.0; lb = 0.0; }
-      if (q == 0) { loss += la + lb; g0 += wa + wb; }
-      if (!want_grad) return;
-    } else {
-      double dva, dvb;
-      dots(dw, fr, dva, dvb);
-      dva += d0; dvb += d0;
-      if (FAM == kLogistic) {
-        double za, zb;
-        dots(pw, fr, za, zb);
-        wa = curvature<FAM>(za + p0) * dva;
-        wb = curvature<FAM>(zb + p0) * dvb;
-      } else {
-        wa = dva; wb = dvb;
+      for (int v = 0; v < V; ++v) {
+        const double s = col_sum<L>(g[c * V + v]);
+        const int col = (c * L + q) * V + v;
+        if (r == 0 && col < f) wsum[warp * Q + base + icpt + col] = s;
       }
-      if (!va) wa = 0.0;
-      if (!vb) wb = 0.0;
-      if (q == 0) g0 += wa + wb;
-    }
-#pragma unroll
-    for (int i = 0; i < CV; ++i) g[i] = fma((isb >> i & 1u) ? wb : wa, fr.x[i], g[i]);
-  };
-
-  if (PF) {      // software pipeline as in k_wide: the next group's loads are in flight while this one is reduced
-    PairFrag<C> cur, nxt;
-    double yac = 0.0, ybc = 0.0, yan = 0.0, ybn = 0.0;
-    bool vac = false, vbc = false, van = false, vbn = false;
-    int64_t grp = (int64_t)blockIdx.x * kWarps + warp;
-    if (grp < ngroups) {
-      const int64_t pair = grp * RW + r;
-      vac = 2 * pair < rows; vbc = 2 * pair + 1 < rows;
-      load_pair<L, C>(cur, X, pair, vac, vbc, f, q);
-      yac = vac ? ld_stream(y + 2 * pair) : 0.0; ybc = vbc ? ld_stream(y + 2 * pair + 1) : 0.0;
-    }
-    while (grp < ngroups) {
-      const int64_t ng = grp + gstr;
-      if (ng < ngroups) {
-        const int64_t pair = ng * RW + r;
-        van = 2 * pair < rows; vbn = 2 * pair + 1 < rows;
-        load_pair<L, C>(nxt, X, pair, van, vbn, f, q);
-        yan = van ? ld_stream(y + 2 * pair) : 0.0; ybn = vbn ? ld_stream(y + 2 * pair + 1) : 0.0;
-      }
-      step(cur, yac, ybc, vac, vbc);
-      cur = nxt; yac = yan; ybc = ybn; vac = van; vbc = vbn;
-      grp = ng;
-    }
   } else {
-    for (int64_t grp = (int64_t)blockIdx.x * kWarps + warp; grp < ngroups; grp += gstr) {
-      PairFrag<C> cur;
-      const int64_t pair = grp * RW + r;
-      const bool va = 2 * pair < rows, vb = 2 * pair + 1 < rows;
-      load_pair<L, C>(cur, X, pair, va, vb, f, q);
-      const double ya = va ? ld_stream(y + 2 * pair) : 0.0, yb = vb ? ld_stream(y + 2 * pair + 1) : 0.0;
-      step(cur, ya, yb, va, vb);
+    // rows of equal parity first (the butterfly skips the lowest row bit), then the r = 0 lanes store their columns and
+    // the r = 1 lanes (other parity, columns one register further) add theirs; one row per warp: a single parity, stored
+    double cs[CV];
+#pragma unroll
+    for (int i = 0; i < CV; ++i) {
+      double s = g[i];
+#pragma unroll
+      for (int o = 2 * L; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      cs[i] = s;
+    }
+#pragma unroll
+    for (int pass = 0; pass < (RW == 1 ? 1 : 2); ++pass) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int col = (c * L + q) * V + v - odd;
+          if (r == pass && col >= 0 && col < f) {
+            double* dst = &wsum[warp * Q + base + icpt + col];
+            *dst = pass ? *dst + cs[c * V + v] : cs[c * V + v];
+          }
+        }
+      __syncwarp();
     }
   }
-
-  // ---- block reduction in warp order; the two rows' halves of a parameter are added one after the other ----
-  double* wsum = smem;                 // [kWarps][Q]
-  double* vals = smem + kWarps * Q;    // [Q]
-  const int base = (MODE == kModeLossGrad) ? 1 : 0;
-  double cs[CV];
-#pragma unroll
-  for (int i = 0; i < CV; ++i) cs[i] = col_sum<L>(g[i]);
-#pragma unroll
-  for (int c = 0; c < C; ++c)
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int e = (c * L + q) * 2 + v;
-      if (r == 0 && e < f) wsum[warp * Q + base + icpt + e] = cs[c * 2 + v];
-    }
-  __syncwarp();
-#pragma unroll
-  for (int c = 0; c < C; ++c)
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int e = (c * L + q) * 2 + v;
-      if (r == 0 && e >= f && e < 2 * f) wsum[warp * Q + base + icpt + e - f] += cs[c * 2 + v];
-    }
   {
     const double s0 = col_sum<L>(g0), sl = col_sum<L>(loss);
     if (lane == 0) {
@@ -311,27 +173,10 @@ k_wide_pair(const double* __restrict__ X, const double* __restrict__ y, int64_t 
   finish_grid(vals, Q, (MODE == kModeLossGrad) ? 1 : 0, P.scale0, partials, out, ticket);
 }
 
-template <int FAM, int MODE, int L, int C>
-int launch_pair_lc(const Shard& s, const Params& P, int want_grad) {
-  auto kern = k_wide_pair<FAM, MODE, L, C>;
-  const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
-  const size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
-  if (per_sm < 1) per_sm = 1;
-  constexpr int RW = 32 / L;
-  const int64_t ngroups = ((s.rows + 1) / 2 + RW - 1) / RW;
-  const int64_t want = std::max<int64_t>(1, (ngroups + kWarps - 1) / kWarps);
-  const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * s.sm_count);
-  if ((size_t)grid * Q > s.partials_doubles || (size_t)Q > s.out_doubles) return SO_ENOMEM;
-  kern<<<grid, kThreads, smem, s.stream>>>(s.X, s.y, s.rows, P, want_grad, s.partials, s.out, s.ticket);
-  return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
-}
-
-template <int FAM, int MODE, int L, int C, int V>
+template <int FAM, int MODE, int L, int C, int V, bool ODD = false>
 int launch_lcv(const Shard& s, const Params& P, int want_grad) {
   constexpr bool PF = (C <= 4);
-  auto kern = k_wide<FAM, MODE, L, C, V, PF>;
+  auto kern = k_wide<FAM, MODE, L, C, V, PF, ODD>;
   const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
   const size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
   int per_sm = 1;
@@ -422,11 +267,11 @@ int launch_small(const Shard& s, const Params& P, int want_grad) {
 
 template <int FAM, int MODE>
 int launch_mapped(const Shard& s, const Params& P, int want_grad) {
-  if ((P.f & 1) && P.f >= 9 && reinterpret_cast<uintptr_t>(s.X) % 16 == 0) {      // odd f: row pairs with 128-bit loads
-    const Mapping mp = choose_mapping(2 * P.f);
-#define SO_PAIR(LL, CC) if (mp.L == LL && mp.C == CC) return launch_pair_lc<FAM, MODE, LL, CC>(s, P, want_grad);
-    SO_PAIR(4, 4) SO_PAIR(8, 4) SO_PAIR(16, 4) SO_PAIR(32, 4) SO_PAIR(32, 8) SO_PAIR(32, 16)
-#undef SO_PAIR
+  if ((P.f & 1) && P.f >= 9) {      // odd f: rows as (f + 1)/2 aligned 16-byte units (k_wide ODD)
+    const Mapping mo = choose_mapping(P.f + 1);
+#define SO_ODD(LL, CC) if (mo.L == LL && mo.C == CC && mo.V == 2) return launch_lcv<FAM, MODE, LL, CC, 2, true>(s, P, want_grad);
+    SO_ODD(2, 4) SO_ODD(4, 4) SO_ODD(8, 4) SO_ODD(16, 4) SO_ODD(32, 4) SO_ODD(32, 8)
+#undef SO_ODD
   }
   const Mapping m = choose_mapping(P.f);
 #define SO_CASE(LL, CC, VV) if (m.L == LL && m.C == CC && m.V == VV) return launch_lcv<FAM, MODE, LL, CC, VV>(s, P, want_grad);

@@ -92,6 +92,35 @@ __device__ __forceinline__ void load_frag(Frag<C, V>& fr, const double* __restri
   }
 }
 
+// ---- odd f (k_wide / k_wide_line with ODD = true, V = 2) --------------------------------------------------------------
+// A row of an odd number of doubles starts 16-byte aligned only every other row, and with 64-bit loads (V = 1) the mapping
+// loses a third of the bandwidth (cfg5 as specified has f = n - 1 = 31 and 127: 0.58 and 0.62 of HBM in round 1).  But
+// every row is COVERED by (f + 1)/2 aligned 16-byte units: a row that starts aligned ends with one foreign element (the
+// first of the next row), a row that does not starts with one (the last of the previous row).  So a lane streams its row
+// as f + 1 elements from the aligned address `row f - odd`, and its weights are shifted by `odd` with a zero on the
+// foreign element.  The parity of a lane's rows never changes — rows per warp step and the group stride are even (or,
+// with one row per warp, the warp index decides) — so the trick costs a pointer offset: the loop is instruction for
+// instruction the even-f one.  The foreign element is data of the same data set (finite whenever the result is), except
+// before the FIRST and after the LAST row of the shard, where it is zeroed in registers (a view's neighbours are not its
+// data; X carries 16 bytes of slack for the load behind the last row, so_api.cu).
+template <int L>
+__device__ __forceinline__ int lane_row_parity(const double* X, int warp, int r) {     // 0: this lane's rows start 16-byte aligned
+  return (((32 / L == 1) ? warp : r) + (int)((reinterpret_cast<uintptr_t>(X) >> 3) & 1)) & 1;
+}
+// Xs = X - odd
+template <int L, int C, int V, bool ODD>
+__device__ __forceinline__ void load_row(Frag<C, V>& fr, const double* __restrict__ Xs, int64_t row, int64_t rows, bool valid,
+                                         int f, int q, int odd) {
+  load_frag<L, C, V>(fr, Xs, row, valid, f, q);
+  if (ODD && ((row == rows - 1 && !odd) || (row == 0 && odd))) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (!odd && (c * L + q) * V + 1 == f) fr.x[c * V + 1] = 0.0;
+      if (odd && c == 0 && q == 0) fr.x[0] = 0.0;
+    }
+  }
+}
+
 // After the row loop: block-level sums in warp order, per-block partials, last block adds in block order.
 // vals[Q] in shared memory holds this block's sums; out[0 .. nscaled) is scaled by scale0.
 __device__ __forceinline__ void finish_grid(const double* vals, int Q, int nscaled, double scale0,

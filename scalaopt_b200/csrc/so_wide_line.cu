@@ -11,7 +11,7 @@ namespace so {
 namespace wide {
 namespace {
 
-template <int FAM, int L, int C, int V, int KPL, bool PF>
+template <int FAM, int L, int C, int V, int KPL, bool PF, bool ODD = false>      // ODD: odd f as aligned 16-byte units (so_wide.cuh)
 __global__ void __launch_bounds__(kThreads, 2)
 k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
             double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
@@ -22,15 +22,19 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
   const int f = P.f, icpt = P.icpt, k = P.k;
   const int Q = 2 * k;
   if (FAM == kLogistic) { exp_table_init(); log_table_init(); __syncthreads(); }
+  static_assert(!ODD || V == 2, "ODD streams 16-byte units");
+  const int odd = ODD ? lane_row_parity<L>(X, warp, r) : 0;
+  const double* Xs = X - odd;
 
   double pj[CV], dj[CV];
 #pragma unroll
   for (int c = 0; c < C; ++c)
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const int col = (c * L + q) * V + v;
-      pj[c * V + v] = (col < f) ? P.p[icpt + col] : 0.0;
-      dj[c * V + v] = (col < f) ? P.d[icpt + col] : 0.0;
+      const int col = (c * L + q) * V + v - odd;
+      const bool live = col >= 0 && col < f;
+      pj[c * V + v] = live ? P.p[icpt + col] : 0.0;
+      dj[c * V + v] = live ? P.d[icpt + col] : 0.0;
     }
   const double p0 = icpt ? P.p[0] : 0.0, d0 = icpt ? P.d[0] : 0.0;
   double al[KPL], phi[KPL], dphi[KPL];
@@ -68,7 +72,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
     if (grp < ngroups) {
       const int64_t row = grp * RW + r;
       vcur = row < rows;
-      load_frag<L, C, V>(cur, X, row, vcur, f, q);
+      load_row<L, C, V, ODD>(cur, Xs, row, rows, vcur, f, q, odd);
       ycur = vcur ? ld_stream(y + row) : 0.0;
     }
     while (grp < ngroups) {
@@ -76,7 +80,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
       if (ng < ngroups) {
         const int64_t row = ng * RW + r;
         vnxt = row < rows;
-        load_frag<L, C, V>(nxt, X, row, vnxt, f, q);
+        load_row<L, C, V, ODD>(nxt, Xs, row, rows, vnxt, f, q, odd);
         ynxt = vnxt ? ld_stream(y + row) : 0.0;
       }
       step(cur, ycur, vcur);
@@ -88,7 +92,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
       Frag<C, V> cur;
       const int64_t row = grp * RW + r;
       const bool valid = row < rows;
-      load_frag<L, C, V>(cur, X, row, valid, f, q);
+      load_row<L, C, V, ODD>(cur, Xs, row, rows, valid, f, q, odd);
       const double yv = valid ? ld_stream(y + row) : 0.0;
       step(cur, yv, valid);
     }
@@ -112,10 +116,10 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
   finish_grid(vals, Q, k, P.scale0, partials, out, ticket);
 }
 
-template <int FAM, int L, int C, int V, int KPL>
+template <int FAM, int L, int C, int V, int KPL, bool ODD>
 int launch_one(const Shard& s, const Params& P) {
   constexpr bool PF = (C <= 4);
-  auto kern = k_wide_line<FAM, L, C, V, KPL, PF>;
+  auto kern = k_wide_line<FAM, L, C, V, KPL, PF, ODD>;
   const int Q = 2 * P.k;
   const size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
   int per_sm = 1;
@@ -130,13 +134,13 @@ int launch_one(const Shard& s, const Params& P) {
   return cudaGetLastError() == cudaSuccess ? 1 : SO_ECUDA;
 }
 
-template <int FAM, int L, int C, int V>
+template <int FAM, int L, int C, int V, bool ODD = false>
 int launch_kpl(const Shard& s, const Params& P) {
   const int kpl = (P.k + L - 1) / L;      // step sizes per lane
-  if (kpl <= 1) return launch_one<FAM, L, C, V, 1>(s, P);
-  if (kpl <= 2) return launch_one<FAM, L, C, V, 2>(s, P);
-  if (kpl <= 4) return launch_one<FAM, L, C, V, 4>(s, P);
-  if (kpl <= 8) return launch_one<FAM, L, C, V, 8>(s, P);
+  if (kpl <= 1) return launch_one<FAM, L, C, V, 1, ODD>(s, P);
+  if (kpl <= 2) return launch_one<FAM, L, C, V, 2, ODD>(s, P);
+  if (kpl <= 4) return launch_one<FAM, L, C, V, 4, ODD>(s, P);
+  if (kpl <= 8) return launch_one<FAM, L, C, V, 8, ODD>(s, P);
   return SO_EINVAL;                        // the API layer sends at most 8 step sizes per pass
 }
 
@@ -219,6 +223,12 @@ int launch_small_line(const Shard& s, const Params& P) {
 
 template <int FAM>
 int launch_mapped(const Shard& s, const Params& P) {
+  if ((P.f & 1) && P.f >= 9) {
+    const Mapping mo = choose_mapping(P.f + 1);
+#define SO_ODD(LL, CC) if (mo.L == LL && mo.C == CC && mo.V == 2) return launch_kpl<FAM, LL, CC, 2, true>(s, P);
+    SO_ODD(2, 4) SO_ODD(4, 4) SO_ODD(8, 4) SO_ODD(16, 4) SO_ODD(32, 4) SO_ODD(32, 8)
+#undef SO_ODD
+  }
   const Mapping m = choose_mapping(P.f);
 #define SO_CASE(LL, CC, VV) if (m.L == LL && m.C == CC && m.V == VV) return launch_kpl<FAM, LL, CC, VV>(s, P);
   SO_CASE(1, 4, 1) SO_CASE(2, 4, 1) SO_CASE(4, 4, 1) SO_CASE(8, 4, 1) SO_CASE(16, 4, 1) SO_CASE(32, 4, 1)

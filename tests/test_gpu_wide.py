@@ -84,6 +84,40 @@ def test_normal_equations_match_oracle(native, oracle, gpu_ctx, name, f, m):
     ds.free()
 
 
+@pytest.mark.parametrize("name,f", [("LINEAR", 9), ("LINEAR_NOINT", 31), ("LOGISTIC", 33), ("LINEAR", 127), ("LINEAR_NOINT", 255)])
+def test_odd_row_lengths_on_views_at_any_offset(native, oracle, gpu_ctx, name, f):
+    """f odd: the kernels stream a row as (f + 1)/2 aligned 16-byte units, i.e. one element of a NEIGHBOUR row travels with it
+    (so_wide.cu, ODD).  Views that start on odd rows (misaligned base), end on either parity, and are followed by a row of
+    NaNs (what lies behind the last row of a shard must never reach a sum) against the oracle on the same rows."""
+    fam = getattr(oracle, name)
+    truth = _truth(name, f)
+    m = 2_004
+    X, y = oracle.generate(fam, m, f, truth)
+    Xp = X.copy()
+    Xp[m - 1, :] = np.nan                                # the row behind ...
+    Xp[0, :] = np.nan                                    # ... and the row before some of the views below
+    ds = native.Dataset(gpu_ctx, m, f).append(Xp, y)
+    p = truth * 0.9 + 0.05
+    for lo, hi in [(1, m - 1), (1, m - 2), (2, m - 1), (2, m - 2), (7, 8), (8, 9), (3, 70)]:
+        v = ds.slice(lo, hi)
+        Xv, yv = X[lo:hi], y[lo:hi]
+        loss, grad = v.loss_grad(fam, p)
+        assert_loss(loss, oracle.apply(fam, Xv, yv, p))
+        assert_vec(grad, oracle.gradient(fam, Xv, yv, p), what=f"grad [{lo},{hi})")
+        d = np.cos(np.arange(p.size)) / p.size
+        assert_vec(v.hess_vec(fam, p, d), oracle.hess_vec(fam, Xv, yv, p, d), rtol=1e-11, what=f"Hd [{lo},{hi})")
+        phi, dphi = v.line(fam, p, d, [0.0, 0.5, 1.0])
+        phi_o, dphi_o = oracle.line(fam, Xv, yv, p, d, [0.0, 0.5, 1.0])
+        assert_vec(phi, phi_o, what=f"phi [{lo},{hi})")
+        assert_vec(dphi, dphi_o, rtol=1e-11, what=f"dphi [{lo},{hi})")
+        JtJ, Jtr, rtr = v.normal_eq(fam, p)
+        JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, Xv, yv, p)
+        np.testing.assert_allclose(JtJ, JtJ_o, rtol=1e-11, atol=1e-11 * np.abs(JtJ_o).max())
+        assert_vec(Jtr, Jtr_o, what=f"Jtr [{lo},{hi})")
+        v.free()
+    ds.free()
+
+
 def test_shapes_beyond_the_catalogue_are_an_error_not_a_fallback(native, gpu_ctx):
     ds = native.Dataset(gpu_ctx, 4, 513)
     ds.append(np.ones((4, 513)), np.ones(4))

@@ -1,4 +1,4 @@
-"""K1 / K4 on odd and even row lengths: python tools/k1_odd.py"""
+"""K1 / K3 / K4 on odd and even row lengths: python tools/k1_odd.py"""
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +11,9 @@ with native.Context(1) as ctx:
         truth = np.arange(1, n + 1) / n
         ds = native.Dataset(ctx, m, f).generate(fam, truth)
         out = {"family": name, "f": f, "rows": m}
-        for what, fn in (("k1_ms", lambda: ds.loss_grad(fam, truth * 0.9)), ("k4_ms", lambda: ds.hess_vec(fam, truth * 0.9, truth))):
+        for what, fn in (("k1_ms", lambda: ds.loss_grad(fam, truth * 0.9)), ("k4_ms", lambda: ds.hess_vec(fam, truth * 0.9, truth)),
+                         ("k3_1_ms", lambda: ds.line(fam, truth * 0.9, truth * 0.01, [0.5])),
+                         ("k3_4_ms", lambda: ds.line(fam, truth * 0.9, truth * 0.01, [0.0, 0.5, 1.0, 2.0]))):
             ks = []
             for _ in range(6):
                 fn(); ks.append(ctx.stats().kernel_ms)
