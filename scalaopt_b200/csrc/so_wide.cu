@@ -16,13 +16,15 @@ enum { kModeLossGrad = 0, kModeHessVec = 1 };
 
 // ODD: f odd streamed as (f + 1)/2 aligned 16-byte units per row, see so_wide.cuh.  The two row parities hold a column in
 // different registers; they meet in the block reduction.
-template <int FAM, int MODE, int L, int C, int V, bool PF, bool ODD = false>
+// PF: 0 no prefetch, 1 register prefetch of the next row group, 2 lane-private cp.async ring (so_wide.cuh; V = 2 only)
+template <int FAM, int MODE, int L, int C, int V, int PF, bool ODD = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
        int want_grad, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   constexpr int RW = 32 / L, CV = C * V;
   static_assert(!ODD || V == 2, "ODD streams 16-byte units");
+  static_assert(PF != 2 || V == 2, "the ring holds 16-byte units");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & (L - 1), r = lane / L;
   const int f = P.f, icpt = P.icpt;
@@ -83,7 +85,30 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
     for (int i = 0; i < CV; ++i) g[i] = fma(w, fr.x[i], g[i]);
   };
 
-  if (PF) {
+  if constexpr (PF == 2) {
+    if constexpr (V == 2) {
+      // [ (kWarps + 1) Q doubles of reduction scratch, rounded up to 16 bytes | ring ]
+      const LaneRing<C> rg = lane_ring<C>(smem + (((kWarps + 1) * Q + 1) & ~1));
+      int64_t gi = grp;
+#pragma unroll
+      for (int st = 0; st < kRingDepth; ++st, gi += gstr) {
+        if (gi < ngroups) { const int64_t row = gi * RW + r; ring_issue<L, C, (MODE == kModeLossGrad)>(rg, st, Xs, y, row, row < rows, f, q); }
+        cpa_commit();
+      }
+      for (int it = 0; grp < ngroups; grp += gstr, gi += gstr, ++it) {
+        const int st = it & (kRingDepth - 1);
+        cpa_wait<kRingDepth - 1>();
+        Frag<C, V> cur;
+        double yv;
+        const int64_t row = grp * RW + r;
+        ring_read<L, C, ODD, (MODE == kModeLossGrad)>(cur, yv, rg, st, row, rows, f, q, odd);
+        step(cur, yv, row < rows);
+        if (gi < ngroups) { const int64_t nrow = gi * RW + r; ring_issue<L, C, (MODE == kModeLossGrad)>(rg, st, Xs, y, nrow, nrow < rows, f, q); }
+        cpa_commit();
+      }
+      cpa_wait<0>();
+    }
+  } else if (PF) {
     // software pipeline: the next row group's loads are in flight while this one is reduced
     Frag<C, V> cur, nxt;
     double ycur = 0.0, ynxt = 0.0;
@@ -173,12 +198,25 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
   finish_grid(vals, Q, (MODE == kModeLossGrad) ? 1 : 0, P.scale0, partials, out, ticket);
 }
 
+#ifndef SO_WIDE_RING
+#define SO_WIDE_RING 1      // 0: register prefetch everywhere; 1: ring where it measured faster (so_wide.cuh); 2: every 16-byte mapping
+#endif
 template <int FAM, int MODE, int L, int C, int V, bool ODD = false>
 int launch_lcv(const Shard& s, const Params& P, int want_grad) {
-  constexpr bool PF = (C <= 4);
+  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= 16 && MODE == kModeLossGrad))) ? 2 : (C <= 4 ? 1 : 0);
   auto kern = k_wide<FAM, MODE, L, C, V, PF, ODD>;
   const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
-  const size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
+  size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
+  if (PF == 2) {
+    smem = sizeof(double) * (size_t)((((kWarps + 1) * Q) + 1) & ~1) + ring_bytes(C);
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr[dev]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return SO_ECUDA;
+      attr[dev] = true;
+    }
+  }
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
   if (per_sm < 1) per_sm = 1;

@@ -75,7 +75,12 @@ __device__ __forceinline__ double col_sum(double v) {       // sum over the 32/L
 template <int C, int V>
 struct Frag { double x[C * V]; };
 
-template <int L, int C, int V>
+// POLICY 0: streaming loads (read once, evict first); 1: L1-allocating loads — for rows that are not sector-aligned (odd f)
+// the 64-byte pieces of neighbouring lane groups share 32-byte sectors, which then come from L1 instead of L2 twice
+#ifndef SO_WIDE_ODD_LD
+#define SO_WIDE_ODD_LD 0
+#endif
+template <int L, int C, int V, int POLICY = 0>
 __device__ __forceinline__ void load_frag(Frag<C, V>& fr, const double* __restrict__ X, int64_t row, bool valid,
                                           int f, int q) {
 #pragma unroll
@@ -83,7 +88,10 @@ __device__ __forceinline__ void load_frag(Frag<C, V>& fr, const double* __restri
     const int col = (c * L + q) * V;
     if (V == 2) {
       double2 v = make_double2(0.0, 0.0);
-      if (valid && col < f) v = ld_stream2(reinterpret_cast<const double2*>(X + row * f + col));
+      if (valid && col < f) {
+        const double2* src = reinterpret_cast<const double2*>(X + row * f + col);
+        v = POLICY == 1 ? __ldg(src) : (POLICY == 2 ? *src : ld_stream2(src));
+      }
       fr.x[c * V] = v.x;
       fr.x[c * V + 1] = v.y;
     } else {
@@ -111,11 +119,84 @@ __device__ __forceinline__ int lane_row_parity(const double* X, int warp, int r)
 template <int L, int C, int V, bool ODD>
 __device__ __forceinline__ void load_row(Frag<C, V>& fr, const double* __restrict__ Xs, int64_t row, int64_t rows, bool valid,
                                          int f, int q, int odd) {
-  load_frag<L, C, V>(fr, Xs, row, valid, f, q);
+  load_frag<L, C, V, ODD ? SO_WIDE_ODD_LD : 0>(fr, Xs, row, valid, f, q);
   if (ODD && ((row == rows - 1 && !odd) || (row == 0 && odd))) {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       if (!odd && (c * L + q) * V + 1 == f) fr.x[c * V + 1] = 0.0;
+      if (odd && c == 0 && q == 0) fr.x[0] = 0.0;
+    }
+  }
+}
+
+// ---- lane-private shared-memory ring (prefetch mode 2) ------------------------------------------------------------------
+// The register prefetch keeps ONE row group in flight per warp: 16 warps x 2 KB = 32 KB per SM, and at ~1700 cycles of
+// DRAM latency that is 5.4 TB/s — exactly what the odd-f K1 ran at (ncu: long_scoreboard 9.2 of 13.3 stall cycles per
+// issue, DRAM bytes = algorithmic; profiles/r2_k1_odd_units_ncu.json).  Here the NEXT kRingDepth groups travel with cp.async
+// (LDGSTS) into slots that belong to the lane that will consume them: no registers are held for data in flight, no
+// barrier (a lane reads back only what it copied itself, cp.async.wait_group orders that; y is the one shared value of a row),
+// and kRingDepth x 32 KB per SM are in flight.  A slot is refilled after its values were consumed (they are operands of the
+// step's FMAs), so the asynchronous write cannot overtake the read.
+// Measured (profiles/r2_wide_ring_ab.jsonl, one box): with 16 or 32 lanes per row (f >= ~64) K1 gains 11-15 % (f = 127:
+// 3.83 -> 3.28 ms per 2e7 rows, f = 128: 3.28 -> 2.93, f = 256: 3.35 -> 2.91 per 1e7) and K3 on odd f as much; K4 and the
+// even-f K3 lose 5-15 %, and with 4 lanes per row (f = 31 / 32: eight 64-byte pieces per LDGSTS) everything loses.  The
+// launchers therefore use it for K1 with L >= 16 and for K3 with odd f and L >= 16 only.
+#ifndef SO_RING_DEPTH
+#define SO_RING_DEPTH 2      // power of two; 2 beat 4 and 8 on every shape it helps (profiles/r2_wide_ring_ab.jsonl)
+#endif
+constexpr int kRingDepth = SO_RING_DEPTH;
+__device__ __forceinline__ void cpa16(void* dst, const void* src, bool valid) {
+  const unsigned int sz = valid ? 16u : 0u;      // src-size 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cpa8(void* dst, const void* src, bool valid) {
+  const unsigned int sz = valid ? 8u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+constexpr size_t ring_bytes(int C) { return (size_t)kRingDepth * kThreads * ((size_t)C * 16 + 8); }
+// this lane's slots: x[(stage * C + c) * kThreads], y[stage * kThreads]
+template <int C> struct LaneRing { double2* x; double* y; };
+template <int C>
+__device__ __forceinline__ LaneRing<C> lane_ring(void* base) {
+  LaneRing<C> rg;
+  rg.x = reinterpret_cast<double2*>(base) + threadIdx.x;
+  rg.y = reinterpret_cast<double*>(reinterpret_cast<double2*>(base) + (size_t)kRingDepth * C * kThreads) + threadIdx.x;
+  return rg;
+}
+// NEEDY: the row's y travels too — copied by the row's first lane only, read by all of its lanes after a __syncwarp
+template <int L, int C, bool NEEDY>
+__device__ __forceinline__ void ring_issue(const LaneRing<C>& rg, int stage, const double* __restrict__ Xs, const double* __restrict__ y,
+                                           int64_t row, bool valid, int f, int q) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int col = (c * L + q) * 2;
+    const bool live = valid && col < f;
+    cpa16(rg.x + (size_t)(stage * C + c) * kThreads, live ? Xs + row * f + col : Xs, live);
+  }
+  if (NEEDY) {
+    if (L > 1) __syncwarp();                                     // every lane of the row has read the y this slot held
+    if (q == 0) cpa8(rg.y + (size_t)stage * kThreads, valid ? y + row : y, valid);
+  }
+}
+template <int L, int C, bool ODD, bool NEEDY>
+__device__ __forceinline__ void ring_read(Frag<C, 2>& fr, double& yv, const LaneRing<C>& rg, int stage, int64_t row, int64_t rows,
+                                          int f, int q, int odd) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const double2 v = rg.x[(size_t)(stage * C + c) * kThreads];
+    fr.x[c * 2] = v.x; fr.x[c * 2 + 1] = v.y;
+  }
+  yv = 0.0;
+  if (NEEDY) {
+    if (L > 1) __syncwarp();                                     // the first lane's wait_group has passed as well
+    yv = *(rg.y + (size_t)stage * kThreads - q);                 // slot of lane (r, 0)
+  }
+  if (ODD && ((row == rows - 1 && !odd) || (row == 0 && odd))) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (!odd && (c * L + q) * 2 + 1 == f) fr.x[c * 2 + 1] = 0.0;
       if (odd && c == 0 && q == 0) fr.x[0] = 0.0;
     }
   }

@@ -11,11 +11,11 @@ namespace so {
 namespace wide {
 namespace {
 
-template <int FAM, int L, int C, int V, int KPL, bool PF, bool ODD = false>      // ODD: odd f as aligned 16-byte units (so_wide.cuh)
+template <int FAM, int L, int C, int V, int KPL, int PF, bool ODD = false>      // PF, ODD: as in k_wide (so_wide.cu, so_wide.cuh)
 __global__ void __launch_bounds__(kThreads, 2)
 k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
             double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   constexpr int RW = 32 / L, CV = C * V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & (L - 1), r = lane / L;
@@ -65,7 +65,29 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
     }
   };
 
-  if (PF) {
+  if constexpr (PF == 2) {
+    if constexpr (V == 2) {
+      const LaneRing<C> rg = lane_ring<C>(smem + (((kWarps + 1) * Q + 1) & ~1));
+      int64_t gi = grp;
+#pragma unroll
+      for (int st = 0; st < kRingDepth; ++st, gi += gstr) {
+        if (gi < ngroups) { const int64_t row = gi * RW + r; ring_issue<L, C, true>(rg, st, Xs, y, row, row < rows, f, q); }
+        cpa_commit();
+      }
+      for (int it = 0; grp < ngroups; grp += gstr, gi += gstr, ++it) {
+        const int st = it & (kRingDepth - 1);
+        cpa_wait<kRingDepth - 1>();
+        Frag<C, V> cur;
+        double yv;
+        const int64_t row = grp * RW + r;
+        ring_read<L, C, ODD, true>(cur, yv, rg, st, row, rows, f, q, odd);
+        step(cur, yv, row < rows);
+        if (gi < ngroups) { const int64_t nrow = gi * RW + r; ring_issue<L, C, true>(rg, st, Xs, y, nrow, nrow < rows, f, q); }
+        cpa_commit();
+      }
+      cpa_wait<0>();
+    }
+  } else if (PF) {
     Frag<C, V> cur, nxt;
     double ycur = 0.0, ynxt = 0.0;
     bool vcur = false, vnxt = false;
@@ -116,12 +138,25 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
   finish_grid(vals, Q, k, P.scale0, partials, out, ticket);
 }
 
+#ifndef SO_WIDE_RING
+#define SO_WIDE_RING 1      // as in so_wide.cu
+#endif
 template <int FAM, int L, int C, int V, int KPL, bool ODD>
 int launch_one(const Shard& s, const Params& P) {
-  constexpr bool PF = (C <= 4);
+  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= 16 && ODD))) ? 2 : (C <= 4 ? 1 : 0);
   auto kern = k_wide_line<FAM, L, C, V, KPL, PF, ODD>;
   const int Q = 2 * P.k;
-  const size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
+  size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
+  if (PF == 2) {
+    smem = sizeof(double) * (size_t)((((kWarps + 1) * Q) + 1) & ~1) + ring_bytes(C);
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr[dev]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return SO_ECUDA;
+      attr[dev] = true;
+    }
+  }
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
   if (per_sm < 1) per_sm = 1;

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscalaopt_cuda.so")
+# SCALAOPT_CUDA_LIB: another build of the same library (same-box A/B runs of kernel variants, tools/)
+LIB_PATH = os.environ.get("SCALAOPT_CUDA_LIB") or os.path.join(_HERE, "libscalaopt_cuda.so")
 
 LINEAR, LINEAR_NOINT, LOGISTIC, EXPDECAY, GAUSS, GAUSS_EXPBKG, POLY, MLP_MSE, MLP_CE, SOFTMAX = range(10)
 FAMILY_NAMES = {LINEAR: "linear", LINEAR_NOINT: "linear_noint", LOGISTIC: "logistic", EXPDECAY: "expdecay",
