@@ -175,7 +175,9 @@ int so_dataset_size(so_dataset* ds, int64_t* m);
 int so_dataset_head(so_dataset* ds, double* x, double* y);
 
 /* Non-owning view of local rows [begin, end) — the data-set analogue of `filter` on the row index
- * (DataSet.scala:60, as used by QR.scala:147).  The parent must outlive the view. */
+ * (DataSet.scala:60, as used by QR.scala:147).  A view aliases its parent's device memory: rows appended to the parent later
+ * do not join it, and once the parent has been freed or cleared every call on the view fails with SO_ESTATE (the library
+ * keeps a generation per owning data set; the view itself must still be released with so_dataset_free). */
 int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_dataset** view);
 
 void so_dataset_free(so_dataset* ds);

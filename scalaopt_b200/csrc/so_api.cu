@@ -23,6 +23,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "so_internal.h"
@@ -120,6 +121,10 @@ struct so_ctx {
   bool finish_multi = false;      // mailboxes of all GPUs / ranks are wired: results up to kMailCap doubles are summed by so_finish
   bool poisoned = false;          // a peer timed out inside an exchange: sequence numbers can no longer be trusted
   uint64_t data_epoch = 1;        // bumped by everything that writes observations (append, load, clear, generate)
+  // owning data sets of this context and their generation (a new one after so_dataset_clear): what a view checks before it
+  // touches its parent's memory, so that a freed or cleared parent is SO_ESTATE instead of a stale read
+  std::unordered_map<const so_dataset*, uint64_t> live;
+  uint64_t next_gen = 1;
 };
 
 struct ShardMem {
@@ -141,6 +146,8 @@ struct so_dataset {
   int ny = 1;           // outputs per observation (row-major y[m x ny]); > 1 only for the network families
   std::vector<ShardMem> shards;   // one per device of the context
   bool view = false;
+  const so_dataset* parent = nullptr;   // views: the owning data set and its generation when the view was taken
+  uint64_t parent_gen = 0;
   int64_t global_m = -1;          // rank mode: sum of filled rows over ranks (cached)
 };
 
@@ -151,6 +158,15 @@ int fail(so_ctx* ctx, int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
   if (ctx) ctx->err = buf; else g_init_error = buf;
   return code;
+}
+
+// a view is only as good as its parent: freed or cleared since the view was taken -> SO_ESTATE (context mutex held)
+int check_view(so_dataset* ds) {
+  if (!ds->view) return SO_OK;
+  const auto it = ds->ctx->live.find(ds->parent);
+  if (it == ds->ctx->live.end()) return fail(ds->ctx, SO_ESTATE, "view of a data set that has been freed");
+  if (it->second != ds->parent_gen) return fail(ds->ctx, SO_ESTATE, "view of a data set that has been cleared since the view was taken");
+  return SO_OK;
 }
 
 #define SO_CUDA(ctx, call)                                                                            \
@@ -534,6 +550,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
              int k, int want_grad, int Q, std::vector<double>& res, const NllCall* nll = nullptr) {
   so_ctx* ctx = ds->ctx;
   if (ctx->poisoned) return fail(ctx, SO_ESTATE, "context unusable after a failed cross-GPU exchange: %s", std::string(ctx->err).c_str());
+  if (int rcv = check_view(ds)) return rcv;
   const bool scalar = nll != nullptr || family_is_scalar_t(family);
   const int G = (int)ctx->devs.size();
   int64_t rows_local = 0, launches = 0;
@@ -861,6 +878,7 @@ extern "C" int so_dataset_create_multi(so_ctx* ctx, int64_t m, int f, int ny, so
       }
     }
   }
+  ctx->live[ds] = ctx->next_gen++;
   *out = ds;
   return SO_OK;
 }
@@ -868,6 +886,7 @@ extern "C" int so_dataset_create_multi(so_ctx* ctx, int64_t m, int f, int ny, so
 extern "C" void so_dataset_free(so_dataset* ds) {
   if (!ds) return;
   if (!ds->view) {
+    { std::lock_guard<std::mutex> lk(ds->ctx->mu); ds->ctx->live.erase(ds); }
     for (size_t g = 0; g < ds->shards.size(); ++g) {
       cudaSetDevice(ds->ctx->devs[g].id);
       if (ds->shards[g].X) cudaFree(ds->shards[g].X);
@@ -1029,6 +1048,7 @@ extern "C" int so_dataset_clear(so_dataset* ds) {
   std::lock_guard<std::mutex> lk(ds->ctx->mu);
   if (ds->view) return fail(ds->ctx, SO_EINVAL, "so_dataset_clear: cannot clear a view");
   ++ds->ctx->data_epoch;
+  ds->ctx->live[ds] = ds->ctx->next_gen++;        // views taken before this point are stale
   for (ShardMem& sm : ds->shards) sm.filled = 0;
   ds->global_m = -1;
   return SO_OK;
@@ -1067,6 +1087,7 @@ extern "C" int so_dataset_read(so_dataset* ds, int64_t row_begin, int64_t rows, 
   if (!ds) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rcv = check_view(ds)) return rcv;
   int64_t filled = 0;
   for (const ShardMem& sm : ds->shards) filled += sm.filled;
   if (row_begin < 0 || rows < 0 || row_begin + rows > filled) return fail(ctx, SO_EINVAL, "so_dataset_read: rows [%lld, %lld) outside [0, %lld)", (long long)row_begin, (long long)(row_begin + rows), (long long)filled);
@@ -1104,11 +1125,14 @@ extern "C" int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_d
   if (!ds || !view) return SO_EINVAL;
   so_ctx* ctx = ds->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rcv = check_view(ds)) return rcv;
   int64_t filled = 0;
   for (const ShardMem& sm : ds->shards) filled += sm.filled;
   if (begin < 0 || end < begin || end > filled) return fail(ctx, SO_EINVAL, "so_dataset_slice: [%lld, %lld) outside [0, %lld)", (long long)begin, (long long)end, (long long)filled);
   so_dataset* v = new so_dataset();
   v->ctx = ctx; v->f = ds->f; v->ny = ds->ny; v->view = true; v->m = end - begin;
+  v->parent = ds->view ? ds->parent : ds;
+  v->parent_gen = ds->view ? ds->parent_gen : ctx->live[ds];
   v->shards.resize(ds->shards.size());
   int64_t base = 0;
   for (size_t g = 0; g < ds->shards.size(); ++g) {

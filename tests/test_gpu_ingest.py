@@ -53,3 +53,32 @@ def test_load_raw_files(native, oracle, gpu_ctx, tmp_path):
     with pytest.raises(native.NativeError):
         native.Dataset(gpu_ctx, 10, f).load_raw(str(tmp_path / "missing"), str(py), 10)
     ds.free()
+
+
+def test_a_view_of_a_freed_or_cleared_data_set_fails_loudly(native, oracle, gpu_ctx):
+    """so_dataset_slice views alias the parent's memory (scalaopt_cuda.h): after the parent is cleared or freed, an evaluation
+    on the view is SO_ESTATE, not a read of stale or released device memory."""
+    fam = oracle.LINEAR
+    X, y = oracle.generate(fam, 1000, 3, np.array([1.0, 2.0, 3.0, 4.0]))
+    p = np.ones(4)
+    ds = native.Dataset(gpu_ctx, 1000, 3).append(X, y)
+    v = ds.slice(10, 500)
+    vv = v.slice(5, 100)                      # a view of a view hangs on the owner
+    loss, _ = v.loss_grad(fam, p)
+    assert loss == pytest.approx(oracle.apply(fam, X[10:500], y[10:500], p), rel=1e-12)
+    ds.clear()
+    ds.append(X[:600], y[:600])               # re-ingested: the old views stay stale
+    for view in (v, vv):
+        with pytest.raises(native.NativeError) as e:
+            view.loss_grad(fam, p)
+        assert e.value.code == -6
+    with pytest.raises(native.NativeError):
+        v.read(0, 1)
+    v2 = ds.slice(10, 500)                    # a fresh view works
+    assert v2.loss_grad(fam, p)[0] == pytest.approx(loss, rel=1e-15)
+    ds.free()
+    with pytest.raises(native.NativeError) as e:
+        v2.loss_grad(fam, p)
+    assert e.value.code == -6
+    for view in (v, vv, v2):
+        view.free()
