@@ -112,36 +112,6 @@ __device__ __forceinline__ double so_exps(double p, double q) {
 }
 static __device__ __noinline__ double exps_slow(double p, double q) { return exp(p * q * kExpS.unscale); }
 
-// Variant with a 4096-entry table (32 KB, in dynamic shared memory) and a degree-3 polynomial: 8 FP64-pipe
-// instructions.  |r| <= ln2/8192, truncation error r^4/24 < 3e-18.  Worth its shared memory only where the kernel
-// is FP64-issue-bound (every FP64 instruction costs >= 2 issue cycles and nothing else hides under it).
-constexpr int kExpBigBits = 12, kExpBigSize = 1 << kExpBigBits;
-struct ExpConstsBig { double inv, shift, nln2hi, c3; };
-static __constant__ ExpConstsBig kExpBig = {
-    0x1.71547652b82fep+12,     // 4096 / ln 2
-    6755399441055744.0,
-    -0x1.62e42fefa39efp-13,    // -(ln 2 / 4096) rounded to double
-    0x1.5555555555555p-3,      // 1/6
-};
-__device__ __forceinline__ void exp_big_table_init(double* tab) {
-  for (int j = threadIdx.x; j < kExpBigSize; j += blockDim.x) {
-    const double v = exp2((double)j * (1.0 / kExpBigSize));
-    tab[j] = __hiloint2double(__double2hiint(v) - (j << 8), __double2loint(v));     // pre-biased as in exp_table_init
-  }
-}
-__device__ __forceinline__ double so_exp_fast_big(double x, const double* __restrict__ tab) {
-  double kd = fma(x, kExpBig.inv, kExpBig.shift);
-  const int ki = __double2loint(kd);
-  kd -= kExpBig.shift;
-  const double r = fma(kd, kExpBig.nln2hi, x);
-  double q = fma(r, kExpBig.c3, 0.5);
-  q = fma(q, r, 1.0);
-  const double pm1 = q * r;
-  const double Tb = tab[ki & (kExpBigSize - 1)];
-  const double T = __hiloint2double(__double2hiint(Tb) + (ki << 8), __double2loint(Tb));
-  return fma(T, pm1, T);
-}
-
 // exp(x) with the range check folded in (one branch); used where the check is not hoisted by the caller.
 __device__ __forceinline__ double so_exp(double x) {
   if (!exp_in_range(x)) return exp_slow(x);

@@ -441,9 +441,9 @@ struct OpQr {
   }
 };
 
-template <class Op, int G, bool BIG, bool CHECK = true>
+template <class Op, int G, bool CHECK = true>
 __device__ __forceinline__ void process_rows(const typename Op::Args& args, const double (&t)[G], const double (&y)[G],
-                                             double (&acc)[Op::Q], const double* __restrict__ big_tab) {
+                                             double (&acc)[Op::Q]) {
   constexpr int NE = Op::NEXP;
   if constexpr (NE == 0) {
     if constexpr (requires { Op::kGroupFold; }) Op::template accum_group<G>(args, t, y, nullptr, acc);
@@ -479,9 +479,9 @@ __device__ __forceinline__ void process_rows(const typename Op::Args& args, cons
 }
 
 // a loop trip carries 4 rows (two 128-bit loads of t and of y); they are processed in groups of Op::G
-template <class Op, bool BIG, bool CHECK = true>
+template <class Op, bool CHECK = true>
 __device__ __forceinline__ void process4(const typename Op::Args& args, double2 ta, double2 ya, double2 tb, double2 yb,
-                                         double (&acc)[Op::Q], const double* __restrict__ big_tab) {
+                                         double (&acc)[Op::Q]) {
   constexpr int G = Op::G;
   const double t4[4] = {ta.x, ta.y, tb.x, tb.y}, y4[4] = {ya.x, ya.y, yb.x, yb.y};
 #pragma unroll
@@ -489,20 +489,18 @@ __device__ __forceinline__ void process4(const typename Op::Args& args, double2 
     double tg[G], yg[G];
 #pragma unroll
     for (int r = 0; r < G; ++r) { tg[r] = t4[g0 + r]; yg[r] = y4[g0 + r]; }
-    process_rows<Op, G, BIG, CHECK>(args, tg, yg, acc, big_tab);
+    process_rows<Op, G, CHECK>(args, tg, yg, acc);
   }
 }
-template <class Op, bool BIG>
-__device__ __forceinline__ void process1(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q],
-                                         const double* __restrict__ big_tab) {
+template <class Op>
+__device__ __forceinline__ void process1(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q]) {
   const double tg[1] = {t}, yg[1] = {y};
-  process_rows<Op, 1, BIG>(args, tg, yg, acc, big_tab);
+  process_rows<Op, 1>(args, tg, yg, acc);
 }
 
-template <class Op, bool BIG>
-__device__ __noinline__ void process1_cold(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q],
-                                           const double* __restrict__ big_tab) {
-  process1<Op, BIG>(args, t, y, acc, big_tab);
+template <class Op>
+__device__ __noinline__ void process1_cold(const typename Op::Args& args, double t, double y, double (&acc)[Op::Q]) {
+  process1<Op>(args, t, y, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -518,20 +516,17 @@ __device__ __noinline__ void process1_cold(const typename Op::Args& args, double
 //   warp-private rings (1 KB copies)   slower than the block ring (54% vs 64% of roofline)  DESIGN.md
 //   barrier right after the LDS        2.5% faster than releasing at the end, but races with the refill (MODE 4 note below)
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int stages_for(int rpt, bool big = false) { return rpt >= 8 ? (big ? 2 : 3) : 4; }
-constexpr size_t ring_bytes(int tpb, int rpt, bool big) { return (size_t)stages_for(rpt, big) * tpb * rpt * 16; }
-constexpr size_t smem_bytes(int tpb, int rpt, bool big) { return ring_bytes(tpb, rpt, big) + (big ? sizeof(double) * kExpBigSize : 0); }
+__host__ __device__ constexpr int stages_for(int rpt) { return rpt >= 8 ? 3 : 4; }
+constexpr size_t smem_bytes(int tpb, int rpt) { return (size_t)stages_for(rpt) * tpb * rpt * 16; }
 
-template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4, bool BIG = false, bool CHECK = true>
+template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4, bool CHECK = true>
 __global__ void __launch_bounds__(TPB, MINBLOCKS)
 k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t rows,
          const __grid_constant__ typename Op::Args args,
          double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  constexpr int Q = Op::Q, WPB = TPB / 32, kChunkRows = TPB * RPT, kStages = stages_for(RPT, BIG);
+  constexpr int Q = Op::Q, WPB = TPB / 32, kChunkRows = TPB * RPT, kStages = stages_for(RPT);
   constexpr size_t kStageBytes = (size_t)kChunkRows * 16;
-  extern __shared__ __align__(128) unsigned char s_dyn[];       // [4096-entry exp table (BIG)] [kStages][ t | y ]
-  const double* big_tab = reinterpret_cast<const double*>(s_dyn);
-  unsigned char* s_ring = s_dyn + (BIG ? sizeof(double) * kExpBigSize : 0);
+  extern __shared__ __align__(128) unsigned char s_ring[];      // [kStages][ t | y ]
   __shared__ double s_red[WPB * Q];
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -558,7 +553,7 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
     for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WPB); }
     mbar_fence_init();
   }
-  if constexpr (Op::NEXP > 0) { if (BIG) exp_big_table_init(reinterpret_cast<double*>(s_dyn)); else exp_table_init(); }
+  if constexpr (Op::NEXP > 0) exp_table_init();
   __syncthreads();
   if (tid == 0) {
 #pragma unroll
@@ -619,19 +614,19 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
       if (tid + 3 * TPB < npairs) {                             // all 8 rows of this thread are there: one fold of 8
         const double t8[8] = {tv[0].x, tv[0].y, tv[1].x, tv[1].y, tv[2].x, tv[2].y, tv[3].x, tv[3].y};
         const double y8[8] = {yv[0].x, yv[0].y, yv[1].x, yv[1].y, yv[2].x, yv[2].y, yv[3].x, yv[3].y};
-        process_rows<Op, 8, BIG, CHECK>(args, t8, y8, acc, big_tab);
+        process_rows<Op, 8, CHECK>(args, t8, y8, acc);
       } else {                                                  // ragged last chunk: one row at a time, out of line
 #pragma unroll
         for (int j = 0; j < RPT / 2; ++j)
-          if (tid + j * TPB < npairs) { process1_cold<Op, BIG>(args, tv[j].x, yv[j].x, acc, big_tab); process1_cold<Op, BIG>(args, tv[j].y, yv[j].y, acc, big_tab); }
+          if (tid + j * TPB < npairs) { process1_cold<Op>(args, tv[j].x, yv[j].x, acc); process1_cold<Op>(args, tv[j].y, yv[j].y, acc); }
       }
     } else
 #pragma unroll
     for (int j = 0; j < RPT / 2; j += 2) {
       if (tid + (j + 1) * TPB < npairs) {
-        process4<Op, BIG, CHECK>(args, tv[j], yv[j], tv[j + 1], yv[j + 1], acc, big_tab);
+        process4<Op, CHECK>(args, tv[j], yv[j], tv[j + 1], yv[j + 1], acc);
       } else {
-        if (tid + j * TPB < npairs) { process1<Op, BIG>(args, tv[j].x, yv[j].x, acc, big_tab); process1<Op, BIG>(args, tv[j].y, yv[j].y, acc, big_tab); }
+        if (tid + j * TPB < npairs) { process1<Op>(args, tv[j].x, yv[j].x, acc); process1<Op>(args, tv[j].y, yv[j].y, acc); }
       }
     }
     if constexpr (requires { Op::renorm(acc); }) Op::renorm(acc);
@@ -655,11 +650,11 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
     }
   }
   if constexpr (requires { Op::kGroupFold; }) {
-    if (blockIdx.x == 0 && tid == 0 && head) process1_cold<Op, BIG>(args, t[0], y[0], acc, big_tab);
-    if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1_cold<Op, BIG>(args, t[rows - 1], y[rows - 1], acc, big_tab);
+    if (blockIdx.x == 0 && tid == 0 && head) process1_cold<Op>(args, t[0], y[0], acc);
+    if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1_cold<Op>(args, t[rows - 1], y[rows - 1], acc);
   } else {
-    if (blockIdx.x == 0 && tid == 0 && head) process1<Op, BIG>(args, t[0], Op::kNeedsY ? y[0] : 0.0, acc, big_tab);
-    if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op, BIG>(args, t[rows - 1], Op::kNeedsY ? y[rows - 1] : 0.0, acc, big_tab);
+    if (blockIdx.x == 0 && tid == 0 && head) process1<Op>(args, t[0], Op::kNeedsY ? y[0] : 0.0, acc);
+    if (blockIdx.x == gridDim.x - 1 && tid == TPB - 1 && tail) process1<Op>(args, t[rows - 1], Op::kNeedsY ? y[rows - 1] : 0.0, acc);
   }
   if constexpr (requires { Op::finalize(acc); }) { Op::renorm(acc); Op::finalize(acc); }
 
@@ -669,10 +664,10 @@ k_scalar(const double* __restrict__ t, const double* __restrict__ y, int64_t row
   else grid_reduce<Q>(acc, s_red, partials, out, args.scale, ticket);
 }
 
-template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4, bool BIG = false, bool CHECK = true>
+template <class Op, int TPB, int MINBLOCKS, int MODE = 0, int RPT = 4, bool CHECK = true>
 int launch_op_cfg(const Shard& s, const typename Op::Args& args) {
-  auto kern = k_scalar<Op, TPB, MINBLOCKS, MODE, RPT, BIG, CHECK>;
-  constexpr size_t smem = smem_bytes(TPB, RPT, BIG);
+  auto kern = k_scalar<Op, TPB, MINBLOCKS, MODE, RPT, CHECK>;
+  constexpr size_t smem = smem_bytes(TPB, RPT);
   static int per_sm_dev[64] = {0};   // per instantiation and per device: function attributes are per-device state
   int dev = 0;
   cudaGetDevice(&dev);
@@ -736,7 +731,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
             typename Opn::Args an; an.pre = pre;
             an.scale[0] = 0.5;
             for (int i = 0; i < N; ++i) an.scale[1 + i] = -pre.D[i];
-            return launch_op_cfg<Opn, kThreads, SO_K1_MINB, 0, SO_K1_RPT, false, false>(s, an);
+            return launch_op_cfg<Opn, kThreads, SO_K1_MINB, 0, SO_K1_RPT, false>(s, an);
           }
         }
         using Op = OpLossGrad<Fam, true, SO_K1_G>;
@@ -768,7 +763,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       if constexpr (std::is_same<Fam, FamGaussExpBkg>::value) {
         // the headline kernel (BASELINE config 3): 2 rows per range-checked group, 8 rows per thread per chunk,
         // 2 blocks/SM.  A/B runs on one box (profiles/r1_k2_call26_groups.log, r1_k2_call27_groups.log): 4 rows per group -1 %, 4 rows per
-        // chunk -3 %, 4096-entry exp table (degree-3 polynomial) +1.5 %, no range check at all +1.5 %, 20-24 warps/SM -8..-25 %.
+        // chunk -3 %, 4096-entry exp table with a degree-3 polynomial +1.5 % (removed), no range check at all +1.5 %, 20-24 warps/SM -8..-25 %.
 #ifndef SO_K2_G
 #define SO_K2_G 2
 #define SO_K2_TPB 256
@@ -788,12 +783,12 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
           using Op4 = OpNormalEq<Fam, SO_K2NC_G>;
           typename Op4::Args a4; a4.pre = a.pre;
           for (int q2 = 0; q2 < Op4::Q; ++q2) { a4.scale[q2] = a.scale[q2]; a4.src[q2] = a.src[q2]; }
-          return launch_op_cfg<Op4, SO_K2NC_TPB, SO_K2NC_MINB, 0, SO_K2NC_RPT, false, false>(s, a4);
+          return launch_op_cfg<Op4, SO_K2NC_TPB, SO_K2NC_MINB, 0, SO_K2NC_RPT, false>(s, a4);
         }
         using Op2 = OpNormalEq<Fam, SO_K2_G>;
         typename Op2::Args a2; a2.pre = a.pre;
         for (int q2 = 0; q2 < Op2::Q; ++q2) { a2.scale[q2] = a.scale[q2]; a2.src[q2] = a.src[q2]; }
-        return launch_op_cfg<Op2, SO_K2_TPB, SO_K2_MINB, SO_K2_MODE, SO_K2_RPT, false, true>(s, a2);
+        return launch_op_cfg<Op2, SO_K2_TPB, SO_K2_MINB, SO_K2_MODE, SO_K2_RPT, true>(s, a2);
       }
       return launch_op<Op, (Op::Q < 21 ? 3 : 2)>(s, a);
     }
@@ -819,7 +814,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
         }
         constexpr int MB = KB >= 5 ? 1 : 2, RP = 8;
         if constexpr (kFamHasRange<Fam>) {
-          if (in_range) return launch_op_cfg<Op, kThreads, MB, 0, RP, false, false>(s, a);     // check-free, see kNormalEq
+          if (in_range) return launch_op_cfg<Op, kThreads, MB, 0, RP, false>(s, a);     // check-free, see kNormalEq
         }
         return launch_op_cfg<Op, kThreads, MB, 0, RP>(s, a);
       };
@@ -838,7 +833,7 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
       for (int i = 0; i < N; ++i) { a.dd[i] = pre.D[i] * d[i]; a.scale[i] = pre.D[i]; a.scale2[i] = -1.0; }
       if constexpr (requires { Fam::args_in_range(pre, 0.0, 0.0); }) {
         if (s.has_range && Fam::args_in_range(pre, s.tmin, s.tmax))
-          return launch_op_cfg<Op, kThreads, SO_K4_MINB, 0, SO_K4_RPT, false, false>(s, a);
+          return launch_op_cfg<Op, kThreads, SO_K4_MINB, 0, SO_K4_RPT, false>(s, a);
       }
       return launch_op_cfg<Op, kThreads, SO_K4_MINB, 0, SO_K4_RPT>(s, a);
     }
@@ -934,7 +929,7 @@ int launch_nll(const Shard& s, int pdf, const double* p, int n, const double* co
     using Opn = OpNll<PdfGaussExpBkg, SO_NLL_NC_G>;
     Opn::Args an; an.pre = pre;
     an.scale[0] = -2.0; an.scale[1] = 0.0; an.scale[2] = 0.0;
-    return launch_op_cfg<Opn, kThreads, SO_NLL_MINB, 0, SO_NLL_RPT, false, false>(s, an);
+    return launch_op_cfg<Opn, kThreads, SO_NLL_MINB, 0, SO_NLL_RPT, false>(s, an);
   }
   using Op = OpNll<PdfGaussExpBkg, SO_NLL_G>;
   Op::Args a;

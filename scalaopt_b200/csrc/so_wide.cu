@@ -313,8 +313,7 @@ int launch_mapped(const Shard& s, const Params& P, int want_grad) {
   }
   const Mapping m = choose_mapping(P.f);
 #define SO_CASE(LL, CC, VV) if (m.L == LL && m.C == CC && m.V == VV) return launch_lcv<FAM, MODE, LL, CC, VV>(s, P, want_grad);
-  SO_CASE(1, 4, 1) SO_CASE(2, 4, 1) SO_CASE(4, 4, 1) SO_CASE(8, 4, 1) SO_CASE(16, 4, 1) SO_CASE(32, 4, 1)
-  SO_CASE(32, 8, 1) SO_CASE(32, 16, 1)
+  // V = 1 (64-bit loads) has no caller left: odd f >= 9 streams aligned 16-byte units (ODD above), n <= 8 is k_small
   SO_CASE(1, 4, 2) SO_CASE(2, 4, 2) SO_CASE(4, 4, 2) SO_CASE(8, 4, 2) SO_CASE(16, 4, 2) SO_CASE(32, 4, 2)
   SO_CASE(32, 8, 2)
 #undef SO_CASE
