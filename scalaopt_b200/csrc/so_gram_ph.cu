@@ -454,7 +454,11 @@ int launch_ph_layout(const Shard& s, const Params& P, const CUtensorMap& tmap, i
 // n = 32: 5.96 -> 5.70 ms, n = 16: 5.82 -> 4.80 ms per 1e8 / 2e8 rows — one block of 16 warps beyond, where the tile
 // triangle is split over up to 8 warps (profiles/r2_gram_ph_v6_half.jsonl, r2_gram_ph_v7_nth.txt).
 // Also measured and not kept: accumulating the next chunk's linear predictor inside the DMMA loop (three stages, one
-// barrier per chunk, no separate phase A): n = 32 5.64 vs 5.48 ms, n = 40 7.47 vs 6.89 ms (profiles/r2_gram_ph_v8_fused.txt).
+// barrier per chunk, no separate phase A): n = 32 5.64 vs 5.48 ms, n = 40 7.47 vs 6.89 ms (profiles/r2_gram_ph_v8_fused.txt);
+// and a three-stage ring with ONE barrier per chunk in which half of the warps (two per sub-partition) run "phase A of chunk
+// c+1, then phase B of chunk c" and the other half the reverse, so that the latency-bound phase always has DMMA warps beside
+// it: n = 32 5.34 -> 5.92 ms, logistic 5.81 -> 6.81, n = 16 4.79 -> 4.68, n = 24 3.85 -> 4.07 (profiles/r2_gram_ph_v9_pipe_roles.jsonl)
+// — a phase-A warp's dependent DFMAs queue behind the DMMA bursts of its sub-partition, the k_gram_tri problem again.
 __host__ __device__ constexpr int ph_threads(int T) { return T <= 3 ? 128 : T <= 8 ? 256 : 512; }
 
 template <int FAM, int T>
