@@ -5,6 +5,7 @@
 //   K4  function/ObjectiveFunctionWithGradient.scala:41-47 ; FFNeuralNetworkTrainer.scala:76-80
 // Bytes per observation: 8 (f + 1); flops per observation ~ 4 f: HBM-bound.
 #include <algorithm>
+#include <cstdlib>
 
 #include "so_wide.cuh"
 
@@ -21,7 +22,7 @@ template <int FAM, int MODE, int L, int C, int V, int PF, bool ODD = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
        int want_grad, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   constexpr int RW = 32 / L, CV = C * V;
   static_assert(!ODD || V == 2, "ODD streams 16-byte units");
   static_assert(PF != 2 || V == 2, "the ring holds 16-byte units");
@@ -88,7 +89,7 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
   if constexpr (PF == 2) {
     if constexpr (V == 2) {
       // [ (kWarps + 1) Q doubles of reduction scratch, rounded up to 16 bytes | ring ]
-      const LaneRing<C> rg = lane_ring<C>(smem + (((kWarps + 1) * Q + 1) & ~1));
+      const LaneRing<C> rg = lane_ring<C>(smem + ring_offset_doubles((kWarps + 1) * Q));
       int64_t gi = grp;
 #pragma unroll
       for (int st = 0; st < kRingDepth; ++st, gi += gstr) {
@@ -198,17 +199,23 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
   finish_grid(vals, Q, (MODE == kModeLossGrad) ? 1 : 0, P.scale0, partials, out, ticket);
 }
 
+#ifndef SO_RING_MIN_L
+#define SO_RING_MIN_L 8
+#endif
+#ifndef SO_RING_K4
+#define SO_RING_K4 0
+#endif
 #ifndef SO_WIDE_RING
 #define SO_WIDE_RING 1      // 0: register prefetch everywhere; 1: ring where it measured faster (so_wide.cuh); 2: every 16-byte mapping
 #endif
 template <int FAM, int MODE, int L, int C, int V, bool ODD = false>
 int launch_lcv(const Shard& s, const Params& P, int want_grad) {
-  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= 16 && MODE == kModeLossGrad))) ? 2 : (C <= 4 ? 1 : 0);
+  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= SO_RING_MIN_L && (MODE == kModeLossGrad || SO_RING_K4)))) ? 2 : (C <= 4 ? 1 : 0);
   auto kern = k_wide<FAM, MODE, L, C, V, PF, ODD>;
   const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
   size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
   if (PF == 2) {
-    smem = sizeof(double) * (size_t)((((kWarps + 1) * Q) + 1) & ~1) + ring_bytes(C);
+    smem = sizeof(double) * (size_t)ring_offset_doubles((kWarps + 1) * Q) + ring_bytes(C);
     static bool attr[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -141,6 +141,10 @@ __device__ __forceinline__ void load_row(Frag<C, V>& fr, const double* __restric
 // 3.83 -> 3.28 ms per 2e7 rows, f = 128: 3.28 -> 2.93, f = 256: 3.35 -> 2.91 per 1e7) and K3 on odd f as much; K4 and the
 // even-f K3 lose 5-15 %, and with 4 lanes per row (f = 31 / 32: eight 64-byte pieces per LDGSTS) everything loses.  The
 // launchers therefore use it for K1 with L >= 16 and for K3 with odd f and L >= 16 only.
+// Also measured and not kept (profiles/r2_wide_long_pieces_ab.jsonl): ONE 16-byte unit per lane and as many lanes per row
+// as the row has units, so that a misaligned row costs one extra sector instead of one per 64-byte piece, with ring depths
+// 2, 4, 8 for the bytes in flight — f = 31: 4.74 -> 7.1 ms, f = 32: 4.21 -> 6.5: the 16-lane shuffle tree per two rows costs
+// more than the sectors saved.
 #ifndef SO_RING_DEPTH
 #define SO_RING_DEPTH 2      // power of two; 2 beat 4 and 8 on every shape it helps (profiles/r2_wide_ring_ab.jsonl)
 #endif
@@ -155,6 +159,14 @@ __device__ __forceinline__ void cpa8(void* dst, const void* src, bool valid) {
 }
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#ifndef SO_RING_ALIGN
+#define SO_RING_ALIGN 128    // bytes; the ring follows the reduction scratch in dynamic shared memory.  A warp's 32 x 16-byte
+                             // LDGSTS should cover four shared-memory lines, not five: with a 16-byte aligned base K1 ran
+                             // at 0.85-0.94 of HBM depending on the scratch size, with 128 bytes at 1.03-1.10
+#endif
+__host__ __device__ constexpr int ring_offset_doubles(int scratch_doubles) {
+  return (scratch_doubles + SO_RING_ALIGN / 8 - 1) / (SO_RING_ALIGN / 8) * (SO_RING_ALIGN / 8);
+}
 constexpr size_t ring_bytes(int C) { return (size_t)kRingDepth * kThreads * ((size_t)C * 16 + 8); }
 // this lane's slots: x[(stage * C + c) * kThreads], y[stage * kThreads]
 template <int C> struct LaneRing { double2* x; double* y; };

@@ -15,7 +15,7 @@ template <int FAM, int L, int C, int V, int KPL, int PF, bool ODD = false>      
 __global__ void __launch_bounds__(kThreads, 2)
 k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
             double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   constexpr int RW = 32 / L, CV = C * V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & (L - 1), r = lane / L;
@@ -67,7 +67,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
 
   if constexpr (PF == 2) {
     if constexpr (V == 2) {
-      const LaneRing<C> rg = lane_ring<C>(smem + (((kWarps + 1) * Q + 1) & ~1));
+      const LaneRing<C> rg = lane_ring<C>(smem + ring_offset_doubles((kWarps + 1) * Q));
       int64_t gi = grp;
 #pragma unroll
       for (int st = 0; st < kRingDepth; ++st, gi += gstr) {
@@ -138,17 +138,23 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
   finish_grid(vals, Q, k, P.scale0, partials, out, ticket);
 }
 
+#ifndef SO_RING_MIN_L
+#define SO_RING_MIN_L 8
+#endif
+#ifndef SO_RING_K3_EVEN
+#define SO_RING_K3_EVEN 1
+#endif
 #ifndef SO_WIDE_RING
 #define SO_WIDE_RING 1      // as in so_wide.cu
 #endif
 template <int FAM, int L, int C, int V, int KPL, bool ODD>
 int launch_one(const Shard& s, const Params& P) {
-  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= 16 && ODD))) ? 2 : (C <= 4 ? 1 : 0);
+  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= SO_RING_MIN_L && (ODD || SO_RING_K3_EVEN)))) ? 2 : (C <= 4 ? 1 : 0);
   auto kern = k_wide_line<FAM, L, C, V, KPL, PF, ODD>;
   const int Q = 2 * P.k;
   size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
   if (PF == 2) {
-    smem = sizeof(double) * (size_t)((((kWarps + 1) * Q) + 1) & ~1) + ring_bytes(C);
+    smem = sizeof(double) * (size_t)ring_offset_doubles((kWarps + 1) * Q) + ring_bytes(C);
     static bool attr[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
