@@ -424,16 +424,16 @@ def run_own(args):
                 traffic_at = tr.get("measured_at")
         except Exception:
             pass
-        # north_star's roofline is the SLOWER of bytes at HBM bandwidth and flops at FP64 peak; this kernel executes 45 FP64
+        # north_star's roofline is the SLOWER of bytes at HBM bandwidth and flops at FP64 peak; this kernel executes 42 FP64
         # instructions per observation (SASS of k_scalar<OpNormalEq<FamGaussExpBkg>>), which at the DFMA
         # rate measured on this pool (profiles/r1_fp64_peak.json) takes longer than its 16 bytes at the HBM rate
         fp64 = None
         try:
             pk = json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_peak.json")))
             dfma_per_s = float(pk["dfma_tflops_burst"]) * 1e12 / 2.0
-            instr = 45.0 * m
+            instr = 42.0 * m
             bound_ms = instr / dfma_per_s * 1e3
-            fp64 = {"fp64_instr_per_observation": 45, "dfma_peak_instr_per_s": dfma_per_s, "bound_ms_per_launch": bound_ms,
+            fp64 = {"fp64_instr_per_observation": 42, "dfma_peak_instr_per_s": dfma_per_s, "bound_ms_per_launch": bound_ms,
                     "hbm_bound_ms_per_launch": alg_bytes / (hbm_peak * 1e9) * 1e3,
                     "frac_of_fp64_bound": bound_ms / (kernel_ms_max / args.steps),
                     "note": "explanatory only; roofline.frac above is against HBM"}
