@@ -200,17 +200,14 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
 }
 
 #ifndef SO_RING_MIN_L
-#define SO_RING_MIN_L 8
-#endif
-#ifndef SO_RING_K4
-#define SO_RING_K4 0
+#define SO_RING_MIN_L 4      // lanes per row from which the ring is used (so_wide.cuh); K4 on odd f with 4 lanes per row stays on registers
 #endif
 #ifndef SO_WIDE_RING
 #define SO_WIDE_RING 1      // 0: register prefetch everywhere; 1: ring where it measured faster (so_wide.cuh); 2: every 16-byte mapping
 #endif
 template <int FAM, int MODE, int L, int C, int V, bool ODD = false>
 int launch_lcv(const Shard& s, const Params& P, int want_grad) {
-  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= SO_RING_MIN_L && (MODE == kModeLossGrad || SO_RING_K4)))) ? 2 : (C <= 4 ? 1 : 0);
+  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= SO_RING_MIN_L && (MODE == kModeLossGrad || L >= 8 || !ODD)))) ? 2 : (C <= 4 ? 1 : 0);
   auto kern = k_wide<FAM, MODE, L, C, V, PF, ODD>;
   const int Q = (MODE == kModeLossGrad) ? P.n + 1 : P.n;
   size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;

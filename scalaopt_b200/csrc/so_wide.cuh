@@ -137,10 +137,14 @@ __device__ __forceinline__ void load_row(Frag<C, V>& fr, const double* __restric
 // barrier (a lane reads back only what it copied itself, cp.async.wait_group orders that; y is the one shared value of a row),
 // and kRingDepth x 32 KB per SM are in flight.  A slot is refilled after its values were consumed (they are operands of the
 // step's FMAs), so the asynchronous write cannot overtake the read.
-// Measured (profiles/r2_wide_ring_ab.jsonl, one box): with 16 or 32 lanes per row (f >= ~64) K1 gains 11-15 % (f = 127:
-// 3.83 -> 3.28 ms per 2e7 rows, f = 128: 3.28 -> 2.93, f = 256: 3.35 -> 2.91 per 1e7) and K3 on odd f as much; K4 and the
-// even-f K3 lose 5-15 %, and with 4 lanes per row (f = 31 / 32: eight 64-byte pieces per LDGSTS) everything loses.  The
-// launchers therefore use it for K1 with L >= 16 and for K3 with odd f and L >= 16 only.
+// Measured (profiles/r2_wide_ring_*.jsonl, one box each).  First version, ring base wherever the reduction scratch ended
+// (16-byte aligned): wins with 16/32 lanes per row for K1 (f = 127: 3.83 -> 3.28 ms per 2e7 rows) but erratic (0.85-0.94 of
+// HBM depending on the scratch size), losses for K4, the even-f K3 and everything with 4 lanes per row.  With the base
+// 128-byte aligned (a warp's 32 x 16-byte LDGSTS covers four shared-memory lines instead of five) it wins nearly
+// everywhere: K1 f = 32: 4.21 -> 3.76 ms per 1e8 rows (0.96 -> 1.07 of the HBM copy figure; the read-only stream ceiling is
+// 1.09), f = 31: 4.73 -> 4.38 (0.89), f = 47: 0.67 -> 0.93, f = 64: 0.95 -> 1.09, f = 128 / 256: 0.94 -> 1.10; K3 alike; K4
+// f = 47: 0.77 -> 0.97, f = 64: 1.01 -> 1.13, f = 128: 1.00 -> 1.10, f = 32: 1.02 -> 1.08.  The one loser left is K4 on odd f
+// with 4 lanes per row (f = 31: 4.13 -> 4.30), which stays on the register prefetch, as do the 1- and 2-lane mappings.
 // Also measured and not kept (profiles/r2_wide_long_pieces_ab.jsonl): ONE 16-byte unit per lane and as many lanes per row
 // as the row has units, so that a misaligned row costs one extra sector instead of one per 64-byte piece, with ring depths
 // 2, 4, 8 for the bytes in flight — f = 31: 4.74 -> 7.1 ms, f = 32: 4.21 -> 6.5: the 16-lane shuffle tree per two rows costs

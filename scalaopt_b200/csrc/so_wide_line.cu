@@ -139,7 +139,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
 }
 
 #ifndef SO_RING_MIN_L
-#define SO_RING_MIN_L 8
+#define SO_RING_MIN_L 4
 #endif
 #ifndef SO_RING_K3_EVEN
 #define SO_RING_K3_EVEN 1
