@@ -139,7 +139,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
 }
 
 #ifndef SO_RING_MIN_L
-#define SO_RING_MIN_L 4
+#define SO_RING_MIN_L 4      // logistic with 4 lanes per row stays on registers: k = 4 / 8 step sizes 4.46 / 6.10 -> 4.71 / 6.82 ms with the ring
 #endif
 #ifndef SO_RING_K3_EVEN
 #define SO_RING_K3_EVEN 1
@@ -149,7 +149,7 @@ k_wide_line(const double* __restrict__ X, const double* __restrict__ y, int64_t 
 #endif
 template <int FAM, int L, int C, int V, int KPL, bool ODD>
 int launch_one(const Shard& s, const Params& P) {
-  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= SO_RING_MIN_L && (ODD || SO_RING_K3_EVEN)))) ? 2 : (C <= 4 ? 1 : 0);
+  constexpr int PF = (V == 2 && C <= 8 && (SO_WIDE_RING == 2 || (SO_WIDE_RING == 1 && L >= SO_RING_MIN_L && (ODD || SO_RING_K3_EVEN) && (L >= 8 || FAM == kLinear)))) ? 2 : (C <= 4 ? 1 : 0);
   auto kern = k_wide_line<FAM, L, C, V, KPL, PF, ODD>;
   const int Q = 2 * P.k;
   size_t smem = sizeof(double) * (size_t)(kWarps + 1) * Q;
