@@ -564,7 +564,7 @@ int run_eval(so_dataset* ds, Kind kind, int family, const double* p, const doubl
   // the two-exponential family's K1-K4 and the likelihood kernel drop their per-row exp range check when the shard's inputs allow it: one
   // 8 B/row pass per data-set state (not per evaluation) finds their range
   const bool wants_range = ds->f == 1 && (nll ? true : family == SO_FAMILY_GAUSS_EXPBKG &&
-                           (kind == kNormalEq || (kind == kLossGrad && want_grad) || kind == kHessVec || kind == kLine));
+                           (kind == kNormalEq || kind == kLossGrad || kind == kHessVec || kind == kLine));
   for (int g = 0; g < G && wants_range; ++g) {
     Device& dv = ctx->devs[g];
     ShardMem& sm = ds->shards[g];

@@ -740,6 +740,14 @@ int launch_family(Kind kind, const Shard& s, const double* p, const double* d, c
         for (int i = 0; i < N; ++i) a.scale[1 + i] = -pre.D[i];
         return launch_op_cfg<Op, kThreads, SO_K1_MINB, 0, SO_K1_RPT>(s, a);
       }
+      // loss only (trial points of Levenberg-Marquardt, line searches): the same two variants as with the gradient
+      if constexpr (requires { Fam::args_in_range(pre, 0.0, 0.0); }) {
+        if (s.has_range && Fam::args_in_range(pre, s.tmin, s.tmax)) {
+          using Opn = OpLossGrad<Fam, false, SO_K1_NC_G>;
+          typename Opn::Args an; an.pre = pre; an.scale[0] = 0.5;
+          return launch_op_cfg<Opn, kThreads, SO_K1_MINB, 0, SO_K1_RPT, false>(s, an);
+        }
+      }
 #ifndef SO_SCALAR_MINIMAL
       using Op = OpLossGrad<Fam, false>;
       typename Op::Args a; a.pre = pre; a.scale[0] = 0.5;
