@@ -2,12 +2,13 @@
 // without intercept and logistic regression, f inputs per observation, row-major X[m x f] + y[m].
 //
 // Thread mapping ("L lanes per row"): a warp covers 32/L consecutive rows per step; lane (r, q) = (lane / L,
-// lane % L) holds columns (c*L + q)*V + v, c < C, v < V of row r in registers, loaded straight from global
-// memory with 64- or 128-bit streaming loads (V = 1 or 2).  Every 32-byte sector of X is requested exactly
-// once; a row's dot product is finished with log2(L) shuffle steps inside the row's L lanes, the per-row
-// scalar work (residual / sigmoid / loss) is done redundantly by those L lanes, and every lane accumulates
-// the gradient components of its own columns.  Nothing is staged through shared memory: the only reuse
-// of a row is register-level (dot product, then rank-1 update with the same registers).
+// lane % L) holds the 16-byte units c*L + q, c < C, of row r in registers (V = 2 doubles per unit; odd row lengths
+// as aligned units, see ODD below).  A row's dot product is finished with log2(L) shuffle steps inside the row's L
+// lanes, the per-row scalar work (residual / sigmoid / loss) is done redundantly by those L lanes, and every lane
+// accumulates the gradient components of its own columns: the only reuse of a row is register-level (dot product,
+// then rank-1 update with the same registers).  How the units get into the registers: from 4 lanes per row on
+// through a lane-private cp.async ring in shared memory (below), with 1-2 lanes per row by 128-bit streaming
+// loads with the next row group prefetched in registers.
 #pragma once
 #include "so_device.cuh"
 #include "so_internal.h"
