@@ -200,6 +200,9 @@ k_wide(const double* __restrict__ X, const double* __restrict__ y, int64_t rows,
   finish_grid(vals, Q, (MODE == kModeLossGrad) ? 1 : 0, P.scale0, partials, out, ticket);
 }
 
+#ifndef SO_SMALL_MAX_N
+#define SO_SMALL_MAX_N 12
+#endif
 #ifndef SO_RING_MIN_L
 #define SO_RING_MIN_L 4      // lanes per row from which the ring is used (so_wide.cuh); K4 on odd f with 4 lanes per row stays on registers
 #endif
@@ -235,12 +238,15 @@ int launch_lcv(const Shard& s, const Params& P, int want_grad) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// n <= 8: one thread per observation (K1 and K4).  With 8-72 bytes per row the lanes-per-row mapping above
+// n <= 12: one thread per observation (K1 and K4).  With 8-96 bytes per row the lanes-per-row mapping above
 // spends its time in shuffles (n = 4: 0.69 of the HBM roofline); a thread that keeps its whole row and n + 1
-// accumulators in registers streams at the rate of k_gram_small (>= 1.0).
+// accumulators in registers streams at the rate of k_gram_small (>= 1.0).  Up to n = 8 since round 1; 9 <= n <= 12
+// (two blocks per SM, <= 104 registers) since the end of round 2 (profiles/r2_small17_ab.jsonl): f = 9: K1 0.64 -> 1.01 of
+// the HBM copy figure, K4 0.68 -> 1.10, K3 0.59 -> 1.0; f = 10: 0.72 -> 0.97 / 1.07 / 0.98.  Not beyond: at f = 16 the rows
+// of a warp are 128 bytes apart and every load instruction touches 32 lines (0.96 -> 0.37), f = 15 gains nothing.
 // ---------------------------------------------------------------------------------------------------
 template <int FAM, int NP, int ICPT, int MODE>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, NP <= 8 ? 4 : 2)
 k_small(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
         int want_grad, double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   constexpr int F = NP - ICPT, Q = (MODE == kModeLossGrad) ? NP + 1 : NP, base = (MODE == kModeLossGrad) ? 1 : 0;
@@ -303,6 +309,7 @@ int launch_small(const Shard& s, const Params& P, int want_grad) {
   switch (P.n) {
     case 1: return P.icpt ? SO_EUNSUPPORTED : launch_small_np<FAM, MODE, 1, 0>(s, P, want_grad);
     SO_CASE(2) SO_CASE(3) SO_CASE(4) SO_CASE(5) SO_CASE(6) SO_CASE(7) SO_CASE(8)
+    SO_CASE(9) SO_CASE(10) SO_CASE(11) SO_CASE(12)
   }
 #undef SO_CASE
   return SO_EUNSUPPORTED;
@@ -328,6 +335,11 @@ int launch_mapped(const Shard& s, const Params& P, int want_grad) {
 }  // namespace
 
 int launch_line(const Shard& s, int fam, const Params& P);                      // so_wide_line.cu
+// rows of up to this many parameters go to the thread-per-row kernels (k_small, k_small_line)
+int small_max_n() {
+  static const int v = [] { const char* e = getenv("SCALAOPT_SMALL_MAX_N"); const int x = e ? atoi(e) : SO_SMALL_MAX_N; return x < 8 ? 8 : (x > 12 ? 12 : x); }();
+  return v;
+}
 int launch_gram(const Shard& s, int fam, const Params& P);                      // so_gram.cu
 int launch_qr(const Shard& s, int fam, const Params& P);                        // so_wide_qr.cu (n <= 8)
 int launch_qr_wide(const Shard& s, int fam, const Params& P);                   // so_wide_qrw.cu (8 < n <= 47)
@@ -358,13 +370,13 @@ int launch_wide(Kind kind, const Shard& s, int family, const double* p, const do
   P.scale0 = (fam == kLinear) ? 0.5 : 1.0;
   switch (kind) {
     case kLossGrad:
-      if (n <= 8) return fam == kLinear ? launch_small<kLinear, kModeLossGrad>(s, P, want_grad)
+      if (n <= small_max_n()) return fam == kLinear ? launch_small<kLinear, kModeLossGrad>(s, P, want_grad)
                                         : launch_small<kLogistic, kModeLossGrad>(s, P, want_grad);
       return fam == kLinear ? launch_mapped<kLinear, kModeLossGrad>(s, P, want_grad)
                             : launch_mapped<kLogistic, kModeLossGrad>(s, P, want_grad);
     case kHessVec:
       P.scale0 = 1.0;
-      if (n <= 8) return fam == kLinear ? launch_small<kLinear, kModeHessVec>(s, P, 1)
+      if (n <= small_max_n()) return fam == kLinear ? launch_small<kLinear, kModeHessVec>(s, P, 1)
                                         : launch_small<kLogistic, kModeHessVec>(s, P, 1);
       return fam == kLinear ? launch_mapped<kLinear, kModeHessVec>(s, P, 1)
                             : launch_mapped<kLogistic, kModeHessVec>(s, P, 1);

@@ -9,6 +9,7 @@
 
 namespace so {
 namespace wide {
+int small_max_n();          // so_wide.cu
 namespace {
 
 template <int FAM, int L, int C, int V, int KPL, int PF, bool ODD = false>      // PF, ODD: as in k_wide (so_wide.cu, so_wide.cuh)
@@ -187,7 +188,7 @@ int launch_kpl(const Shard& s, const Params& P) {
 
 // n <= 8: one thread per observation, KB step sizes in registers (see k_small in so_wide.cu)
 template <int FAM, int NP, int ICPT, int KB>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, NP <= 8 ? 4 : 2)
 k_small_line(const double* __restrict__ X, const double* __restrict__ y, int64_t rows, const __grid_constant__ Params P,
              double* __restrict__ partials, double* __restrict__ out, unsigned int* ticket) {
   constexpr int F = NP - ICPT, Q = 2 * KB;
@@ -245,6 +246,11 @@ int launch_small_line_kb(const Shard& s, const Params& P) {
 
 template <int FAM, int NP, int ICPT>
 int launch_small_line_np(const Shard& s, const Params& P) {
+  if constexpr (NP > 8) {      // fewer instantiations for the wider rows
+    if (P.k <= 2) return launch_small_line_kb<FAM, NP, ICPT, 2>(s, P);
+    if (P.k <= 4) return launch_small_line_kb<FAM, NP, ICPT, 4>(s, P);
+    return launch_small_line_kb<FAM, NP, ICPT, 8>(s, P);
+  }
   if (P.k <= 1) return launch_small_line_kb<FAM, NP, ICPT, 1>(s, P);
   if (P.k <= 2) return launch_small_line_kb<FAM, NP, ICPT, 2>(s, P);
   if (P.k <= 4) return launch_small_line_kb<FAM, NP, ICPT, 4>(s, P);
@@ -257,6 +263,7 @@ int launch_small_line(const Shard& s, const Params& P) {
   switch (P.n) {
     case 1: return P.icpt ? SO_EUNSUPPORTED : launch_small_line_np<FAM, 1, 0>(s, P);
     SO_CASE(2) SO_CASE(3) SO_CASE(4) SO_CASE(5) SO_CASE(6) SO_CASE(7) SO_CASE(8)
+    SO_CASE(9) SO_CASE(10) SO_CASE(11) SO_CASE(12)
   }
 #undef SO_CASE
   return SO_EUNSUPPORTED;
@@ -283,7 +290,7 @@ int launch_mapped(const Shard& s, const Params& P) {
 
 int launch_line(const Shard& s, int fam, const Params& P) {
   if (P.k < 1 || P.k > 8) return SO_EINVAL;
-  if (P.n <= 8) return fam == kLinear ? launch_small_line<kLinear>(s, P) : launch_small_line<kLogistic>(s, P);
+  if (P.n <= small_max_n()) return fam == kLinear ? launch_small_line<kLinear>(s, P) : launch_small_line<kLogistic>(s, P);
   return fam == kLinear ? launch_mapped<kLinear>(s, P) : launch_mapped<kLogistic>(s, P);
 }
 
