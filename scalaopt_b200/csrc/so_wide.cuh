@@ -246,6 +246,9 @@ __device__ __forceinline__ void finish_grid(const double* vals, int Q, int nscal
   }
 }
 
+#ifndef SO_MAP_4X5
+#define SO_MAP_4X5 1
+#endif
 // lane-mapping choice for f inputs
 struct Mapping { int L, C, V; };
 inline Mapping choose_mapping(int f) {
@@ -257,6 +260,9 @@ inline Mapping choose_mapping(int f) {
   while (m.L < 32 && units > m.L * 4) m.L *= 2;
   if (units > m.L * m.C) m.C = 8;
   if (units > m.L * m.C) m.C = 16;
+  // 17-20 units (f = 33 .. 40): 4 lanes x 5 units instead of 8 lanes x 4 with half of them idle (cfg2's shape plus an
+  // intercept column or a few features more: 0.51 of HBM with the 8-lane mapping)
+  if (SO_MAP_4X5 && m.V == 2 && units > 16 && units <= 20) { m.L = 4; m.C = 5; }
   return m;
 }
 
