@@ -263,6 +263,11 @@ inline Mapping choose_mapping(int f) {
   // 17-20 units (f = 33 .. 40): 4 lanes x 5 units instead of 8 lanes x 4 with half of them idle (cfg2's shape plus an
   // intercept column or a few features more: 0.51 of HBM with the 8-lane mapping)
   if (SO_MAP_4X5 && m.V == 2 && units > 16 && units <= 20) { m.L = 4; m.C = 5; }
+  // the same gap one and two octaves up: 33-40 units (f = 65 .. 80) -> 8 x 5, 65-80 units (f = 129 .. 160) -> 16 x 5,
+  // 129-160 units (f = 257 .. 320) -> 32 x 5 instead of 32 x 8
+  if (SO_MAP_4X5 && m.V == 2 && units > 32 && units <= 40) { m.L = 8; m.C = 5; }
+  if (SO_MAP_4X5 && m.V == 2 && units > 64 && units <= 80) { m.L = 16; m.C = 5; }
+  if (SO_MAP_4X5 && m.V == 2 && units > 128 && units <= 160) { m.L = 32; m.C = 5; }
   return m;
 }
 

@@ -274,14 +274,14 @@ int launch_mapped(const Shard& s, const Params& P) {
   if ((P.f & 1) && P.f >= 9) {
     const Mapping mo = choose_mapping(P.f + 1);
 #define SO_ODD(LL, CC) if (mo.L == LL && mo.C == CC && mo.V == 2) return launch_kpl<FAM, LL, CC, 2, true>(s, P);
-    SO_ODD(2, 4) SO_ODD(4, 4) SO_ODD(4, 5) SO_ODD(8, 4) SO_ODD(16, 4) SO_ODD(32, 4) SO_ODD(32, 8)
+    SO_ODD(2, 4) SO_ODD(4, 4) SO_ODD(4, 5) SO_ODD(8, 4) SO_ODD(8, 5) SO_ODD(16, 4) SO_ODD(16, 5) SO_ODD(32, 4) SO_ODD(32, 5) SO_ODD(32, 8)
 #undef SO_ODD
   }
   const Mapping m = choose_mapping(P.f);
 #define SO_CASE(LL, CC, VV) if (m.L == LL && m.C == CC && m.V == VV) return launch_kpl<FAM, LL, CC, VV>(s, P);
   // V = 1 (64-bit loads) has no caller left: odd f >= 9 streams aligned 16-byte units (ODD above), n <= 8 is k_small
-  SO_CASE(1, 4, 2) SO_CASE(2, 4, 2) SO_CASE(4, 4, 2) SO_CASE(4, 5, 2) SO_CASE(8, 4, 2) SO_CASE(16, 4, 2) SO_CASE(32, 4, 2)
-  SO_CASE(32, 8, 2)
+  SO_CASE(1, 4, 2) SO_CASE(2, 4, 2) SO_CASE(4, 4, 2) SO_CASE(4, 5, 2) SO_CASE(8, 4, 2) SO_CASE(8, 5, 2) SO_CASE(16, 4, 2) SO_CASE(16, 5, 2) SO_CASE(32, 4, 2)
+  SO_CASE(32, 5, 2) SO_CASE(32, 8, 2)
 #undef SO_CASE
   return SO_EUNSUPPORTED;
 }

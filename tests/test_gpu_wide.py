@@ -21,6 +21,9 @@ CASES = [
     ("LINEAR_NOINT", 2), ("LINEAR_NOINT", 8), ("LINEAR_NOINT", 46), ("LINEAR_NOINT", 128), ("LINEAR_NOINT", 256),
     ("LINEAR_NOINT", 511), ("LINEAR_NOINT", 512),
     ("LOGISTIC", 2), ("LOGISTIC", 7), ("LOGISTIC", 32), ("LOGISTIC", 33), ("LOGISTIC", 64),
+    # 5 units per lane (17-20, 33-40, 65-80, 129-160 units per row), even and odd f; thread-per-row up to n = 12
+    ("LINEAR", 35), ("LINEAR_NOINT", 40), ("LINEAR_NOINT", 72), ("LOGISTIC", 79), ("LINEAR", 150), ("LINEAR_NOINT", 157),
+    ("LINEAR_NOINT", 300), ("LINEAR", 319), ("LINEAR", 9), ("LINEAR_NOINT", 12), ("LOGISTIC", 11),
 ]
 
 

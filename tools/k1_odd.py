@@ -6,7 +6,7 @@ from scalaopt_b200 import native
 HBM = 6554.2
 with native.Context(1) as ctx:
     only = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else None
-    for name, f, m in (("linear", 31, 100_000_000), ("linear_noint", 32, 100_000_000), ("linear", 127, 20_000_000), ("linear_noint", 128, 20_000_000), ("logistic", 33, 80_000_000), ("linear", 35, 80_000_000), ("linear_noint", 40, 80_000_000), ("logistic", 32, 100_000_000), ("linear_noint", 256, 10_000_000), ("linear", 47, 60_000_000), ("linear_noint", 48, 60_000_000), ("linear", 63, 50_000_000), ("linear_noint", 64, 50_000_000), ("linear", 9, 200_000_000), ("linear", 10, 200_000_000), ("logistic", 12, 200_000_000), ("linear_noint", 16, 200_000_000), ("linear", 15, 200_000_000)):
+    for name, f, m in (("linear", 31, 100_000_000), ("linear_noint", 32, 100_000_000), ("linear", 127, 20_000_000), ("linear_noint", 128, 20_000_000), ("logistic", 33, 80_000_000), ("linear", 35, 80_000_000), ("linear_noint", 40, 80_000_000), ("logistic", 32, 100_000_000), ("linear_noint", 256, 10_000_000), ("linear", 47, 60_000_000), ("linear_noint", 48, 60_000_000), ("linear", 63, 50_000_000), ("linear_noint", 64, 50_000_000), ("linear_noint", 72, 40_000_000), ("linear", 150, 20_000_000), ("linear_noint", 300, 10_000_000), ("linear", 9, 200_000_000), ("linear", 10, 200_000_000), ("logistic", 12, 200_000_000), ("linear_noint", 16, 200_000_000), ("linear", 15, 200_000_000)):
         if only and f not in only or (only and name == 'logistic' and f == 33 and 33 not in only):
             continue
         fam = {"linear_noint": native.LINEAR_NOINT, "linear": native.LINEAR, "logistic": native.LOGISTIC}[name]
