@@ -82,7 +82,7 @@ soh_objective* soh_objective_gpu(so_ctx* ctx, so_dataset* ds, int f, int family,
 
 /* GpuMSEFunction.jacobianAndResidualsMatrix from so_eval_qr (on-device Householder TSQR of [J | r])
  * instead of so_eval_normal_eq + Cholesky: one pass either way, about 2.5x the kernel time at n = 5, and the condition
- * number of J is not squared.  Single-input families. */
+ * number of J is not squared.  Single-input families; linear (+- intercept) and logistic rows up to n = 63. */
 int soh_objective_use_tsqr(soh_objective* objective, int on);
 
 /* Levenberg-Marquardt trial-point losses from a K2 pass whose sums are kept for the Jacobian request that follows an
@@ -115,6 +115,11 @@ int soh_zoom_step_length(soh_objective* f, const double* x, const double* d, int
  * R is n*n row-major with R(i,j) of QR.scala:55-67. */
 int soh_qr(const double* ab, int64_t m, int n, int pivoting, double* R, double* qtb, int32_t* ipvt, double* acnorms,
            double* bnorm, double* solution);
+
+/* linear.lm(GpuDataSet(ds), addOrigin) (linear/package.scala:54-63): least-squares solution beta[f + addOrigin] of
+ * (1, x) beta = y through the reference's QR(...).solution on the (n+1)-row system of one K2 pass (use_tsqr: of the
+ * on-device Householder TSQR, f + addOrigin <= 63).  Failure(e) of the reference's Try = a non-zero return code. */
+int soh_gpu_lm(so_ctx* ctx, so_dataset* ds, int f, int add_origin, int use_tsqr, double* beta);
 
 const char* soh_last_error(void);
 

@@ -24,7 +24,7 @@ OK, MAX_ITER, ILLEGAL_ARG, GPU_ERROR, ERROR = range(5)
 EXPORTS = ["soh_default_config", "soh_objective_from_callbacks", "soh_objective_gpu", "soh_objective_use_tsqr", "soh_objective_set_decay", "soh_objective_speculate", "soh_objective_gpu_nll", "soh_objective_free",
            "soh_objective_counters", "soh_objective_apply", "soh_objective_gradient", "soh_objective_dirder",
            "soh_objective_dir_hessian", "soh_objective_jacobian_rows", "soh_minimize", "soh_zoom_step_length",
-           "soh_qr", "soh_last_error"]
+           "soh_qr", "soh_gpu_lm", "soh_last_error"]
 
 
 class MaxIterException(RuntimeError):
@@ -100,6 +100,7 @@ def load():
     L.soh_minimize.argtypes = [C.c_int, vp, _dp, C.c_int, C.POINTER(Config), _dp, C.POINTER(Result)]
     L.soh_zoom_step_length.argtypes = [vp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.POINTER(Config), _dp]
     L.soh_qr.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int32), _dp, _dp, _dp]
+    L.soh_gpu_lm.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, _dp]
     L.soh_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -270,6 +271,16 @@ def qr(ab, n, pivoting=True):
     if rc != OK:
         _raise(rc)
     return {"R": R, "qtb": qtb, "ipvt": ipvt, "acNorms": acn, "bNorm": bn.value, "solution": sol}
+
+
+def gpu_lm(ctx: native.Context, ds: native.Dataset, add_origin: bool = True, tsqr: bool = False):
+    """linear.lm(GpuDataSet(ds), addOrigin) (linear/package.scala:54-63): beta of (1, x) beta = y in the least-squares sense from
+    one pass over the resident rows (K2, or the on-device TSQR) + the reference's QR(...).solution on n+1 rows."""
+    beta = np.zeros(ds.f + (1 if add_origin else 0))
+    rc = load().soh_gpu_lm(ctx._h, ds._h, ds.f, int(add_origin), int(tsqr), _ptr(beta))
+    if rc != OK:
+        _raise(rc)
+    return beta
 
 
 def bench_lm(ctx, ds, family, x0, barrier=lambda: None, max_over_ranks=lambda v: v, repeats=3, speculate=True, runs=4):

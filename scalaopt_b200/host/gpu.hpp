@@ -330,6 +330,20 @@ class GpuMSEFunction : public MSEFunction {
   }
 };
 
+// linear.lm(data, addOrigin) (linear/package.scala:54-63): the least-squares solution of a beta = y through
+// QR(rows (a | y), n).solution, a = (1, x) with the origin.  On a GpuDataSet the m rows never reach the host: at p = 0 the
+// linear family's Jacobian/residual rows are s_i (-a_i | y_i), s_i = sign(y_i), so the (n+1)-row system of
+// GpuMSEFunction carries the Gram of (-a | y) and the reference's own QR(...).solution on it is -beta.  One pass over the
+// data (K2, or the on-device Householder TSQR with use_tsqr) against the 2n+1 passes of QR.apply.
+inline Vec gpu_lm(const std::shared_ptr<GpuDataSet>& data, bool add_origin = true, bool use_tsqr = false) {
+  const int n = data->f + (add_origin ? 1 : 0);
+  GpuMSEFunction fn(data, add_origin ? SO_FAMILY_LINEAR : SO_FAMILY_LINEAR_NOINT, n);
+  fn.use_tsqr = use_tsqr;
+  Vec beta = QR::solve(*fn.jacobianAndResidualsMatrix(Vec(n, 0.0)), n);
+  for (double& b : beta) b = -b;
+  return beta;
+}
+
 // negLogLikelihood(pdf, data) _ as an objective (std-apps/.../stats/package.scala:74-103).  The reference hands this plain
 // closure to an optimizer through `toFunctionWoGradient` (core/.../package.scala:74-77), i.e. as an
 // ObjectiveFunctionFiniteDiffDerivatives: derivatives are forward differences of the (GPU-evaluated) objective.

@@ -250,6 +250,14 @@ extern "C" int soh_zoom_step_length(soh_objective* f, const double* x, const dou
   });
 }
 
+extern "C" int soh_gpu_lm(so_ctx* ctx, so_dataset* ds, int f, int add_origin, int use_tsqr, double* beta) {
+  if (!ctx || !ds || f < 1 || !beta) { g_err = "soh_gpu_lm: bad arguments"; return SOH_ILLEGAL_ARG; }
+  return guarded([&] {
+    const Vec b = gpu_lm(std::make_shared<GpuDataSet>(ctx, ds, f, false), add_origin != 0, use_tsqr != 0);
+    std::copy(b.begin(), b.end(), beta);
+  });
+}
+
 extern "C" int soh_qr(const double* ab, int64_t m, int n, int pivoting, double* R, double* qtb, int32_t* ipvt, double* acnorms,
                       double* bnorm, double* solution) {
   if (n < 1 || m < 0 || (m > 0 && !ab)) return SOH_ILLEGAL_ARG;

@@ -163,3 +163,34 @@ def test_gpu_dataset_mirrors_the_dataset_trait(native, oracle, host, gpu_ctx):
     Xr, yr = ds.read(10, 5)
     np.testing.assert_array_equal(Xr, X[10:15]); np.testing.assert_array_equal(yr, y[10:15])
     ds.free()
+
+
+@pytest.mark.parametrize("tsqr", [False, True])
+@pytest.mark.parametrize("case", ["linear_spec", "no_origin", "wide"])
+def test_linear_lm_on_the_gpu(native, oracle, host, gpu_ctx, case, tsqr):
+    """linear.lm(data, addOrigin) (linear/package.scala:54-63; LinearSpec.scala:32-54) on a GpuDataSet: one pass over the
+    resident rows (K2 / TSQR) + the reference's QR.solution on n+1 rows, against the reference's 2n+1-pass QR of the
+    materialised rows (oracle) and, for the spec case, the spec's own +-0.5 on every coefficient."""
+    if case == "linear_spec":
+        (X, y, truth), _ = lm_spec_data(oracle)
+        origin = True
+    elif case == "no_origin":
+        truth = np.array([0.5, -1.0, 2.0, 0.25])
+        X, y = oracle.generate(oracle.LINEAR_NOINT, 100_003, 4, truth)      # y takes both signs
+        origin = False
+    else:
+        truth = np.concatenate([[3.0], np.linspace(-1.0, 1.0, 32)])            # cfg5's n = 33 shape (with origin)
+        X, y = oracle.generate(oracle.LINEAR, 20_001, 32, truth)
+        origin = True
+    n = X.shape[1] + int(origin)
+    ds = native.Dataset(gpu_ctx, len(y), X.shape[1]).append(X, y)
+    launches0 = gpu_ctx.stats().total_launches
+    beta = host.gpu_lm(gpu_ctx, ds, add_origin=origin, tsqr=tsqr)
+    assert gpu_ctx.stats().total_launches - launches0 == 1                     # one pass over the data
+    a = np.hstack([np.ones((len(y), 1)), X]) if origin else X
+    beta_ref = oracle.qr(np.hstack([a, y[:, None]]), n).solution()              # lm(data) as the reference computes it
+    assert beta.size == n
+    np.testing.assert_allclose(beta, beta_ref, rtol=1e-9, atol=1e-9)
+    if case == "linear_spec":
+        np.testing.assert_allclose(beta, truth, rtol=0, atol=0.5)              # LinearSpec.scala:47-49
+    ds.free()

@@ -1,7 +1,7 @@
 """CPU tests of the host-side mirror (libscalaopt_host.so): the reference's specs, re-run against the restated
 optimizers with the CPU oracle (or plain closures) as the objective.  These read like the reference's own tests:
 QRSpec, BFGSSpec / ConjugateGradientSpec / NewtonCGSpec / SteihaugCGSpec, StrongWolfeSpec, LevenbergMarquardtSpec,
-FFNeuralNetworkTrainerSpec (logistic regression by BFGS)."""
+FFNeuralNetworkTrainerSpec (logistic regression by BFGS), LinearSpec."""
 import json
 import os
 
@@ -52,6 +52,31 @@ def test_host_qr_equals_oracle_qr(host, oracle):
         np.testing.assert_array_equal(a["qtb"], b.qtb)
         np.testing.assert_array_equal(a["solution"], b.solution())
         assert list(a["ipvt"]) == list(b.ipvt)
+
+
+def test_linear_spec_lm_by_qr(host, oracle):
+    """LinearSpec.scala:32-54: `lm(data)` = QR(rows (1, x | y), n).solution (linear/package.scala:54-63) on 1000 rows of 10
+    uniform inputs from Random(12345), truth (80, 0, 1, ..., 9) + N(0,1) noise, every coefficient within 0.5.  Both
+    restatements of QR.apply (the oracle's and the host mirror's) and LAPACK's least-squares solution."""
+    (X, y, truth), _ = lm_spec_data(oracle)                    # same generator and draw order as LinearSpec.scala:34-44
+    ab = np.hstack([np.ones((len(y), 1)), X, y[:, None]])      # Input(1.0) +: row.x, row.y(0)   package.scala:58-60
+    n = X.shape[1] + 1
+    beta_oracle = oracle.qr(ab, n).solution()                  # pivoting defaults to true, QR.scala:131-134
+    beta_host = host.qr(ab, n)["solution"]
+    assert beta_oracle.size == n
+    np.testing.assert_allclose(beta_oracle, truth, rtol=0, atol=0.5)          # the spec's own assertion
+    np.testing.assert_array_equal(beta_host, beta_oracle)
+    beta_lapack = np.linalg.lstsq(ab[:, :n], y, rcond=None)[0]
+    np.testing.assert_allclose(beta_oracle, beta_lapack, rtol=0, atol=1e-10)
+    # without the origin column (addOrigin = false) the 80.0 has nowhere to go: the call still succeeds, n = 10
+    assert oracle.qr(np.hstack([X, y[:, None]]), n - 1).solution().size == n - 1
+    # what gpu_lm (host/gpu.hpp) does with a GpuDataSet, from the oracle's sums instead of a K2 pass: at p = 0 the linear
+    # family's rows are sign(y) (-a | y), the (n+1)-row system has their Gram, and QR(...).solution on it is -beta
+    rows = compressed_rows(oracle, oracle.LINEAR, X, y, np.zeros(n))
+    np.testing.assert_allclose(-host.qr(rows, n)["solution"], beta_oracle, rtol=0, atol=1e-9)
+    ys = y - 84.0                                              # both signs of y among the rows
+    rows = compressed_rows(oracle, oracle.LINEAR, X, ys, np.zeros(n))
+    np.testing.assert_allclose(-host.qr(rows, n)["solution"], np.linalg.lstsq(ab[:, :n], ys, rcond=None)[0], rtol=0, atol=1e-9)
 
 
 X0 = np.array([0.5, 2.0])
