@@ -7,7 +7,7 @@ BASELINE config 3: Levenberg-Marquardt Gaussian-peak + exponential-background fi
 
   python bench.py --gpus 1 --steps K --warmup W              own arm (this repo's CUDA path through the C ABI)
   python bench.py --impl reference ...                       the reference's algorithm on the host cores
-  torchrun --nproc-per-node N bench.py --gpus N ...          one rank per GPU, NCCL all-reduce per evaluation
+  torchrun --nproc-per-node N bench.py --gpus N ...          one rank per GPU, cross-GPU sum inside the evaluation kernel
 
 One "step" = one evaluation of (loss, J^T r, J^T J) over the whole resident data set at a fresh parameter
 vector.  `value` is timed with the observations already in HBM; `e2e` re-ingests the observations from

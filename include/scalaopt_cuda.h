@@ -183,8 +183,9 @@ int so_dataset_slice(so_dataset* ds, int64_t begin, int64_t end, so_dataset** vi
 void so_dataset_free(so_dataset* ds);
 
 /* ---------------------------------------------------------------------------------------------
- * Evaluation  —  one pass over the resident observations per call, one all-reduce of the small
- * partial buffer when the context spans several GPUs (replaces `DataSet.aggregate`, DataSet.scala:49)
+ * Evaluation  —  one pass over the resident observations per call; when the context spans several GPUs the small
+ * result is summed across them by the evaluation kernel's folding block over NVLink peer memory, in rank order
+ * (NCCL all-reduce only above 16384 doubles).  Replaces `DataSet.aggregate`, DataSet.scala:49
  * ------------------------------------------------------------------------------------------- */
 
 /* K1. loss and gradient in one fused pass.
@@ -244,7 +245,7 @@ typedef struct so_call_stats {
   int64_t rows;            /* observations streamed by the last so_eval_* (this process) */
   int64_t bytes;           /* algorithmic HBM bytes of that pass: rows * 8 * (f+1) */
   double  kernel_ms;       /* CUDA-event time of the evaluation kernel (max over this process's GPUs) */
-  double  device_ms;       /* kernel + all-reduce + result copy, CUDA events on the evaluation stream */
+  double  device_ms;       /* kernel incl. cross-GPU sum and host delivery (or + all-reduce + result copy), CUDA events on the evaluation stream */
   int64_t launches;        /* kernels launched by the last call (all GPUs of this process) */
   int64_t total_launches;  /* kernels launched since so_init */
   int64_t total_evals;     /* so_eval_* calls since so_init */

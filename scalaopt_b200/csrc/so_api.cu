@@ -2,10 +2,11 @@
 // sets, the four evaluation entry points and the cross-GPU sum.
 //
 // Per evaluation and per GPU: ONE kernel launch (parameters travel in the kernel argument buffer, the
-// per-block partials are folded by the last block of the same launch), then — only when the context
-// spans several GPUs — one ncclAllReduce of the (Q+1)-double partial buffer over NVLink, then one small
-// device->pinned-host copy.  The reference does the same sum as `rdd.aggregate` on the Spark driver
-// (spark-apps/.../SparkDataSetConverter.scala:42-45).
+// per-block partials are folded by the last block of the same launch).  That block also sums the result
+// across the GPUs / ranks over NVLink peer memory and writes the total into mapped pinned host memory
+// (so_finish, so_device.cuh): no collective launch, no device->host copy, no stream synchronisation.
+// Only results above kMailCap doubles take ncclAllReduce + a copy.  The reference does the same sum as
+// `rdd.aggregate` on the Spark driver (spark-apps/.../SparkDataSetConverter.scala:42-45).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <fcntl.h>
