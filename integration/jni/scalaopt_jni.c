@@ -1,6 +1,7 @@
 /*
  * scalaopt_jni.c — JNI glue between com.github.bruneli.scalaopt.gpu.NativeLib and libscalaopt_cuda.so.
- * Compiled only where a JDK is present (this image has none): UNVERIFIED.
+ * Compiled only where a JDK is present (this image has none); type-checked against include/scalaopt_cuda.h with a stand-in
+ * <jni.h> by tests/test_abi.py, never run.
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include scalaopt_jni.c \
  *       -L../../scalaopt_b200 -lscalaopt_cuda -o libscalaopt_jni.so
  */
@@ -58,74 +59,78 @@ JNIEXPORT jint JNICALL JFN(datasetRead)(JNIEnv* e, jobject o, jlong ds, jlong b,
 JNIEXPORT jlong JNICALL JFN(datasetSize)(JNIEnv* e, jobject o, jlong ds) {
   int64_t m = -1; so_dataset_size((so_dataset*)(intptr_t)ds, &m); return m;
 }
+/* Evaluations: parameter vectors and results are a few doubles (n, n*n + n + 1, 2k, ...), so Get/ReleaseDoubleArrayElements —
+ * which may copy — costs nothing against a pass over the data, and unlike GetPrimitiveArrayCritical it may be held across a
+ * blocking call: so_eval_* blocks for the duration of the kernel (milliseconds to seconds, and in a multi-rank context until
+ * the slowest rank has posted its sums), which must not happen inside a JNI critical section (the GC would be held off). */
 JNIEXPORT void JNICALL JFN(datasetFree)(JNIEnv* e, jobject o, jlong ds) { so_dataset_free((so_dataset*)(intptr_t)ds); }
 JNIEXPORT jint JNICALL JFN(evalLossGrad)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray out, jboolean g) {
   jsize n = (*e)->GetArrayLength(e, p);
-  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
-  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  double* pp = (*e)->GetDoubleArrayElements(e, p, 0);
+  double* po = (*e)->GetDoubleArrayElements(e, out, 0);
   int rc = so_eval_loss_grad((so_dataset*)(intptr_t)ds, fam, pp, n, po, g ? po + 1 : 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, out, po, 0);
+  (*e)->ReleaseDoubleArrayElements(e, p, pp, JNI_ABORT);
   return rc;
 }
 JNIEXPORT jint JNICALL JFN(evalNormalEq)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray out) {
   jsize n = (*e)->GetArrayLength(e, p);
-  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
-  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  double* pp = (*e)->GetDoubleArrayElements(e, p, 0);
+  double* po = (*e)->GetDoubleArrayElements(e, out, 0);
   int rc = so_eval_normal_eq((so_dataset*)(intptr_t)ds, fam, pp, n, po, po + n * n, po + n * n + n);
-  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, out, po, 0);
+  (*e)->ReleaseDoubleArrayElements(e, p, pp, JNI_ABORT);
   return rc;
 }
 JNIEXPORT jint JNICALL JFN(evalLine)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray d, jdoubleArray a, jdoubleArray out) {
   jsize n = (*e)->GetArrayLength(e, p), k = (*e)->GetArrayLength(e, a);
-  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
-  double* pd = (*e)->GetPrimitiveArrayCritical(e, d, 0);
-  double* pa = (*e)->GetPrimitiveArrayCritical(e, a, 0);
-  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  double* pp = (*e)->GetDoubleArrayElements(e, p, 0);
+  double* pd = (*e)->GetDoubleArrayElements(e, d, 0);
+  double* pa = (*e)->GetDoubleArrayElements(e, a, 0);
+  double* po = (*e)->GetDoubleArrayElements(e, out, 0);
   int rc = so_eval_line((so_dataset*)(intptr_t)ds, fam, pp, pd, n, pa, k, po, po + k);
-  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, a, pa, JNI_ABORT);
-  (*e)->ReleasePrimitiveArrayCritical(e, d, pd, JNI_ABORT);
-  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, out, po, 0);
+  (*e)->ReleaseDoubleArrayElements(e, a, pa, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, d, pd, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, p, pp, JNI_ABORT);
   return rc;
 }
 JNIEXPORT jint JNICALL JFN(evalHessVec)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray d, jdoubleArray out) {
   jsize n = (*e)->GetArrayLength(e, p);
-  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
-  double* pd = (*e)->GetPrimitiveArrayCritical(e, d, 0);
-  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  double* pp = (*e)->GetDoubleArrayElements(e, p, 0);
+  double* pd = (*e)->GetDoubleArrayElements(e, d, 0);
+  double* po = (*e)->GetDoubleArrayElements(e, out, 0);
   int rc = so_eval_hess_vec((so_dataset*)(intptr_t)ds, fam, pp, pd, n, po);
-  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, d, pd, JNI_ABORT);
-  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, out, po, 0);
+  (*e)->ReleaseDoubleArrayElements(e, d, pd, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, p, pp, JNI_ABORT);
   return rc;
 }
 JNIEXPORT jint JNICALL JFN(datasetGenerate)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jlong seed, jdouble sigma, jlong off) {
   jsize n = (*e)->GetArrayLength(e, p);
-  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
+  double* pp = (*e)->GetDoubleArrayElements(e, p, 0);
   int rc = so_dataset_generate((so_dataset*)(intptr_t)ds, fam, pp, n, (uint64_t)seed, sigma, off);
-  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, p, pp, JNI_ABORT);
   return rc;
 }
 JNIEXPORT jint JNICALL JFN(evalQr)(JNIEnv* e, jobject o, jlong ds, jint fam, jdoubleArray p, jdoubleArray out) {
   jsize n = (*e)->GetArrayLength(e, p);                  /* out: (n+1)*(n+1) doubles, the R factor of [J | r] */
-  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
-  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  double* pp = (*e)->GetDoubleArrayElements(e, p, 0);
+  double* po = (*e)->GetDoubleArrayElements(e, out, 0);
   int rc = so_eval_qr((so_dataset*)(intptr_t)ds, fam, pp, n, po);
-  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, out, po, 0);
+  (*e)->ReleaseDoubleArrayElements(e, p, pp, JNI_ABORT);
   return rc;
 }
 JNIEXPORT jint JNICALL JFN(evalNll)(JNIEnv* e, jobject o, jlong ds, jint pdf, jdoubleArray p, jdoubleArray consts, jdoubleArray out) {
   jsize n = (*e)->GetArrayLength(e, p), nc = (*e)->GetArrayLength(e, consts);
-  double* pp = (*e)->GetPrimitiveArrayCritical(e, p, 0);
-  double* pc = (*e)->GetPrimitiveArrayCritical(e, consts, 0);
-  double* po = (*e)->GetPrimitiveArrayCritical(e, out, 0);
+  double* pp = (*e)->GetDoubleArrayElements(e, p, 0);
+  double* pc = (*e)->GetDoubleArrayElements(e, consts, 0);
+  double* po = (*e)->GetDoubleArrayElements(e, out, 0);
   int rc = so_eval_nll((so_dataset*)(intptr_t)ds, pdf, pp, n, pc, nc, po);
-  (*e)->ReleasePrimitiveArrayCritical(e, out, po, 0);
-  (*e)->ReleasePrimitiveArrayCritical(e, consts, pc, JNI_ABORT);
-  (*e)->ReleasePrimitiveArrayCritical(e, p, pp, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, out, po, 0);
+  (*e)->ReleaseDoubleArrayElements(e, consts, pc, JNI_ABORT);
+  (*e)->ReleaseDoubleArrayElements(e, p, pp, JNI_ABORT);
   return rc;
 }
 JNIEXPORT jint JNICALL JFN(datasetLoadRaw)(JNIEnv* e, jobject o, jlong ds, jstring xPath, jstring yPath, jlong rows, jlong fileRowOffset) {
