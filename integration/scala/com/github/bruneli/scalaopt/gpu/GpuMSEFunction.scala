@@ -46,7 +46,7 @@ case class GpuMSEFunction(family: Int, gpuData: GpuDataSet, useTsqr: Boolean = f
   private var trialsSinceJacobian = 0
   private var specP: Array[Double] = Array.empty         // trial point whose K2 / TSQR sums are kept
   private var specSystem: Array[Double] = Array.empty
-  private var lossMemo = Map.empty[Seq[Double], Double]
+  private var lossMemo = scala.collection.immutable.ListMap.empty[Seq[Double], Double]   // insertion-ordered: takeRight keeps the newest
 
   private def lossGrad(p: UnconstrainedVariablesType): Array[Double] = {
     val x = raw(p)
