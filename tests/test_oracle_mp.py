@@ -198,3 +198,18 @@ def test_network_gradient_against_50_digit_differentiation(oracle, sizes, cross_
     Lg = objective(True)
     grad_ref = [float(_partial(Lg, wm, j)) for j in range(n)]
     assert _rel(grad_o, grad_ref) < 1e-13
+
+
+def test_negative_log_likelihood_against_50_digit_arithmetic(oracle):
+    """sum_i -2 log pdf(p, x_i) (stats/package.scala:97-103) for the example's pdf (ExSignalPlusBackgroundFit.scala:78-114:
+    fSig N(mu, sigma) + (1 - fSig) lambda exp(-lambda (x - xMin))) on the example's own 2000 variates."""
+    mp.mp.dps = 50
+    x = oracle.nll_example_data()
+    for p in ([0.3, 125.0, 10.0, 0.05], [0.05, 125.0, 10.0, 1.0 / 15.0]):
+        fs, mu, sg, lam = [mp.mpf(v) for v in p]
+        ref = mp.mpf(0)
+        for v in x:
+            t = mp.mpf(float(v))
+            ref += -2 * mp.log(fs * mp.exp(-((t - mu) / sg) ** 2 / 2) / (mp.sqrt(2 * mp.pi) * sg) + (1 - fs) * lam * mp.exp(-lam * (t - 50)))
+        got = oracle.nll(oracle.PDF_GAUSS_EXPBKG, x, p, [50.0])
+        assert abs(got - float(ref)) <= 1e-13 * abs(float(ref))
