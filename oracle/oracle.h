@@ -6,10 +6,13 @@
  *
  * Parity status: the reference is pure Scala and there is no JVM in this image or on the GPU box, so
  * the reference cannot be executed.  This restatement is pinned against the reference's own golden
- * vectors where they exist (QRSpec.scala:66-71,120-125 via orc_qr; java.util.Random(12345) first draw;
- * LevenbergMarquardtSpec / BFGSSpec / FFNeuralNetworkTrainerSpec recoveries through oracle/pyref).
+ * vectors and known-answer tests where they exist (QRSpec.scala:33-43,66-71,120-125 via orc_qr, both pivoting
+ * modes; java.util.Random(12345) draws; LinearSpec.scala:32-54; the LevenbergMarquardtSpec / BFGSSpec /
+ * NewtonCGSpec / FFNeuralNetworkTrainerSpec / NelderMeadSpec recoveries with their iteration counts, driven through
+ * the restated optimizers — tests/test_oracle.py, tests/test_host.py).
  * No reference test pins loss/gradient/JtJ/Hv to better than 1e-5; beyond that the parity target is
- * this file's line-by-line restatement.
+ * this file's line-by-line restatement, whose hand-derived derivative formulas are in turn checked
+ * against independent 50-digit numerical differentiation of the models' definitions (tests/test_oracle_mp.py, 1e-13).
  *
  * All paths below are relative to /root/reference; core/... = core/src/main/scala/com/github/bruneli/scalaopt/core/...
  */
