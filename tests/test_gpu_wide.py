@@ -24,6 +24,8 @@ CASES = [
     # 5 units per lane (17-20, 33-40, 65-80, 129-160 units per row), even and odd f; thread-per-row up to n = 12
     ("LINEAR", 35), ("LINEAR_NOINT", 40), ("LINEAR_NOINT", 72), ("LOGISTIC", 79), ("LINEAR", 150), ("LINEAR_NOINT", 157),
     ("LINEAR_NOINT", 300), ("LINEAR", 319), ("LINEAR", 9), ("LINEAR_NOINT", 12), ("LOGISTIC", 11),
+    # 2 lanes per row (5-8 units, register prefetch): what is left of it above the thread-per-row range, n = 13 .. 17
+    ("LINEAR", 12), ("LINEAR_NOINT", 13), ("LOGISTIC", 14), ("LINEAR", 15), ("LINEAR_NOINT", 16),
 ]
 
 
@@ -87,7 +89,7 @@ def test_normal_equations_match_oracle(native, oracle, gpu_ctx, name, f, m):
     ds.free()
 
 
-@pytest.mark.parametrize("name,f", [("LINEAR", 9), ("LINEAR_NOINT", 31), ("LOGISTIC", 33), ("LINEAR", 127), ("LINEAR_NOINT", 255)])
+@pytest.mark.parametrize("name,f", [("LINEAR", 9), ("LINEAR_NOINT", 13), ("LINEAR_NOINT", 31), ("LOGISTIC", 33), ("LINEAR", 127), ("LINEAR_NOINT", 255)])
 def test_odd_row_lengths_on_views_at_any_offset(native, oracle, gpu_ctx, name, f):
     """f odd: the kernels stream a row as (f + 1)/2 aligned 16-byte units, i.e. one element of a NEIGHBOUR row travels with it
     (so_wide.cu, ODD).  Views that start on odd rows (misaligned base), end on either parity, and are followed by a row of
