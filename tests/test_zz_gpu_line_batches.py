@@ -1,0 +1,61 @@
+"""K3 (`so_eval_line`) at every batch size.  The single-input families have one kernel instantiation per k = 1..8
+(OpLine<Fam, KB> in so_scalar.cu) and longer schedules take ceil(k/8) passes; the parity cases elsewhere use k = 2..5
+(and 1, 2, 5, 11 for the linear-predictor families), so k = 1, 6, 7, 8 and the multi-pass split of these families are
+covered here.  Sorted last on purpose: this file was added after the round's GPU minutes were spent, its first run on
+a B200 is the driver's."""
+import numpy as np
+import pytest
+
+from parity import assert_vec
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("EXPDECAY", [2.0, -1.3], 0.1),
+    ("GAUSS", [2.0, 0.5, 0.05], 0.05),
+    ("GAUSS_EXPBKG", [2.0, 0.5, 0.05, 1.0, 3.0], 0.05),   # BASELINE config 3
+    ("POLY", [1.0, -2.0, 0.5, 3.0], 0.1),
+]
+SCHEDULE = [0.0, 1.0, 2.0, 4.0, 0.37, 0.5, 3.0, 1.5, 0.1, 2.5, 0.75, 3.5, 0.25]
+
+
+@pytest.mark.parametrize("name,truth,sigma", CASES)
+@pytest.mark.parametrize("k", [1, 6, 7, 8, 9, 13])
+def test_line_scores_at_every_batch_size(native, oracle, gpu_ctx, name, truth, sigma, k):
+    fam = getattr(oracle, name)
+    m = 100_003
+    X, y = oracle.generate(fam, m, 1, truth, noise_sigma=sigma)
+    ds = native.Dataset(gpu_ctx, m, 1).append(X, y)
+    p = np.array(truth) * 1.05 + 0.01
+    _, grad = ds.loss_grad(fam, p)
+    d = -0.02 * np.abs(p) * np.sign(grad)                  # a descent direction that moves every parameter by <= 8 % at alpha = 4
+    alphas = SCHEDULE[:k]
+    phi, dphi = ds.line(fam, p, d, alphas)
+    phi_o, dphi_o = oracle.line(fam, X, y, p, d, alphas)
+    assert_vec(phi, phi_o, what=f"phi k={k}")
+    assert_vec(dphi, dphi_o, rtol=1e-11, what=f"dphi k={k}")
+    # the batch is the same function of each step size as a pass of its own
+    for j in sorted({0, k - 1}):
+        phi1, dphi1 = ds.line(fam, p, d, [alphas[j]])
+        assert_vec([phi[j]], phi1, what=f"phi[{j}] vs single")
+        assert_vec([dphi[j]], dphi1, rtol=1e-11, what=f"dphi[{j}] vs single")
+    ds.free()
+
+
+@pytest.mark.parametrize("name,f", [("LINEAR", 3), ("LOGISTIC", 7), ("LINEAR", 12), ("LINEAR_NOINT", 32), ("LOGISTIC", 33)])
+@pytest.mark.parametrize("k", [6, 7, 8])
+def test_line_scores_of_the_linear_predictor_families_at_6_to_8_step_sizes(native, oracle, gpu_ctx, name, f, k):
+    fam = getattr(oracle, name)
+    n = f + (0 if name == "LINEAR_NOINT" else 1)
+    truth = np.array([(((j % 7) - 3) / 4.0) for j in range(n)])
+    m = 20_001
+    X, y = oracle.generate(fam, m, f, truth)
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    p = truth * 0.9 + 0.05
+    d = 0.02 * np.cos(np.arange(n))
+    alphas = SCHEDULE[:k]
+    phi, dphi = ds.line(fam, p, d, alphas)
+    phi_o, dphi_o = oracle.line(fam, X, y, p, d, alphas)
+    assert_vec(phi, phi_o, what=f"phi k={k}")
+    assert_vec(dphi, dphi_o, rtol=1e-11, what=f"dphi k={k}")
+    ds.free()
