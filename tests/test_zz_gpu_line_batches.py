@@ -1,12 +1,13 @@
 """K3 (`so_eval_line`) at every batch size.  The single-input families have one kernel instantiation per k = 1..8
 (OpLine<Fam, KB> in so_scalar.cu) and longer schedules take ceil(k/8) passes; the parity cases elsewhere use k = 2..5
 (and 1, 2, 5, 11 for the linear-predictor families), so k = 1, 6, 7, 8 and the multi-pass split of these families are
-covered here.  Sorted last on purpose: this file was added after the round's GPU minutes were spent, its first run on
-a B200 is the driver's."""
+covered here; so are the Gram widths T = ceil(f/8) = 10, 11, 12 of k_gram_ph (f = 73..96) and the logistic family at
+T = 13, the largest shared-memory footprint of that kernel (229 184 of 232 448 bytes).  Sorted last on purpose: this
+file was added after the round's GPU minutes were spent, its first run on a B200 is the driver's."""
 import numpy as np
 import pytest
 
-from parity import assert_vec
+from parity import assert_gram, assert_loss, assert_vec
 
 pytestmark = pytest.mark.gpu
 
@@ -58,4 +59,26 @@ def test_line_scores_of_the_linear_predictor_families_at_6_to_8_step_sizes(nativ
     phi_o, dphi_o = oracle.line(fam, X, y, p, d, alphas)
     assert_vec(phi, phi_o, what=f"phi k={k}")
     assert_vec(dphi, dphi_o, rtol=1e-11, what=f"dphi k={k}")
+    ds.free()
+
+
+@pytest.mark.parametrize("name,f", [("LINEAR_NOINT", 80), ("LINEAR", 88), ("LINEAR_NOINT", 96), ("LINEAR", 95), ("LOGISTIC", 96),
+                                    ("LOGISTIC", 104), ("LOGISTIC", 79)])
+@pytest.mark.parametrize("m", [6_001, 5])
+def test_normal_equations_at_the_remaining_tile_counts(native, oracle, gpu_ctx, name, f, m):
+    fam = getattr(oracle, name)
+    n = f + (0 if name == "LINEAR_NOINT" else 1)
+    truth = np.array([(((j % 7) - 3) / 4.0) for j in range(n)])
+    X, y = oracle.generate(fam, m, f, truth)
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    p = truth * 0.9 + 0.05
+    JtJ, Jtr, rtr = ds.normal_eq(fam, p)
+    JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p)
+    if name == "LOGISTIC":       # (x * error) / residual with error == residual in the reference: 1-ulp noise per entry
+        np.testing.assert_allclose(JtJ, JtJ_o, rtol=1e-11, atol=1e-11 * np.abs(JtJ_o).max())
+        assert np.array_equal(JtJ, JtJ.T)
+    else:
+        assert_gram(JtJ, JtJ_o)
+    assert_vec(Jtr, Jtr_o, what="Jtr")
+    assert_loss(rtr, rtr_o)
     ds.free()
