@@ -2,7 +2,8 @@
 (OpLine<Fam, KB> in so_scalar.cu) and longer schedules take ceil(k/8) passes; the parity cases elsewhere use k = 2..5
 (and 1, 2, 5, 11 for the linear-predictor families), so k = 1, 6, 7, 8 and the multi-pass split of these families are
 covered here; so are the Gram widths T = ceil(f/8) = 10, 11, 12 of k_gram_ph (f = 73..96) and the logistic family at
-T = 13, the largest shared-memory footprint of that kernel (229 184 of 232 448 bytes).  Sorted last on purpose: this
+T = 13, the largest shared-memory footprint of that kernel (229 184 of 232 448 bytes), and K1 / K3 / K4 on odd rows with 8
+lanes x 4 units (f = 41..63 odd), which only smoke() reached.  Sorted last on purpose: this
 file was added after the round's GPU minutes were spent, its first run on a B200 is the driver's."""
 import numpy as np
 import pytest
@@ -81,4 +82,26 @@ def test_normal_equations_at_the_remaining_tile_counts(native, oracle, gpu_ctx, 
         assert_gram(JtJ, JtJ_o)
     assert_vec(Jtr, Jtr_o, what="Jtr")
     assert_loss(rtr, rtr_o)
+    ds.free()
+
+
+@pytest.mark.parametrize("name,f", [("LINEAR", 47), ("LOGISTIC", 63), ("LINEAR_NOINT", 41)])
+def test_odd_rows_on_the_8_lane_mapping(native, oracle, gpu_ctx, name, f):
+    fam = getattr(oracle, name)
+    n = f + (0 if name == "LINEAR_NOINT" else 1)
+    truth = np.array([(((j % 7) - 3) / 4.0) for j in range(n)])
+    m = 20_001
+    X, y = oracle.generate(fam, m, f, truth)
+    ds = native.Dataset(gpu_ctx, m, f).append(X, y)
+    p = truth * 0.9 + 0.05
+    loss, grad = ds.loss_grad(fam, p)
+    assert_loss(loss, oracle.apply(fam, X, y, p))
+    assert_vec(grad, oracle.gradient(fam, X, y, p))
+    d = 0.02 * np.cos(np.arange(n))
+    for alphas in ([0.5], [0.0, 1.0, 2.0], SCHEDULE[:8]):
+        phi, dphi = ds.line(fam, p, d, alphas)
+        phi_o, dphi_o = oracle.line(fam, X, y, p, d, alphas)
+        assert_vec(phi, phi_o, what=f"phi k={len(alphas)}")
+        assert_vec(dphi, dphi_o, rtol=1e-11, what=f"dphi k={len(alphas)}")
+    assert_vec(ds.hess_vec(fam, p, d), oracle.hess_vec(fam, X, y, p, d), rtol=1e-11, what="Hd")
     ds.free()
