@@ -64,3 +64,26 @@ def test_sharded_wide_family(native, oracle, G):
         assert_loss(loss, oracle.apply(fam, X, y, p))
         assert_vec(grad, oracle.gradient(fam, X, y, p))
         ds.free()
+
+
+@pytest.mark.parametrize("G", [2, 8])
+@pytest.mark.parametrize("f", [128, 256])
+def test_sharded_wide_gram(native, oracle, G, f):
+    """K2 with f > 104 (k_gram_ws: every block emits a slice of the result, so the cross-GPU sum is the separate k_finish
+    launch): f = 128 -> 8 385 sums, through the peer mailboxes; f = 256 -> 33 153 sums, above the mailbox capacity, through
+    ncclAllReduce.  Not run on a multi-GPU box before the round ended (written after the GPU minutes were spent); the same
+    two routes with smaller results are covered by the cases above and by test_gpu_rank.py."""
+    if _ngpus() < G:
+        pytest.skip(f"needs {G} GPUs")
+    fam = oracle.LINEAR_NOINT
+    truth = np.arange(1, f + 1, dtype=float) / f
+    m = 4_001
+    X, y = oracle.generate(fam, m, f, truth)
+    with native.Context(G) as ctx:
+        ds = native.Dataset(ctx, m, f).append(X, y)
+        p = truth * 0.9 + 0.05
+        JtJ, Jtr, rtr = ds.normal_eq(fam, p)
+        assert ctx.stats().finished_on_device == (1 if f == 128 else 0)
+        JtJ_o, Jtr_o, rtr_o = oracle.normal_eq(fam, X, y, p)
+        assert_gram(JtJ, JtJ_o); assert_vec(Jtr, Jtr_o, what="Jtr"); assert_loss(rtr, rtr_o)
+        ds.free()
