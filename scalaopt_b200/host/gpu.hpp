@@ -324,6 +324,16 @@ class GpuMSEFunction : public MSEFunction {
     std::vector<double> phi(al.size()), dphi(al.size());
     check(so_eval_line(data->ds, family, ray_origin.data(), ray_d.data(), n, al.data(), (int)al.size(), phi.data(), dphi.data()));
     counters.k3_passes++;
+    if (decay > 0.0) {
+      // the device scores the data term only; the trainer's weight decay (loss |w|^2/2 decay / m, gradient w decay / m,
+      // see fused) belongs to every point of the ray as well: phi += decay |x_a|^2 / (2m), phi' += decay (x_a . d) / m
+      const double m = (double)data->size();
+      for (size_t i = 0; i < al.size(); ++i) {
+        const Vec xa = add(ray_origin, mul(ray_d, al[i]));
+        phi[i] += decay_loss(xa);
+        dphi[i] += decay * dot(xa, ray_d) / m;
+      }
+    }
     for (size_t i = 0; i < al.size(); ++i) line.push_back(LineEntry{al[i], phi[i], dphi[i]});
     ray_trials++;
     return line[line.size() - al.size()];

@@ -105,3 +105,33 @@ def test_odd_rows_on_the_8_lane_mapping(native, oracle, gpu_ctx, name, f):
         assert_vec(dphi, dphi_o, rtol=1e-11, what=f"dphi k={len(alphas)}")
     assert_vec(ds.hess_vec(fam, p, d), oracle.hess_vec(fam, X, y, p, d), rtol=1e-11, what="Hd")
     ds.free()
+
+
+@pytest.mark.parametrize("decay", [0.0, 0.05])
+def test_batched_line_scores_carry_the_weight_decay(native, oracle, gpu_ctx, decay):
+    """GpuMSEFunction scores the later trial points of a line search with K3 passes (score_ray, host/gpu.hpp).  The device
+    returns the data term; the trainer's weight decay (Trainer.scala:59-69: loss |w|^2/2 decay / m, gradient w decay / m)
+    is added on the host — on the K1 route since round 2, on the K3 route only since this test was written: phi and phi' of a
+    point on the ray must be the trainer's loss and directional derivative there, decay included."""
+    from scalaopt_b200 import host
+    sizes = (4, 5, 3)
+    n = oracle.net_nweights(sizes)
+    rng = np.random.default_rng(7)
+    lab = np.repeat(np.arange(3), 40)
+    X = rng.standard_normal((120, 4)) + lab[:, None]
+    Y = np.eye(3)[lab]
+    w0 = rng.uniform(-0.5, 0.5, n)
+    ds = native.Dataset(gpu_ctx, 120, 4, ny=3).append(X, Y)
+    f = host.Objective.gpu(gpu_ctx, ds, native.MLP_CE, n, decay=decay)
+    ref = lambda w: oracle.net_loss_grad(sizes, True, X, Y, w, decay=decay)
+    l0, g0 = ref(w0)
+    d = -g0
+    assert f(w0) == pytest.approx(l0, rel=1e-12)
+    assert f.dirder(w0, d) == pytest.approx(float(g0 @ d), rel=1e-11)            # K1 route; tells the objective the ray
+    for alpha in (0.5, 0.125):
+        w = w0 + alpha * d
+        lr, gr = ref(w)
+        assert f(w) == pytest.approx(lr, rel=1e-12)                              # K3 route: first request at this point
+        assert f.dirder(w, d) == pytest.approx(float(gr @ d), rel=1e-10)
+    assert f.counters()["k3_passes"] >= 1
+    f.free(); ds.free()
