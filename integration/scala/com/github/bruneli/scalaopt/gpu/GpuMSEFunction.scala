@@ -97,6 +97,8 @@ case class GpuMSEFunction(family: Int, gpuData: GpuDataSet, useTsqr: Boolean = f
   override def dirHessian(p: UnconstrainedVariablesType, d: UnconstrainedVariablesType): UnconstrainedVariablesType = {
     val out = new Array[Double](p.length)
     check(NativeLib.evalHessVec(gpuData.handle, family, raw(p), raw(d), out))   // K4 (exact product)
+    // the trainer's dirHessian differences gradients that contain w * decay / m: + decay * d / m
+    if (decay > 0.0) { val dd = raw(d); for (i <- out.indices) out(i) += decay * dd(i) / m }
     new UnconstrainedVariables(out)
   }
 

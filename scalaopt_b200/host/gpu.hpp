@@ -174,6 +174,8 @@ class GpuMSEFunction : public MSEFunction {
     Vec out(n);
     check(so_eval_hess_vec(data->ds, family, x.data(), d.data(), n, out.data()));
     counters.k4_passes++;
+    // the trainer's dirHessian differences gradients that contain w decay / m (Trainer.scala:64-69,76-80): + decay d / m
+    if (decay > 0.0) { const double m = (double)data->size(); for (int i = 0; i < n; ++i) out[i] += decay * d[i] / m; }
     return out;
   }
   // The (n+1)-row system with the same R, Q^T b, column norms and ||b|| (up to row signs) as the m-row

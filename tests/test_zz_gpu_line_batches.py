@@ -135,3 +135,31 @@ def test_batched_line_scores_carry_the_weight_decay(native, oracle, gpu_ctx, dec
         assert f.dirder(w, d) == pytest.approx(float(gr @ d), rel=1e-10)
     assert f.counters()["k3_passes"] >= 1
     f.free(); ds.free()
+
+
+def test_hessian_vector_product_carries_the_weight_decay(native, oracle, gpu_ctx):
+    """FFNeuralNetworkTrainer.dirHessian = (gradient(w + eps d) - gradient(w)) / eps with gradients that contain w decay / m
+    (Trainer.scala:64-69,76-80).  The device composes the data part; decay d / m is added by the host objective (it was
+    missing until this test was written).  Against the same difference of the restated trainer's gradients; the decay is
+    large here so that its term (1.3 % of max |H d| on these data) stands clear of the differencing noise (1e-8 .. 1e-6 relative)."""
+    from scalaopt_b200 import host
+    sizes, decay, eps = (4, 5, 3), 0.5, 1.0e-8
+    n = oracle.net_nweights(sizes)
+    rng = np.random.default_rng(11)
+    lab = np.repeat(np.arange(3), 40)
+    X = rng.standard_normal((120, 4)) + lab[:, None]
+    Y = np.eye(3)[lab]
+    w = rng.uniform(-0.5, 0.5, n)
+    d = rng.standard_normal(n)
+    ds = native.Dataset(gpu_ctx, 120, 4, ny=3).append(X, Y)
+    grad = lambda v, dec: oracle.net_loss_grad(sizes, True, X, Y, v, decay=dec)[1]
+    for dec in (0.0, decay):
+        f = host.Objective.gpu(gpu_ctx, ds, native.MLP_CE, n, decay=dec)
+        Hd = f.dirHessian(w, d)
+        ref = (grad(w + d * eps, dec) - grad(w, dec)) / eps
+        scale = np.abs(ref).max()
+        assert np.abs(Hd - ref).max() <= 1e-4 * scale, (dec, np.abs(Hd - ref).max() / scale)
+        f.free()
+    # the decay term itself is well above that tolerance: without it the second comparison cannot pass
+    assert decay * np.abs(d).max() / 120 > 1e-3 * np.abs((grad(w + d * eps, decay) - grad(w, decay)) / eps).max()
+    ds.free()
