@@ -1,10 +1,12 @@
-"""K3 (`so_eval_line`) at every batch size.  The single-input families have one kernel instantiation per k = 1..8
-(OpLine<Fam, KB> in so_scalar.cu) and longer schedules take ceil(k/8) passes; the parity cases elsewhere use k = 2..5
-(and 1, 2, 5, 11 for the linear-predictor families), so k = 1, 6, 7, 8 and the multi-pass split of these families are
-covered here; so are the Gram widths T = ceil(f/8) = 10, 11, 12 of k_gram_ph (f = 73..96) and the logistic family at
-T = 13, the largest shared-memory footprint of that kernel (229 184 of 232 448 bytes), and K1 / K3 / K4 on odd rows with 8
-lanes x 4 units (f = 41..63 odd), which only smoke() reached.  Sorted last on purpose: this
-file was added after the round's GPU minutes were spent, its first run on a B200 is the driver's."""
+"""GPU parity cases written after the round's GPU minutes were spent — sorted last on purpose: their first run on a B200 is
+the driver's; their logic was dry-run against an oracle-backed stand-in data set.  What they reach that no earlier case does:
+  * K3 (`so_eval_line`) of the single-input families at k = 1, 6, 7, 8 (one kernel instantiation per k = 1..8, OpLine<Fam, KB> in
+    so_scalar.cu; the other cases use k = 2..5) and the ceil(k/8)-pass split; k = 6, 7, 8 for the linear-predictor families;
+  * K2 at the tile counts T = ceil(f/8) = 10, 11, 12 of k_gram_ph (f = 73..96) and the logistic family at T = 13, the largest
+    shared-memory footprint of that kernel (229 184 of 232 448 bytes);
+  * K1 / K3 / K4 on odd rows with 8 lanes x 4 units (f = 41..63 odd), which only smoke() reached;
+  * the weight-decay terms of GpuMSEFunction on the K3 (batched line-search) route and in dirHessian — both were missing
+    until these cases were written (host/gpu.hpp)."""
 import numpy as np
 import pytest
 
