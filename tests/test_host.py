@@ -209,3 +209,32 @@ def test_nelder_mead_spec(host):
     except host.MaxIterException:
         pass
     np.testing.assert_allclose(seen[:3], [[0.0, 4.0], [0.00025, 4.0], [0.0, 0.2]])
+
+
+def test_qr_on_rank_deficient_and_badly_scaled_systems(host, oracle):
+    """QR.apply + QR.solution (linalg/QR.scala:97-114,131-250) where the spec's 3 x 3 system does not go: a zero column, a
+    duplicated column, columns scaled over 12 decades.  The two restatements (oracle.c for the parity tests, the host mirror
+    for the callers) must agree bit for bit, with and without pivoting, and a full-rank solution is LAPACK's."""
+    rng = np.random.default_rng(2024)
+    A = rng.standard_normal((60, 6))
+    b = rng.standard_normal(60)
+    cases = {"full rank": A, "zero column": np.column_stack([A[:, :3], np.zeros(60), A[:, 4:]]),
+             "duplicate column": np.column_stack([A[:, :5], A[:, 1]]),
+             "column scales 1e-6 .. 1e6": A * 10.0 ** np.linspace(-6, 6, 6)}
+    for name, M in cases.items():
+        ab = np.column_stack([M, b])
+        for piv in (False, True):
+            h, o = host.qr(ab, 6, piv), oracle.qr(ab, 6, piv)
+            np.testing.assert_array_equal(h["R"], o.Rmat(), err_msg=name)
+            np.testing.assert_array_equal(h["qtb"], o.qtb, err_msg=name)
+            np.testing.assert_array_equal(h["solution"], o.solution(), err_msg=name)
+            assert sorted(h["ipvt"]) == list(range(6))
+            # R^T R is the Gram of the (permuted) columns whatever the rank
+            P = M[:, h["ipvt"]]
+            G = P.T @ P
+            np.testing.assert_allclose(h["R"].T @ h["R"], G, rtol=0, atol=1e-9 * np.abs(G).max(), err_msg=name)
+            if name in ("full rank", "column scales 1e-6 .. 1e6"):
+                # Householder QR is invariant to column scaling, an SVD-based solver is not: solve the column-normalised system
+                sc = np.linalg.norm(M, axis=0)
+                ref = np.linalg.lstsq(M / sc, b, rcond=None)[0] / sc
+                np.testing.assert_allclose(h["solution"], ref, rtol=1e-9, atol=0, err_msg=name)
