@@ -3,9 +3,10 @@
  * Usage is unchanged:   LevenbergMarquardt.minimize(GpuMSEFunction(GaussExpBkg, gpuData), p0)
  *                       BFGS.minimize(GpuMSEFunction(Logistic, gpuData), w0)
  *                       LevenbergMarquardt.minimize(GpuMSEFunction(MlpCe, irisOnGpu, decay = 0.05), w0)
- * UNVERIFIED SOURCE (no JVM here); C++ twin: scalaopt_b200/host/gpu.hpp (compiled, tested on B200).  What the twin has
- * and this file does not: batching of the later trial points of a line search into one K3 pass (score_ray) — here every
- * LineSearchPoint is one fused K1 pass, memoised.
+ * UNVERIFIED SOURCE (no JVM here); C++ twin: scalaopt_b200/host/gpu.hpp (compiled, tested on B200), which this file follows
+ * function by function: fused K1 pass with a memo on the bit pattern of p, speculative K2 / TSQR pass at Levenberg-Marquardt
+ * trial points, and the later trial points of a StrongWolfe search scored in batches by K3 (scoreRay).  The twin keeps the last
+ * 8 evaluated points, this file the last one (+ 8 losses).
  */
 package com.github.bruneli.scalaopt.gpu
 
@@ -21,9 +22,11 @@ import com.github.bruneli.scalaopt.core.variable._
  * @param speculate Levenberg-Marquardt: score the first trial point after a Jacobian with a K2 / TSQR pass whose sums serve
  *                  the Jacobian request that follows an accepted step (one pass per iteration instead of two)
  * @param decay     FFNeuralNetworkTrainer's weight decay (std-apps/.../nnet/FFNeuralNetworkTrainer.scala:57-69,147-153)
+ * @param lineBatch step sizes scored per K3 pass once a line search needs a second trial point: the requested one and the
+ *                  continuation of the bracket schedule alpha <- c3 alpha (linesearch/StrongWolfe.scala:114)
  */
 case class GpuMSEFunction(family: Int, gpuData: GpuDataSet, useTsqr: Boolean = false, speculate: Boolean = true,
-                          decay: Double = 0.0) extends MSEFunction {
+                          decay: Double = 0.0, lineBatch: Int = 3) extends MSEFunction {
 
   override val data: DataSet[DataPoint] = gpuData
 
@@ -55,8 +58,55 @@ case class GpuMSEFunction(family: Int, gpuData: GpuDataSet, useTsqr: Boolean = f
       check(NativeLib.evalLossGrad(gpuData.handle, family, x, out, true))   // K1: one fused pass
       if (decay > 0.0) { out(0) += decayLoss(x); for (i <- x.indices) out(1 + i) += x(i) * decay / m }
       lastP = x.clone(); lastOut = out
+      if (onRayBeta(x).isDefined) rayTrials += 1
     }
     lastOut
+  }
+
+  // ---- the ray a line search walks (set by dirder): later trial points on it are scored in batches by K3 ----
+  private var rayOrigin: Array[Double] = Array.empty
+  private var rayD: Array[Double] = Array.empty
+  private var rayTrials = 0                              // distinct points evaluated on the current ray
+  private var line = Vector.empty[(Double, Double, Double)]   // (beta, phi, phi') of the points scored so far, decay included
+
+  private def dot(a: Array[Double], b: Array[Double]): Double = a.indices.map(i => a(i) * b(i)).sum
+  private def sameDir(d: Array[Double]): Boolean = rayD.nonEmpty && java.util.Arrays.equals(d, rayD)
+  private def noteRay(x: Array[Double], d: Array[Double]): Unit =
+    if (!sameDir(d)) { rayOrigin = x.clone(); rayD = d.clone(); rayTrials = 1; line = Vector.empty }
+
+  /** beta with x = origin + beta d, to a few ulp of the point's magnitude */
+  private def onRayBeta(x: Array[Double]): Option[Double] =
+    if (rayD.isEmpty || x.length != rayD.length) None
+    else {
+      val dd = dot(rayD, rayD)
+      if (!(dd > 0.0)) None
+      else {
+        val diff = x.indices.map(i => x(i) - rayOrigin(i)).toArray
+        val beta = dot(diff, rayD) / dd
+        val err = x.indices.map(i => math.abs(diff(i) - beta * rayD(i))).max
+        val scale = x.indices.map(i => math.abs(x(i)) + math.abs(beta * rayD(i))).max
+        if (err > 64.0 * 2.220446049250313e-16 * math.max(scale, 1e-300)) None else Some(beta)
+      }
+    }
+
+  private def findOnRay(x: Array[Double]): Option[(Double, Double, Double)] =
+    if (line.isEmpty) None
+    else onRayBeta(x).flatMap(beta => line.find(le => math.abs(le._1 - beta) <= 1e-12 * math.max(1.0, math.abs(beta))))
+
+  /** one K3 pass: this step size and the next lineBatch - 1 of the bracket schedule beta <- 2 beta + 1 */
+  private def scoreRay(beta: Double): (Double, Double, Double) = {
+    val al = Iterator.iterate(beta)(b => 2.0 * b + 1.0).take(if (rayTrials >= 1) lineBatch else 1).toArray
+    val out = new Array[Double](2 * al.length)           // phi[0, k), phi'[k, 2k)
+    check(NativeLib.evalLine(gpuData.handle, family, rayOrigin, rayD, al, out))
+    val entries = al.indices.map { i =>
+      // the device scores the data term; the trainer's weight decay belongs to every point of the ray as well
+      val xa = rayOrigin.indices.map(j => rayOrigin(j) + rayD(j) * al(i)).toArray
+      val (penPhi, penDphi) = if (decay > 0.0) (decayLoss(xa), decay * dot(xa, rayD) / m) else (0.0, 0.0)
+      (al(i), out(i) + penPhi, out(al.length + i) + penDphi)
+    }
+    line = line ++ entries
+    rayTrials += 1
+    entries.head
   }
 
   def apply(p: UnconstrainedVariablesType, x: InputsType): OutputsType =
@@ -71,6 +121,8 @@ case class GpuMSEFunction(family: Int, gpuData: GpuDataSet, useTsqr: Boolean = f
     val x = raw(p)
     lossMemo.get(x.toSeq) match {
       case Some(l) => l
+      case None if findOnRay(x).isDefined => findOnRay(x).get._2          // scored by an earlier K3 pass
+      case None if onRayBeta(x).isDefined => scoreRay(onRayBeta(x).get)._2
       case None =>
         val l =
           if (lossOnly && speculate && lossScale > 0.0 && trialsSinceJacobian == 0 && (useTsqr || x.length <= 16)) {
@@ -92,7 +144,14 @@ case class GpuMSEFunction(family: Int, gpuData: GpuDataSet, useTsqr: Boolean = f
   override def gradient(p: UnconstrainedVariablesType): UnconstrainedVariablesType =
     new UnconstrainedVariables(lossGrad(p).drop(1))
 
-  override def dirder(p: UnconstrainedVariablesType, d: UnconstrainedVariablesType): Double = gradient(p) dot d
+  /** gradient(p) dot d (ObjectiveFunctionWithGradient.scala:37-39); also tells the objective which ray the search walks */
+  override def dirder(p: UnconstrainedVariablesType, d: UnconstrainedVariablesType): Double = {
+    val x = raw(p)
+    val dd = raw(d)
+    if (java.util.Arrays.equals(x, lastP)) { noteRay(x, dd); dot(lastOut.drop(1), dd) }
+    else if (sameDir(dd) && findOnRay(x).isDefined) findOnRay(x).get._3
+    else { val g = lossGrad(p).drop(1); noteRay(x, dd); dot(g, dd) }
+  }
 
   override def dirHessian(p: UnconstrainedVariablesType, d: UnconstrainedVariablesType): UnconstrainedVariablesType = {
     val out = new Array[Double](p.length)
